@@ -1,0 +1,162 @@
+/* wavenet_b200.h -- C ABI of libwavenet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the two hot paths of vincentherrmann/pytorch-wavenet:
+ *   (T) the training-time dilated causal convolution stack  WaveNetModel.forward / .wavenet
+ *       (reference wavenet_model.py:125-196, wavenet_modules.py:10-39,80-127), and
+ *   (G) the Fast-WaveNet cached-queue sampling loop         WaveNetModel.generate_fast
+ *       (reference wavenet_model.py:237-315, wavenet_modules.py:42-77).
+ * The reference is pure Python on torch and has no FFI of its own; these entry points are what a binding
+ * for those Python methods calls (see INTEGRATION.md for the ctypes stub a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value, or a negative WN_E_* argument error;
+ *     nothing throws; wn_last_error_string() describes the last failure on the calling thread.
+ *   - all pointers named d_* are DEVICE pointers owned by the caller; no function allocates persistent device
+ *     memory behind the caller's back (the sampler handle owns only host-side bookkeeping).
+ *   - every launch is asynchronous on the cudaStream_t passed as `void* stream` (NULL = legacy default stream).
+ *   - "frames layout": activations are (B, L, C) fp32, C contiguous, frame t of sequence b at ((b*L+t)*C);
+ *     time is ABSOLUTE (frame L-1 is the newest sample); a layer's valid frames are [start, L) and history
+ *     left of `start` reads as zero -- this restates the reference's left zero-pad + time->batch fold
+ *     (wavenet_modules.py:24-37) without moving data.
+ */
+#ifndef WAVENET_B200_H
+#define WAVENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WN_ABI_VERSION 1
+
+#define WN_E_BADARG   (-1)   /* null pointer / non-positive size / inconsistent shapes        */
+#define WN_E_UNSUPP   (-2)   /* shape outside what the kernels cover (message says which)     */
+#define WN_E_NODEVICE (-3)   /* no sm_100 device visible                                      */
+#define WN_E_STATE    (-4)   /* sampler handle used before wn_gen_bind / after destroy        */
+
+/* ---------------------------------------------------------------- library / device */
+int         wn_version(void);
+const char* wn_last_error_string(void);
+/* sm_count, compute capability, max opt-in shared memory per block, L2 bytes of the CURRENT device */
+int         wn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin, int* l2_bytes);
+
+/* ---------------------------------------------------------------- (T) weight packing
+ * The training kernels read weights K-outer ("transposed") so a K-slab is a contiguous copy into shared
+ * memory.  Packing is device->device, asynchronous, and must be redone after the parameters change.
+ *
+ *   filter/gate  (D,R,k) x2 + biases -> wfg_t [k*R][N1p],  bfg [N1p],  N1p = wn_n1p(D)
+ *        column chunk c (128 wide): cols [0,64) = filter channels 64c.., cols [64,128) = gate channels 64c..
+ *        row j*R + r holds tap j (j = 0 is the OLDEST tap, as in nn.Conv1d weight[:,:,0]) of input channel r
+ *   residual (R,D,1) + skip (S,D,1) + biases -> wrs_t [D][N2p], brs [N2p], N2p = wn_n2p(R+S)
+ *        cols [0,R) residual outputs, [R,R+S) skip outputs
+ *   plain 1x1 (N,K,1) + bias -> w_t [K][Np], b [Np], Np = wn_n2p(N)          (end_conv_1 / end_conv_2)
+ * Bias pointers may be NULL (bias=False in the reference ctor, wavenet_model.py:39): packed bias is zero. */
+int wn_n1p(int D);
+int wn_n2p(int N);
+int wn_pack_gate_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
+                         int R, int D, int k, float* d_wfg_t, float* d_bfg, void* stream);
+int wn_pack_res_skip_weights(const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
+                             int R, int D, int S, float* d_wrs_t, float* d_brs, void* stream);
+int wn_pack_1x1_weights(const float* d_w, const float* d_b, int N, int K, float* d_w_t, float* d_b_p, void* stream);
+
+/* ---------------------------------------------------------------- (T) start conv
+ * replaces: start_conv applied to the (B,classes,L) input, wavenet_model.py:65-68,127.
+ * dense : d_x (B,classes,L) fp32 (any values; one-hot in the reference data path, audio_data.py:119-121)
+ * index : d_idx (B,L) class indices (uint8 / int64) -- equals the dense form on one-hot input bit for bit.
+ * d_w_t / d_b_p: start_conv.weight (R,classes,1) and bias packed by wn_pack_1x1_weights (N=R, K=classes), i.e.
+ * a (classes, wn_n2p(R)) table whose row c is the embedding of class c.  Output d_h (B,L,R) frames layout. */
+int wn_start_fwd_dense(const float* d_x, const float* d_w_t, const float* d_b_p, float* d_h,
+                       int B, int classes, int L, int R, void* stream);
+int wn_start_fwd_index_u8(const uint8_t* d_idx, const float* d_w_t, const float* d_b_p, float* d_h,
+                          int B, int classes, int L, int R, void* stream);
+int wn_start_fwd_index_i64(const int64_t* d_idx, const float* d_w_t, const float* d_b_p, float* d_h,
+                           int B, int classes, int L, int R, void* stream);
+
+/* ---------------------------------------------------------------- (T) one residual block, one launch
+ * replaces the loop body of WaveNetModel.wavenet, wavenet_model.py:142-165, including both dilate() calls
+ * (wavenet_modules.py:10-39) and the constant pad (:80-127):
+ *     z[t]     = tanh(sum_j Wf[:,:,j] hp[t-(k-1-j)d] + bf) * sigmoid(sum_j Wg[:,:,j] hp[t-(k-1-j)d] + bg)
+ *     h_out[t] = Wr z[t] + br + hp[t]                     for t in [out_start, L)
+ *     skip[t]  = Ws z[t] + bs (+ skip[t] unless skip_init) for t in [skip_start, L)
+ * with hp[t] = h_in[t] for t >= in_start, else 0.  d_skip is (B, L-skip_start, S) frames layout.
+ * mode: 0 = exact fp32 FFMA (any shape); other values are reserved for the tensor-core variants. */
+typedef struct wn_block_args {
+    const float* d_h_in;  float* d_h_out;  float* d_skip;
+    const float* d_wfg_t; const float* d_bfg; const float* d_wrs_t; const float* d_brs;
+    int B, L, R, D, S, k, dilation;
+    int in_start, out_start, skip_start, skip_init;
+    int mode;
+} wn_block_args;
+int wn_block_fwd(const wn_block_args* a, void* stream);
+
+/* ---------------------------------------------------------------- (T) head
+ * replaces relu -> end_conv_1 -> relu -> end_conv_2 (wavenet_model.py:167-169) and forward()'s
+ * slice/transpose/view (:191-196): logits (B*out_len, classes) for the LAST out_len frames only.
+ * d_skip is (B, L-skip_start, S); requires out_len <= L-skip_start (the reference raises on view otherwise). */
+typedef struct wn_head_args {
+    const float* d_skip; float* d_logits;
+    const float* d_w1_t; const float* d_b1; const float* d_w2_t; const float* d_b2;
+    int B, L, S, E, classes, skip_start, out_len;
+    int mode;
+} wn_head_args;
+int wn_head_fwd(const wn_head_args* a, void* stream);
+
+/* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
+ * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with
+ * DilatedQueue.enqueue/dequeue/reset (wavenet_modules.py:55-77): ONE persistent cooperative kernel runs
+ * `n_evals` network evaluations without returning to the host; the per-layer ring buffers live in d_rings.
+ *
+ * Weights are the reference's own parameter tensors, UNPACKED (state_dict layout); bias pointers may be NULL.
+ * n_streams independent streams share the weights (the reference has a single stream, wavenet_model.py:179;
+ * stream s of a multi-stream run equals a single-stream run with the same inputs bit for bit).            */
+typedef struct wn_gen_weights {
+    const float* d_start_w; const float* d_start_b;            /* (R,classes,1), (R) */
+    const float* const* d_wf; const float* const* d_bf;        /* HOST arrays [n_layers] of device pointers */
+    const float* const* d_wg; const float* const* d_bg;        /* (D,R,k), (D)   */
+    const float* const* d_wr; const float* const* d_br;        /* (R,D,1), (R)   */
+    const float* const* d_ws; const float* const* d_bs;        /* (S,D,1), (S)   */
+    const float* d_end1_w; const float* d_end1_b;              /* (E,S,1), (E)   */
+    const float* d_end2_w; const float* d_end2_b;              /* (classes,E,1)  */
+} wn_gen_weights;
+
+typedef struct wn_gen_shape {
+    int n_layers, k, R, D, S, E, classes, n_streams;
+    const int* dilations;                                      /* HOST array [n_layers] */
+} wn_gen_shape;
+
+/* bytes the caller must provide: rings (all layers, all streams) and scratch (exchange vectors, barrier) */
+int wn_gen_workspace_bytes(const wn_gen_shape* s, size_t* ring_bytes, size_t* scratch_bytes);
+
+typedef struct wn_gen_handle wn_gen_handle;
+int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, float* d_rings, void* d_scratch,
+                  wn_gen_handle** out);
+/* zero the rings and the time counter (DilatedQueue.reset, wavenet_modules.py:74-77) */
+int wn_gen_reset(wn_gen_handle* h, void* stream);
+/* Run evaluations [t0, t0+n_evals) of a schedule with n_given given samples per stream:
+ *   evaluation e takes as input  d_first[s*n_given + e]            if e <  n_given
+ *                                d_forced[s*n_samples + e-n_given] if d_forced != NULL   (teacher forcing)
+ *                                the index chosen at evaluation e-1 otherwise,
+ *   and, when e >= n_given-1, chooses sample i = e-(n_given-1): argmax of (logits - regularize*(c-classes/2)^2)
+ *   if temperature <= 0 (wavenet_model.py:290-294), else inverse-CDF sampling of softmax(./temperature) with the
+ *   float64 uniform d_uniforms[s*n_samples + i] exactly as numpy.random.choice does (wavenet_model.py:282-289).
+ *   d_out_idx (n_streams, n_samples) int32; d_out_logits optional (n_streams, n_samples, classes) fp32 holding
+ *   logits - regularizer.  t0 must continue where the previous call stopped (0 after wn_gen_reset).          */
+typedef struct wn_gen_run_args {
+    const int32_t* d_first; int n_given;
+    const int32_t* d_forced; const double* d_uniforms;
+    int32_t* d_out_idx; float* d_out_logits;
+    int n_samples;            /* row pitch of forced / uniforms / out_idx                  */
+    int t0, n_evals;
+    float temperature, regularize;
+} wn_gen_run_args;
+int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
+int wn_gen_destroy(wn_gen_handle* h);
+/* how the last wn_gen_run was launched: grid size, block size, barriers per evaluation */
+int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVENET_B200_H */

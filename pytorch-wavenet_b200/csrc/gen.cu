@@ -1,0 +1,551 @@
+// gen.cu -- Fast-WaveNet sampling as ONE persistent cooperative kernel.
+//
+// Replaces (reference file:line): WaveNetModel.generate_fast's warm-up and sampling loops wavenet_model.py:260-302,
+// queue_dilate :177-184, the layer loop :131-165 and head :167-169 evaluated on single columns, and
+// DilatedQueue.enqueue/dequeue/reset wavenet_modules.py:55-77.
+//
+// Work decomposition.  One network evaluation is a chain of matrix-vector products with a full dependency
+// between stages, so the whole GPU works on every stage and stages are separated by a grid barrier:
+//   per layer   stage 1: rows (f_c, g_c) of the k-tap conv for the CTA's dilation channels c -> z_c (exchange buffer)
+//               stage 2: rows of residual_conv (-> next layer's ring slot for time t) and of skip_conv
+//                        (-> running skip sum, kept in shared memory of the owning CTA across all layers)
+//   head        end_conv_1 rows -> end_conv_2 rows -> every CTA redundantly picks the next sample
+// Row r of a stage belongs to CTA (r mod G); one warp computes one row for all streams (lanes split K, butterfly
+// reduction), so a stream's arithmetic does not depend on how many streams run beside it.
+// The rings ("dilated queues") are the exchange medium between layers: ring l has (k-1)*d_l+1 slots of
+// [n_streams][R]; slot (t mod len) holds the layer's input at time t, unwritten slots are zero (reset).
+// Exchanged vectors are read with ld.global.cg (L2) because L1 is not coherent across SMs.
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <new>
+#include <vector>
+
+namespace wn {
+
+constexpr int GEN_NT = 256;
+constexpr int GEN_WARPS = GEN_NT / 32;
+
+struct GenLayer {
+    const float *wf, *wg, *wr, *ws, *bf, *bg, *br, *bs;
+    long long ring_off;     // in floats, from rings base
+    int dil, ring_len;
+};
+
+struct GenParams {
+    const GenLayer* layers;
+    int n_layers, k, R, D, S, E, C, NS;
+    const float *start_w, *start_b, *e1w, *e1b, *e2w, *e2b;
+    float* rings;
+    float *zbuf, *skipbuf, *y1buf, *logitbuf;
+    int* cur_idx;
+    unsigned* bar;
+    // run
+    const int* first; int n_given;
+    const int* forced; const double* uniforms;
+    int* out_idx; float* out_logits;
+    int n_samples, t0, n_evals;
+    float temperature, regularize;
+    // smem carve (floats)
+    int regA, regB, pre_n, skacc_n;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target, unsigned G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += G;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// dot products of one weight row (K floats, global) with the vectors xs[s][0..K) (shared) for streams s0..s0+SB
+template <int SB>
+__device__ __forceinline__ void row_dot(const float* __restrict__ w, const float* __restrict__ xs, int K, int NS,
+                                        int s0, int lane, float (&acc)[SB]) {
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = 0.f;
+    if ((K & 3) == 0) {
+        const float4* w4p = reinterpret_cast<const float4*>(w);
+        for (int i4 = lane; i4 < (K >> 2); i4 += 32) {
+            const float4 w4 = __ldg(w4p + i4);
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                if (s0 + j < NS) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)(s0 + j) * K + 4 * i4);
+                    float a = acc[j];
+                    a = fmaf(w4.x, x4.x, a); a = fmaf(w4.y, x4.y, a); a = fmaf(w4.z, x4.z, a); a = fmaf(w4.w, x4.w, a);
+                    acc[j] = a;
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < K; i += 32) {
+            const float wv = __ldg(w + i);
+#pragma unroll
+            for (int j = 0; j < SB; ++j)
+                if (s0 + j < NS) acc[j] = fmaf(wv, xs[(size_t)(s0 + j) * K + i], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = warp_sum(acc[j]);
+}
+
+__device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int SB>
+__global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* regA = sm;                          // stage-1 inputs [NS][k*R] / head input [NS][S]
+    float* regB = regA + p.regA;               // z [NS][D] / y1 [NS][E]
+    float* pre = regB + p.regB;                // per-item results [items][NS]
+    float* skacc = pre + p.pre_n;              // running skip sums of the rows this CTA owns [rows][NS]
+    int* idx_s = reinterpret_cast<int*>(skacc + p.skacc_n);     // current input index per stream [NS]
+    float* prob = reinterpret_cast<float*>(idx_s + p.NS);       // [GEN_WARPS][C] softmax scratch
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int NS = p.NS, R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, k = p.k;
+    const int K1 = k * R;
+    unsigned bar_target = 0;
+
+    // owned rows per stage: row r belongs to CTA (r mod G); local index r / G
+    const int nD = (D > cta) ? (D - cta + G - 1) / G : 0;
+    const int nR = (R > cta) ? (R - cta + G - 1) / G : 0;
+    const int nS = (S > cta) ? (S - cta + G - 1) / G : 0;
+    const int nE = (E > cta) ? (E - cta + G - 1) / G : 0;
+    const int nC = (C > cta) ? (C - cta + G - 1) / G : 0;
+
+    // the index chosen by the evaluation before t0 (continuation of a previous launch)
+    for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.cur_idx[s];
+    __syncthreads();
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;                           // absolute evaluation counter == time
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);              // sample number this evaluation chooses
+        // ---- input index of this evaluation
+        if (t < p.n_given) {
+            for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.first[(size_t)s * p.n_given + t];
+        } else if (p.forced != nullptr) {
+            for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.forced[(size_t)s * p.n_samples + (t - p.n_given)];
+        }
+        for (int i = tid; i < nS * NS; i += GEN_NT) skacc[i] = 0.f;
+        __syncthreads();
+
+        for (int l = 0; l < p.n_layers; ++l) {
+            const GenLayer L = p.layers[l];
+            float* ring = p.rings + L.ring_off;
+            const int slot_t = t % L.ring_len;
+            // ---- gather stage-1 inputs, interleaved like a conv weight row: regA[s][r*k + j] = tap j of channel r
+            for (int i = tid; i < NS * K1; i += GEN_NT) {
+                const int s = i / K1, rem = i - s * K1, r = rem / k, j = rem - r * k;
+                float v;
+                if (j == k - 1 && l == 0) {                 // current input of layer 0 = start conv column
+                    int c = idx_s[s];
+                    c = c < 0 ? 0 : (c >= C ? C - 1 : c);
+                    v = __ldg(p.start_w + (size_t)r * C + c) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
+                    if (r % G == cta) ring[((size_t)slot_t * NS + s) * R + r] = v;       // enqueue (owner writes)
+                } else {
+                    int tt = t - (k - 1 - j) * L.dil;        // time of tap j
+                    int slot = tt % L.ring_len;
+                    if (slot < 0) slot += L.ring_len;        // never-written slot: zero history
+                    v = __ldcg(ring + ((size_t)slot * NS + s) * R + r);
+                }
+                regA[i] = v;
+            }
+            __syncthreads();
+            // ---- stage 1: filter / gate rows of the owned dilation channels
+            for (int it = warp; it < 2 * nD; it += GEN_WARPS) {
+                const int c = (it >> 1) * G + cta;
+                const float* w = ((it & 1) ? L.wg : L.wf) + (size_t)c * K1;
+                const float* bp = (it & 1) ? L.bg : L.bf;
+                const float bias = bp ? __ldg(bp + c) : 0.f;
+                for (int s0 = 0; s0 < NS; s0 += SB) {
+                    float acc[SB];
+                    row_dot<SB>(w, regA, K1, NS, s0, lane, acc);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < SB; ++j)
+                            if (s0 + j < NS) pre[it * NS + s0 + j] = acc[j] + bias;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < nD * NS; i += GEN_NT) {
+                const int ci = i / NS, s = i - ci * NS;
+                const float z = tanhf(pre[(2 * ci) * NS + s]) * sigmoid_(pre[(2 * ci + 1) * NS + s]);
+                p.zbuf[(size_t)s * D + ci * G + cta] = z;
+            }
+            grid_barrier(p.bar, bar_target, G);
+            // ---- stage 2: residual rows (not needed after the last layer) and skip rows (not needed in warm-up)
+            for (int i = tid; i < NS * D; i += GEN_NT) regB[i] = __ldcg(p.zbuf + i);
+            __syncthreads();
+            const int nres = (l + 1 < p.n_layers) ? nR : 0;
+            const int nskp = want_head ? nS : 0;
+            for (int it = warp; it < nres + nskp; it += GEN_WARPS) {
+                const bool is_res = it < nres;
+                const int li = is_res ? it : it - nres;
+                const int row = li * G + cta;
+                const float* w = (is_res ? L.wr : L.ws) + (size_t)row * D;
+                const float* bp = is_res ? L.br : L.bs;
+                const float bias = bp ? __ldg(bp + row) : 0.f;
+                for (int s0 = 0; s0 < NS; s0 += SB) {
+                    float acc[SB];
+                    row_dot<SB>(w, regB, D, NS, s0, lane, acc);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < SB; ++j) {
+                            const int s = s0 + j;
+                            if (s >= NS) break;
+                            const float v = acc[j] + bias;
+                            if (is_res) {
+                                const GenLayer& Ln = p.layers[l + 1];
+                                const float cur = regA[(size_t)s * K1 + row * k + (k - 1)];
+                                p.rings[Ln.ring_off + ((size_t)(t % Ln.ring_len) * NS + s) * R + row] = v + cur;
+                            } else {
+                                skacc[li * NS + s] = v + skacc[li * NS + s];
+                            }
+                        }
+                    }
+                }
+            }
+            if (l + 1 == p.n_layers && want_head) {
+                __syncthreads();
+                for (int i = tid; i < nS * NS; i += GEN_NT) {
+                    const int li = i / NS, s = i - li * NS;
+                    p.skipbuf[(size_t)s * S + li * G + cta] = skacc[i];
+                }
+            }
+            grid_barrier(p.bar, bar_target, G);
+        }
+        if (!want_head) continue;
+
+        // ---- head A: y1 = relu(W1 relu(skip) + b1)
+        for (int i = tid; i < NS * S; i += GEN_NT) regA[i] = fmaxf(__ldcg(p.skipbuf + i), 0.f);
+        __syncthreads();
+        for (int it = warp; it < nE; it += GEN_WARPS) {
+            const int row = it * G + cta;
+            const float bias = __ldg(p.e1b + row);
+            for (int s0 = 0; s0 < NS; s0 += SB) {
+                float acc[SB];
+                row_dot<SB>(p.e1w + (size_t)row * S, regA, S, NS, s0, lane, acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < SB; ++j)
+                        if (s0 + j < NS) p.y1buf[(size_t)(s0 + j) * E + row] = fmaxf(acc[j] + bias, 0.f);
+                }
+            }
+        }
+        grid_barrier(p.bar, bar_target, G);
+        // ---- head B: logits = W2 y1 + b2, minus the regularizer (wavenet_model.py:273-274,280)
+        for (int i = tid; i < NS * E; i += GEN_NT) regB[i] = __ldcg(p.y1buf + i);
+        __syncthreads();
+        for (int it = warp; it < nC; it += GEN_WARPS) {
+            const int row = it * G + cta;
+            const float bias = __ldg(p.e2b + row);
+            const float dc = (float)row - (float)C / 2.f;
+            const float reg = (dc * dc) * p.regularize;
+            for (int s0 = 0; s0 < NS; s0 += SB) {
+                float acc[SB];
+                row_dot<SB>(p.e2w + (size_t)row * E, regB, E, NS, s0, lane, acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < SB; ++j) {
+                        const int s = s0 + j;
+                        if (s >= NS) break;
+                        const float v = (acc[j] + bias) - reg;
+                        p.logitbuf[(size_t)s * C + row] = v;
+                        if (p.out_logits) p.out_logits[((size_t)s * p.n_samples + samp) * C + row] = v;
+                    }
+                }
+            }
+        }
+        grid_barrier(p.bar, bar_target, G);
+        // ---- choose (every CTA redundantly, so no broadcast barrier is needed): warp per stream
+        float* pw = prob + warp * C;
+        for (int s = warp; s < NS; s += GEN_WARPS) {
+            const float* lg = p.logitbuf + (size_t)s * C;
+            int choice;
+            if (p.temperature > 0.f) {
+                float m = -INFINITY;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = __ldcg(lg + c) / p.temperature;
+                    pw[c] = x;
+                    m = fmaxf(m, x);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int c = lane; c < C; c += 32) {
+                    const float e = expf(pw[c] - m);
+                    pw[c] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                __syncwarp();
+                choice = 0;
+                if (lane == 0) {
+                    // numpy.random.choice: float64 cumulative sum, normalised by its last element, searchsorted 'right'
+                    double total = 0.0;
+                    for (int c = 0; c < C; ++c) total += (double)(pw[c] / sum);
+                    const double u = p.uniforms[(size_t)s * p.n_samples + samp];
+                    double run = 0.0;
+                    int cnt = 0;
+                    for (int c = 0; c < C; ++c) {
+                        run += (double)(pw[c] / sum);
+                        cnt += ((run / total) <= u) ? 1 : 0;
+                    }
+                    choice = cnt < C ? cnt : C - 1;
+                }
+                choice = __shfl_sync(0xffffffffu, choice, 0);
+            } else {
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = __ldcg(lg + c);
+                    if (x > best || (x == best && c < bi)) { best = x; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                choice = bi == 0x7fffffff ? 0 : bi;
+            }
+            if (lane == 0) {
+                idx_s[s] = choice;
+                if (cta == 0) p.out_idx[(size_t)s * p.n_samples + samp] = choice;
+            }
+        }
+        __syncthreads();
+    }
+    if (cta == 0)
+        for (int s = tid; s < NS; s += GEN_NT) p.cur_idx[s] = idx_s[s];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct ScratchLayout {
+    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, total;
+};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static ScratchLayout scratch_layout(const wn_gen_shape& s) {
+    ScratchLayout o;
+    size_t off = 0;
+    o.bar = off; off += 256;
+    o.cur_idx = off; off = align_up(off + sizeof(int) * s.n_streams, 256);
+    o.layers = off; off = align_up(off + sizeof(GenLayer) * s.n_layers, 256);
+    o.zbuf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.D, 256);
+    o.skipbuf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.S, 256);
+    o.y1buf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.E, 256);
+    o.logitbuf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.classes, 256);
+    o.total = off;
+    return o;
+}
+static size_t ring_floats(const wn_gen_shape& s, std::vector<long long>* offs) {
+    size_t total = 0;
+    for (int l = 0; l < s.n_layers; ++l) {
+        if (offs) offs->push_back((long long)total);
+        total += (size_t)((s.k - 1) * s.dilations[l] + 1) * s.n_streams * s.R;
+    }
+    return total;
+}
+
+}  // namespace wn
+
+using namespace wn;
+
+struct wn_gen_handle {
+    wn_gen_shape shape;
+    std::vector<int> dil;
+    std::vector<GenLayer> layers;
+    GenParams base;
+    ScratchLayout lay;
+    char* scratch;
+    size_t ring_bytes;
+    int grid, sm_count;
+    size_t smem;
+    bool tables_uploaded;
+    int cur_t;
+};
+
+static int validate_shape(const wn_gen_shape* s) {
+    WN_REQUIRE(s && s->dilations, WN_E_BADARG, "wn_gen: null shape");
+    WN_REQUIRE(s->n_layers > 0 && s->k >= 1 && s->R > 0 && s->D > 0 && s->S > 0 && s->E > 0 && s->classes > 0 &&
+                   s->n_streams > 0,
+               WN_E_BADARG, "wn_gen: bad shape");
+    for (int l = 0; l < s->n_layers; ++l) WN_REQUIRE(s->dilations[l] >= 1, WN_E_BADARG, "wn_gen: bad dilation");
+    return 0;
+}
+
+extern "C" int wn_gen_workspace_bytes(const wn_gen_shape* s, size_t* ring_bytes, size_t* scratch_bytes) {
+    if (int rc = validate_shape(s)) return rc;
+    if (ring_bytes) *ring_bytes = sizeof(float) * ring_floats(*s, nullptr);
+    if (scratch_bytes) *scratch_bytes = scratch_layout(*s).total;
+    return 0;
+}
+
+extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, float* d_rings, void* d_scratch,
+                             wn_gen_handle** out) {
+    if (int rc = validate_shape(s)) return rc;
+    WN_REQUIRE(w && d_rings && d_scratch && out, WN_E_BADARG, "wn_gen_create: null pointer");
+    WN_REQUIRE(w->d_start_w && w->d_wf && w->d_wg && w->d_wr && w->d_ws && w->d_end1_w && w->d_end1_b && w->d_end2_w &&
+                   w->d_end2_b,
+               WN_E_BADARG, "wn_gen_create: null weight pointer");
+    int dev = 0, sms = 0, smem_optin = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    WN_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+    wn_gen_handle* h = new (std::nothrow) wn_gen_handle();
+    WN_REQUIRE(h, WN_E_BADARG, "wn_gen_create: out of host memory");
+    h->shape = *s;
+    h->dil.assign(s->dilations, s->dilations + s->n_layers);
+    h->shape.dilations = h->dil.data();
+    h->lay = scratch_layout(h->shape);
+    h->scratch = (char*)d_scratch;
+    std::vector<long long> offs;
+    h->ring_bytes = sizeof(float) * ring_floats(h->shape, &offs);
+    h->layers.resize(s->n_layers);
+    for (int l = 0; l < s->n_layers; ++l) {
+        GenLayer& L = h->layers[l];
+        L.wf = w->d_wf[l]; L.wg = w->d_wg[l]; L.wr = w->d_wr[l]; L.ws = w->d_ws[l];
+        L.bf = w->d_bf ? w->d_bf[l] : nullptr; L.bg = w->d_bg ? w->d_bg[l] : nullptr;
+        L.br = w->d_br ? w->d_br[l] : nullptr; L.bs = w->d_bs ? w->d_bs[l] : nullptr;
+        if (!(L.wf && L.wg && L.wr && L.ws)) {
+            delete h;
+            return set_err(WN_E_BADARG, "wn_gen_create: null weight pointer in layer %d", l);
+        }
+        L.ring_off = offs[l];
+        L.dil = s->dilations[l];
+        L.ring_len = (s->k - 1) * s->dilations[l] + 1;
+    }
+    GenParams& p = h->base;
+    p.layers = reinterpret_cast<const GenLayer*>(h->scratch + h->lay.layers);
+    p.n_layers = s->n_layers; p.k = s->k; p.R = s->R; p.D = s->D; p.S = s->S; p.E = s->E; p.C = s->classes;
+    p.NS = s->n_streams;
+    p.start_w = w->d_start_w; p.start_b = w->d_start_b;
+    p.e1w = w->d_end1_w; p.e1b = w->d_end1_b; p.e2w = w->d_end2_w; p.e2b = w->d_end2_b;
+    p.rings = d_rings;
+    p.zbuf = reinterpret_cast<float*>(h->scratch + h->lay.zbuf);
+    p.skipbuf = reinterpret_cast<float*>(h->scratch + h->lay.skipbuf);
+    p.y1buf = reinterpret_cast<float*>(h->scratch + h->lay.y1buf);
+    p.logitbuf = reinterpret_cast<float*>(h->scratch + h->lay.logitbuf);
+    p.cur_idx = reinterpret_cast<int*>(h->scratch + h->lay.cur_idx);
+    p.bar = reinterpret_cast<unsigned*>(h->scratch + h->lay.bar);
+
+    // grid: as many CTAs as keep the per-stage row count per CTA minimal, at most one per SM
+    const int rows_max = s->D;
+    const int per = ceil_div(rows_max, sms);
+    int G = ceil_div(rows_max, per);
+    if (G > sms) G = sms;
+    if (G < 1) G = 1;
+    h->grid = G;
+    h->sm_count = sms;
+    const int NS = s->n_streams;
+    auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+    const int mx1 = (s->k * s->R > s->S) ? s->k * s->R : s->S;
+    const int mx2 = (s->D > s->E) ? s->D : s->E;
+    p.regA = NS * mx1;
+    p.regB = NS * mx2;
+    int items = 2 * cdiv(s->D, G);
+    p.pre_n = items * NS;
+    p.skacc_n = cdiv(s->S, G) * NS;
+    if (p.skacc_n < 4) p.skacc_n = 4;
+    p.regA = (p.regA + 3) / 4 * 4; p.regB = (p.regB + 3) / 4 * 4; p.pre_n = (p.pre_n + 3) / 4 * 4;
+    p.skacc_n = (p.skacc_n + 3) / 4 * 4;
+    h->smem = sizeof(float) * ((size_t)p.regA + p.regB + p.pre_n + p.skacc_n + NS + (size_t)GEN_WARPS * s->classes);
+    if (h->smem > (size_t)smem_optin) {
+        const size_t need = h->smem;
+        delete h;
+        return set_err(WN_E_UNSUPP, "wn_gen_create: %zu bytes of shared memory needed for %d streams, %d available", need,
+                       NS, smem_optin);
+    }
+    h->tables_uploaded = false;
+    h->cur_t = 0;
+    *out = h;
+    return 0;
+}
+
+extern "C" int wn_gen_reset(wn_gen_handle* h, void* stream) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_reset: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    WN_CUDA(cudaMemsetAsync(h->base.rings, 0, h->ring_bytes, st));
+    WN_CUDA(cudaMemsetAsync(h->scratch + h->lay.cur_idx, 0, sizeof(int) * h->shape.n_streams, st));
+    if (!h->tables_uploaded) {
+        WN_CUDA(cudaMemcpyAsync(h->scratch + h->lay.layers, h->layers.data(), sizeof(GenLayer) * h->layers.size(),
+                                cudaMemcpyHostToDevice, st));
+        WN_CUDA(cudaStreamSynchronize(st));       // h->layers is pageable host memory owned by the handle
+        h->tables_uploaded = true;
+    }
+    h->cur_t = 0;
+    return 0;
+}
+
+template <int SB>
+static int launch_gen(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    int per_sm = 0;
+    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel<SB>, GEN_NT, h->smem));
+    WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
+    void* args[] = {(void*)&p};
+    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel<SB>, dim3(h->grid), dim3(GEN_NT), args, h->smem, st));
+    return 0;
+}
+
+extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_run: null handle");
+    WN_REQUIRE(h->tables_uploaded, WN_E_STATE, "wn_gen_run: call wn_gen_reset first");
+    WN_REQUIRE(a && a->d_first && a->d_out_idx, WN_E_BADARG, "wn_gen_run: null pointer");
+    WN_REQUIRE(a->n_given >= 1 && a->n_samples >= 0 && a->n_evals >= 0 && a->t0 >= 0, WN_E_BADARG, "wn_gen_run: bad counts");
+    WN_REQUIRE(a->t0 == h->cur_t, WN_E_STATE, "wn_gen_run: t0=%d does not continue the previous call (expected %d)", a->t0,
+               h->cur_t);
+    WN_REQUIRE(a->t0 + a->n_evals <= a->n_given - 1 + a->n_samples, WN_E_BADARG,
+               "wn_gen_run: evaluations [%d,%d) exceed the schedule of %d given + %d samples", a->t0, a->t0 + a->n_evals,
+               a->n_given, a->n_samples);
+    WN_REQUIRE(!(a->temperature > 0.f) || a->d_uniforms, WN_E_BADARG, "wn_gen_run: temperature > 0 needs d_uniforms");
+    if (a->n_evals == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bars_per_eval = 2 * h->shape.n_layers + 2;
+    int done = 0;
+    while (done < a->n_evals) {
+        // keep the barrier counter below 2^31: chunk very long runs
+        long long max_evals = (long long)0x7fffffff / ((long long)bars_per_eval * h->grid);
+        int n = a->n_evals - done;
+        if ((long long)n > max_evals) n = (int)max_evals;
+        GenParams p = h->base;
+        p.first = a->d_first; p.n_given = a->n_given; p.forced = a->d_forced; p.uniforms = a->d_uniforms;
+        p.out_idx = a->d_out_idx; p.out_logits = a->d_out_logits; p.n_samples = a->n_samples;
+        p.t0 = a->t0 + done; p.n_evals = n; p.temperature = a->temperature; p.regularize = a->regularize;
+        WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
+        int rc = (h->shape.n_streams == 1) ? launch_gen<1>(h, p, st) : launch_gen<8>(h, p, st);
+        if (rc) return rc;
+        done += n;
+    }
+    h->cur_t = a->t0 + a->n_evals;
+    return 0;
+}
+
+extern "C" int wn_gen_destroy(wn_gen_handle* h) {
+    delete h;
+    return 0;
+}
+
+extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_launch_info: null handle");
+    if (grid) *grid = h->grid;
+    if (block) *block = GEN_NT;
+    if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;
+    return 0;
+}

@@ -1,0 +1,122 @@
+"""ctypes binding of libwavenet_b200.so (the C ABI declared in include/wavenet_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+Build the library with ``make -C pytorch-wavenet_b200/csrc`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwavenet_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class BlockArgs(C.Structure):
+    _fields_ = [("d_h_in", C.c_void_p), ("d_h_out", C.c_void_p), ("d_skip", C.c_void_p),
+                ("d_wfg_t", C.c_void_p), ("d_bfg", C.c_void_p), ("d_wrs_t", C.c_void_p), ("d_brs", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("k", C.c_int),
+                ("dilation", C.c_int), ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int),
+                ("skip_init", C.c_int), ("mode", C.c_int)]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("d_skip", C.c_void_p), ("d_logits", C.c_void_p),
+                ("d_w1_t", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2_t", C.c_void_p), ("d_b2", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("S", C.c_int), ("E", C.c_int), ("classes", C.c_int),
+                ("skip_start", C.c_int), ("out_len", C.c_int), ("mode", C.c_int)]
+
+
+class GenWeights(C.Structure):
+    _fields_ = [("d_start_w", C.c_void_p), ("d_start_b", C.c_void_p),
+                ("d_wf", c_void_pp), ("d_bf", c_void_pp), ("d_wg", c_void_pp), ("d_bg", c_void_pp),
+                ("d_wr", c_void_pp), ("d_br", c_void_pp), ("d_ws", c_void_pp), ("d_bs", c_void_pp),
+                ("d_end1_w", C.c_void_p), ("d_end1_b", C.c_void_p), ("d_end2_w", C.c_void_p), ("d_end2_b", C.c_void_p)]
+
+
+class GenShape(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("k", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int),
+                ("E", C.c_int), ("classes", C.c_int), ("n_streams", C.c_int), ("dilations", C.POINTER(C.c_int))]
+
+
+class GenRunArgs(C.Structure):
+    _fields_ = [("d_first", C.c_void_p), ("n_given", C.c_int),
+                ("d_forced", C.c_void_p), ("d_uniforms", C.c_void_p),
+                ("d_out_idx", C.c_void_p), ("d_out_logits", C.c_void_p),
+                ("n_samples", C.c_int), ("t0", C.c_int), ("n_evals", C.c_int),
+                ("temperature", C.c_float), ("regularize", C.c_float)]
+
+
+# every exported symbol of include/wavenet_b200.h: name -> (restype, argtypes)
+SIGNATURES = {
+    "wn_version": (C.c_int, []),
+    "wn_last_error_string": (C.c_char_p, []),
+    "wn_device_info": (C.c_int, [C.POINTER(C.c_int)] * 5),
+    "wn_n1p": (C.c_int, [C.c_int]),
+    "wn_n2p": (C.c_int, [C.c_int]),
+    "wn_pack_gate_weights": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 3),
+    "wn_pack_res_skip_weights": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 3),
+    "wn_pack_1x1_weights": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 3),
+    "wn_start_fwd_dense": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
+    "wn_start_fwd_index_u8": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
+    "wn_start_fwd_index_i64": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
+    "wn_block_fwd": (C.c_int, [C.POINTER(BlockArgs), C.c_void_p]),
+    "wn_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "wn_gen_workspace_bytes": (C.c_int, [C.POINTER(GenShape), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "wn_gen_create": (C.c_int, [C.POINTER(GenShape), C.POINTER(GenWeights), C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_void_p)]),
+    "wn_gen_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "wn_gen_run": (C.c_int, [C.c_void_p, C.POINTER(GenRunArgs), C.c_void_p]),
+    "wn_gen_destroy": (C.c_int, [C.c_void_p]),
+    "wn_gen_launch_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"wavenet_b200: {LIB_PATH} is missing -- build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                "(there is no CPU or eager fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError here == header and library disagree
+            fn.restype, fn.argtypes = res, args
+        if handle.wn_version() != 1:
+            raise RuntimeError("wavenet_b200: ABI version mismatch between native.py and libwavenet_b200.so")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().wn_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"wavenet_b200 native call failed ({what}, code {rc}): {msg}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def ptr_array(tensors):
+    """ctypes array of device pointers (None entries -> NULL); keep the return value alive during the call."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def device_info():
+    vals = [C.c_int() for _ in range(5)]
+    check(lib().wn_device_info(*[C.byref(v) for v in vals]), "wn_device_info")
+    keys = ("sm_count", "cc_major", "cc_minor", "smem_optin", "l2_bytes")
+    return {k: v.value for k, v in zip(keys, vals)}

@@ -36,3 +36,49 @@ def classify_stream(got_idx, ref_idx, ref_margins, tol=1e-4):
         return len(ref_idx), True
     i = int(neq[0])
     return i, bool(ref_margins[i] < tol)
+
+
+# ---------------------------------------------------------------- product-side helpers (GPU tests)
+def build_model(g, device="cuda", output_length=None):
+    """WaveNetModel (product) with the constructor args / weights stored in a golden file."""
+    import wavenet_model as wmod
+    kw = {k[3:]: (bool(g[k]) if k == "kw_bias" else int(g[k])) for k in g.files if k.startswith("kw_")}
+    if output_length is not None:
+        kw["output_length"] = output_length
+    torch.manual_seed(0)
+    m = wmod.WaveNetModel(**kw)
+    ref = params_from_golden(g)
+    if ref:
+        m.load_state_dict(ref, strict=True)
+    else:
+        assert weight_checksum(m.state_dict()) == float(g["w_checksum"])
+    return m.to(device)
+
+
+def snapshot_model(gs, device="cuda", output_length=64):
+    import wavenet_model as wmod
+    m = wmod.WaveNetModel(layers=int(gs["layers"]), blocks=int(gs["blocks"]), dilation_channels=32,
+                          residual_channels=32, skip_channels=1024, end_channels=512, classes=256,
+                          output_length=output_length, kernel_size=2, bias=True)
+    m.load_state_dict(params_from_golden(gs), strict=True)
+    return m.to(device)
+
+
+def one_hot_cuda(idx, classes=256):
+    idx = torch.as_tensor(np.asarray(idx)).long().cuda()
+    b, l = idx.shape
+    return torch.zeros(b, classes, l, device="cuda").scatter_(1, idx.view(b, 1, l), 1.0)
+
+
+def assert_stream_parity(got_idx, ref_idx, ref_logits, tol=1e-4):
+    """Bit-exact index stream, except that a first mismatch is accepted only where the reference's own top-1/top-2
+    logit gap is below tol (a tie-break divergence, SURVEY.md section 7 hard part 3).  Returns the agreed prefix."""
+    got_idx, ref_idx = np.asarray(got_idx), np.asarray(ref_idx)
+    neq = np.nonzero(got_idx != ref_idx)[0]
+    if len(neq) == 0:
+        return len(ref_idx)
+    i = int(neq[0])
+    top2 = np.sort(ref_logits[i])[-2:]
+    assert top2[1] - top2[0] < tol * max(1.0, float(np.abs(ref_logits[i]).max())), (
+        f"stream diverges at step {i}: got {got_idx[i]} want {ref_idx[i]}, reference margin {top2[1] - top2[0]:.3e}")
+    return i
