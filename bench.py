@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the two WaveNet hot paths on B200, with roofline and the CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|generate|train]
+
+Under torchrun (N>1) every rank runs; rank 0 prints ONE JSON line.
+
+Primary metric (BASELINE.json configs[1]): generate_fast samples/sec -- layers=10, blocks=5, 256 channels,
+16000 samples (1 s of 16 kHz audio), single stream; a "step" is one full generate_fast run.  At N>1 each rank runs
+an independent replica (the path does not shard).
+Secondary metric, same JSON line under "train": training-forward mu-law frames/sec (configs[2] shape: B=8 per GPU,
+L=16000, output_length=10885), batch-sharded over the ranks (weak scaling; the forward has no collective).
+
+`value` is device-timed with inputs resident in HBM; `e2e` goes through the reference-facing Python API with host
+buffers.  `cpu_baseline` / `--impl reference` time the CPU port of the reference (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch-wavenet_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+GEN_KW = dict(layers=10, blocks=5, dilation_channels=256, residual_channels=256, skip_channels=256,
+              end_channels=256, classes=256, output_length=16000 - 5116 + 1, kernel_size=2, bias=False)
+GEN_SAMPLES = 16000
+TRAIN_B, TRAIN_L = 8, 16000
+TEMPERATURE = 1.0
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def build_model(kw, seed=0):
+    import wavenet_model as wmod
+    torch.manual_seed(seed)
+    return wmod.WaveNetModel(**kw)
+
+
+class L2Flush:
+    def __init__(self):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+# ------------------------------------------------------------------------------------------------ generation
+def bench_generate(args, world, rank):
+    model = build_model(GEN_KW).cuda()
+    rt = model._runtime()
+    NS, n = 1, GEN_SAMPLES
+    s = rt.sampler(NS)
+    dev = rt.device()
+    first = torch.full((NS, 1), 128, dtype=torch.int32, device=dev)
+    np.random.seed(rank)
+    uni = torch.from_numpy(np.random.random_sample((NS, n))).to(dev)
+    out = torch.zeros(NS, n, dtype=torch.int32, device=dev)
+    flush = L2Flush()
+
+    def step():
+        rt.generate_resident(s, first, 1, n, TEMPERATURE, 0.0, out, d_uni=uni)
+
+    for _ in range(args.warmup):
+        step()
+    barrier_sync(world)
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier_sync(world)
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    ms = max_over_ranks(ms, world)
+    value = world * NS * n * args.steps / (ms / 1e3)
+
+    # end to end through the reference-facing API: host first_samples / numpy RNG in, float64 waveform out
+    model.generate_fast(256, temperature=TEMPERATURE)                     # warm
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        audio = model.generate_fast(n, temperature=TEMPERATURE)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    assert audio.shape == (n,) and np.isfinite(audio).all()
+    e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "samples/s",
+           "h2d_bytes_per_step": int(rt.h2d_bytes_last), "d2h_bytes_per_step": int(rt.d2h_bytes_last),
+           "api": "WaveNetModel.generate_fast(16000, temperature=1.0) -> float64 ndarray"}
+
+    # argmax path, for reference
+    t_arg = []
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rt.generate_resident(s, first, 1, n, 0.0, 0.0, out)
+        e1.record()
+        torch.cuda.synchronize()
+        t_arg.append(e0.elapsed_time(e1))
+
+    import ctypes, native
+    g, b, bars = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    native.lib().wn_gen_launch_info(s["handle"], ctypes.byref(g), ctypes.byref(b), ctypes.byref(bars))
+    weight_bytes = 4 * sum(p.numel() for p in model.parameters())
+    ring_cols = sum(q.max_length for q in model.dilated_queues)
+    per_launch_ms = ms / args.steps
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per launch: every sample touches all weights once (they do not fit on chip: 79.4 MB fp32)
+    # plus k ring columns read and one written per layer
+    alg_bytes = n * (weight_bytes + 50 * 3 * 256 * 4)
+    roof = {"kernel": "gen_kernel<1> (persistent cooperative sampler)", "bound": "hbm",
+            "achieved": alg_bytes / (per_launch_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg_bytes / (per_launch_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "note": "latency-bound path: weights are re-read per sample from L2, not HBM; the governing figure is "
+                    "us per grid barrier",
+            "us_per_sample": per_launch_ms * 1e3 / n, "grid_barriers_per_sample": bars.value,
+            "us_per_barrier_stage": per_launch_ms * 1e3 / n / bars.value, "grid": g.value, "block": b.value}
+    return dict(value=value, ms_per_step=ms / args.steps, clocks=clk, e2e=e2e, roofline=roof,
+                argmax_samples_per_s=n / (min(t_arg) / 1e3), wall_s=t_wall, launches=args.steps)
+
+
+# ------------------------------------------------------------------------------------------------ training forward
+def train_alg_bytes(model, B, L, dense_input):
+    """per layer e*B*(R*T_in + R*T_out + 2*S*T_final); start and head added."""
+    import wavenet_model as wmod
+    dil = [d for d, _ in model.dilations]
+    plan = wmod.StackPlan(dil, model.kernel_size, L)
+    R, S, C = model.residual_channels, model.skip_channels, model.classes
+    e = 4
+    per_layer = []
+    for i in range(len(dil)):
+        t_in, t_out = L - plan.in_start[i], L - plan.out_start[i]
+        per_layer.append(e * B * (R * t_in + R * t_out + (1 if i == 0 else 2) * S * plan.t_final))
+    start = B * L * (C * e if dense_input else 1) + e * B * R * L
+    head = e * B * (S * plan.t_final + C * model.output_length)
+    flops = sum(2 * B * (L - plan.out_start[i]) * (2 * model.kernel_size * R * model.dilation_channels +
+                                                     model.dilation_channels * R) +
+                2 * B * plan.t_final * model.dilation_channels * S for i in range(len(dil)))
+    return per_layer, start, head, flops
+
+
+def bench_train(args, world, rank):
+    kw = dict(GEN_KW)
+    model = build_model(kw).cuda()
+    rt = model._runtime()
+    B, L = TRAIN_B, TRAIN_L
+    idx = torch.randint(0, 256, (B, L), generator=torch.Generator().manual_seed(1234 + rank))
+    d_idx = idx.to(torch.uint8).cuda()
+    flush = L2Flush()
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = model.forward_indices(d_idx)
+        barrier_sync(world)
+        clocks = ClockSampler(torch.cuda.current_device())
+        clocks.start()
+        evs, bevs = [], []
+        for _ in range(args.steps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rt.block_events = (b0, b1)
+            e0.record()
+            y = model.forward_indices(d_idx)
+            e1.record()
+            evs.append((e0, e1)); bevs.append((b0, b1))
+        rt.block_events = None
+        barrier_sync(world)
+        clk = clocks.stop()
+        ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), world)
+        block_ms = sum(a.elapsed_time(b) for a, b in bevs) / args.steps
+        value = world * B * L * args.steps / (ms / 1e3)
+
+        # end to end through forward(): pinned host one-hot in, logits read back
+        x_host = torch.zeros(B, 256, L).scatter_(1, idx.view(B, 1, L), 1.0).pin_memory()
+        y_host = torch.empty(B * model.output_length, 256).pin_memory()
+        model(x_host.cuda(non_blocking=True))
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            y = model(x_host.cuda(non_blocking=True))
+            y_host.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+        e2e = {"value": world * B * L * e2e_steps / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
+               "api": "WaveNetModel.forward((8,256,16000) one-hot fp32 from pinned host) -> logits copied to host"}
+        # index API (uint8 indices in, argmax of logits out): the traffic-minimal use of the same kernels
+        idx_host = idx.to(torch.uint8).pin_memory()
+        am_host = torch.empty(B * model.output_length, dtype=torch.int64).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            am = model.forward_indices(idx_host.cuda(non_blocking=True)).argmax(1)
+            am_host.copy_(am, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_idx_s = max_over_ranks(time.perf_counter() - t0, world)
+    per_layer, start_b, head_b, flops = train_alg_bytes(model, B, L, dense_input=False)
+    n_layers = len(per_layer)
+    peak, peak_src = measured_peaks()
+    ach = (sum(per_layer) / n_layers) / (block_ms / n_layers / 1e3) / 1e9
+    roof = {"kernel": "block_fwd_kernel<128> (fused residual block, exact fp32 FFMA)", "bound": "hbm",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "launches_per_step": n_layers, "avg_launch_ms": block_ms / n_layers,
+            "alg_bytes_per_launch": sum(per_layer) / n_layers,
+            "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L),
+            "tflops_fp32_achieved": flops / (block_ms / 1e3) / 1e12,
+            "note": "exact-fp32 mode is bound by the fp32 FMA pipe, not by HBM (AI ~196 FLOP/B)"}
+    return dict(metric="training-forward mu-law frames/sec", value=value, unit="frames/s", ms_per_step=ms / args.steps,
+                clocks=clk, e2e=e2e, e2e_index_api={"value": world * B * L * e2e_steps / e2e_idx_s, "unit": "frames/s",
+                                                   "h2d_bytes_per_step": int(idx_host.numel()),
+                                                   "d2h_bytes_per_step": int(am.numel() * 8)},
+                roofline=roof, dtype="f32", scaling="weak",
+                config={"workload": "cfg3 forward: layers=10 blocks=5 ch=256, B=8 per GPU, L=16000, output_length=10885, "
+                                    "uint8 index input resident in HBM", "global_batch": world * B, "seq_len": L,
+                        "parallelism": f"dp{world} (batch shards, no collective in forward)"},
+                launches=args.steps * rt.launches_last_forward)
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_generate(budget_s, temperature, threads):
+    """samples/s of the CPU port at `threads` torch threads, on a sample sized to ~budget_s seconds."""
+    from oracle import wavenet_oracle as O
+    torch.set_num_threads(threads)
+    spec = O.NetSpec(**GEN_KW)
+    p = O.init_params(spec, seed=0)
+    np.random.seed(0)
+    # per-step cost is position independent, so a short run stands in for 16000 samples
+    t0 = time.perf_counter()
+    O.generate_fast(p, spec, 4, temperature=temperature)           # probe (also warms the allocator / thread pool)
+    rate = 4 / (time.perf_counter() - t0)
+    n = int(max(8, min(400, rate * budget_s)))
+    t0 = time.perf_counter()
+    O.generate_fast(p, spec, n, temperature=temperature)
+    return n / (time.perf_counter() - t0), n
+
+
+def cpu_generate_best(budget_s, temperature):
+    """The reference leaves torch's thread count at its default (= all cores), which is a poor choice for these
+    tiny matrix-vector ops; time 1, 8 and all threads and keep the fastest so the baseline is not a straw man."""
+    cores = os.cpu_count() or 1
+    res = {}
+    for th in sorted({1, min(8, cores), cores}):
+        res[th] = cpu_generate(budget_s, temperature, th)
+    best = max(res, key=lambda k: res[k][0])
+    note = ", ".join(f"{th} threads: {v[0]:.1f} samples/s ({v[1]} samples)" for th, v in res.items())
+    return res[best][0], best, note
+
+
+def cpu_train_forward(B, threads):
+    from oracle import wavenet_oracle as O
+    torch.set_num_threads(threads)
+    spec = O.NetSpec(**GEN_KW)
+    p = O.init_params(spec, seed=0)
+    idx = torch.randint(0, 256, (B, TRAIN_L), generator=torch.Generator().manual_seed(1234))
+    x = O.one_hot(idx, 256)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.forward(p, spec, x)
+        dt = time.perf_counter() - t0
+    return B * TRAIN_L / dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference (oracle/) on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    _, threads, note = cpu_generate_best(4.0, TEMPERATURE)
+    vals, n_per_step = [], 0
+    for i in range(args.warmup + args.steps):
+        v, n_per_step = cpu_generate(6.0, TEMPERATURE, threads)
+        if i >= args.warmup:
+            vals.append(v)
+    value = len(vals) / sum(1.0 / v for v in vals)
+    sample = (f"~{n_per_step} samples per step, temperature=1.0 (per-sample cost is position independent); "
+              f"thread sweep: {note}")
+    print(json.dumps({
+        "impl": "reference", "metric": "generate_fast samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_per_step / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 generate_fast: layers=10 blocks=5 ch=256 classes=256, single stream, temperature=1.0"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "generate", "train"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
+    world, rank, _ = dist_setup(args.gpus)
+    gen = bench_generate(args, world, rank) if args.workload in ("all", "generate") else None
+    train = bench_train(args, world, rank) if args.workload in ("all", "train") else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, note = cpu_generate_best(8.0, TEMPERATURE)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "generate_fast samples for ~8 s per thread setting (position-independent per-sample cost), "
+                         "temperature=1.0, torch CPU fp32 op-for-op port of the reference (oracle/wavenet_oracle.py); "
+                         + note}
+        threads = os.cpu_count() or 1
+        if train is not None:
+            train["cpu_baseline"] = {"value": cpu_train_forward(2, threads), "unit": "frames/s", "cores": threads,
+                                     "kind": "port", "sample": "one no_grad forward of B=2, L=16000 one-hot input"}
+    if rank == 0:
+        primary = gen if gen is not None else train
+        line = {
+            "metric": "generate_fast samples/sec" if gen is not None else train["metric"],
+            "value": primary["value"], "unit": "samples/s" if gen is not None else "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": ({"workload": "cfg2 generate_fast: layers=10 blocks=5 ch=256 classes=256, 16000 samples, single "
+                                    "stream per GPU, temperature=1.0, seeded random-init weights",
+                        "parallelism": f"{world} independent replicas (the sampling loop does not shard)",
+                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"}
+                       if gen is not None else train["config"]),
+            "clocks": primary["clocks"], "e2e": primary["e2e"], "gpu_launches": primary["launches"],
+            "roofline": primary["roofline"],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if gen is not None:
+            line["argmax_samples_per_s"] = gen["argmax_samples_per_s"]
+            if train is not None:
+                line["train"] = train
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,7 @@ typedef struct wn_block_args {
     int B, L, R, D, S, k, dilation;
     int in_start, out_start, skip_start, skip_init;
     int mode;
+    float* d_fg_save;   /* optional (B,L,2D): tanh(F) in [0,D), sigmoid(G) in [D,2D) per frame, kept for the backward */
 } wn_block_args;
 int wn_block_fwd(const wn_block_args* a, void* stream);
 
@@ -102,6 +103,40 @@ typedef struct wn_head_args {
     int mode;
 } wn_head_args;
 int wn_head_fwd(const wn_head_args* a, void* stream);
+
+/* ---------------------------------------------------------------- (T) backward, data gradients
+ * replace autograd's backward through the layer loop (the reference calls loss.backward(), wavenet_training.py:71).
+ * Gradient buffers use the frames layout; each carries a first valid frame, left of which it is structurally zero
+ * and is neither read nor written:
+ *   gs_out   first frame where d_dh_out may be non-zero (L if the block output is unused, as for the last layer)
+ *   ds_start first frame of d_dskip, which is (B, L-ds_start, S)       (= L - output_length)
+ *   gz       first frame for which dz / d_dfg / d_z are produced       (>= out_start)
+ *   gs_in    first frame for which d_dh_in is produced                 (>= in_start)
+ * d_wrs_rows: [(R+S)][wn_n2p(D)] rows of residual_conv.weight then skip_conv.weight (zero padded columns);
+ * d_wfg_bwd : [k*2D][wn_n2p(R)], row j*2D+n holds [filter;gate].weight[n, :, j].
+ * Weight gradients are plain GEMMs over the produced buffers (dWr = dh_out^T z, dWs = dskip^T z,
+ * dW{f,g}[:,:,j] = d{F,G}^T h_in(t-(k-1-j)d), biases = column sums) and are left to the caller. */
+typedef struct wn_block_bwd_args {
+    const float* d_dh_out; const float* d_dskip; const float* d_fg;
+    float* d_dfg; float* d_z; float* d_dh_in;
+    const float* d_wrs_rows; const float* d_wfg_bwd;
+    int B, L, R, D, S, k, dilation;
+    int in_start, out_start;
+    int gs_out, ds_start, gz, gs_in;
+} wn_block_bwd_args;
+int wn_block_bwd_data(const wn_block_bwd_args* a, void* stream);
+
+/* head: given d_dlogits (B*out_len, classes) and the saved skip sum (B, L-skip_start, S) produce
+ * d_y1 (B*out_len, E) = relu(W1 relu(skip)+b1) (recomputed), d_dy1 (B*out_len, E) and d_dskip (B, out_len, S).
+ * d_w1_t/d_b1: end_conv_1 packed by wn_pack_1x1_weights; d_w2_rows [classes][wn_n2p(E)] = end_conv_2.weight rows;
+ * d_w1_rows [E][wn_n2p(S)] = end_conv_1.weight rows. */
+typedef struct wn_head_bwd_args {
+    const float* d_dlogits; const float* d_skip;
+    float* d_y1; float* d_dy1; float* d_dskip;
+    const float* d_w1_t; const float* d_b1; const float* d_w2_rows; const float* d_w1_rows;
+    int B, L, S, E, classes, skip_start, out_len;
+} wn_head_bwd_args;
+int wn_head_bwd_data(const wn_head_bwd_args* a, void* stream);
 
 /* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
  * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with
@@ -153,7 +188,13 @@ typedef struct wn_gen_run_args {
 } wn_gen_run_args;
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
-/* how the last wn_gen_run was launched: grid size, block size, barriers per evaluation */
+/* Exchange mechanism between the stages of one evaluation: 0 = flag-in-data pairs, no grid barrier (default, needs
+ * n_layers >= 2); 1 = atomic grid barrier between stages (the simple reference kernel).  Both give the same
+ * indices; call right after wn_gen_reset. */
+int wn_gen_set_mode(wn_gen_handle* h, int mode);
+/* Synchronise the stream and report whether a launch aborted (a CTA waited > ~3 s for a tag): 0 = fine. */
+int wn_gen_check(wn_gen_handle* h, void* stream);
+/* how wn_gen_run launches: grid size, block size, dependent exchange stages per evaluation */
 int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval);
 
 #ifdef __cplusplus

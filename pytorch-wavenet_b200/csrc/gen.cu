@@ -47,6 +47,12 @@ struct GenParams {
     float temperature, regularize;
     // smem carve (floats)
     int regA, regB, pre_n, skacc_n;
+    // ---- flag-in-data ("LL") exchange kernel
+    uint2* ringLL;          // same geometry as rings, 8-byte {value, tag} elements
+    uint2 *zLL, *skipLL, *y1LL, *logitLL;      // [2 parities][...] exchange vectors
+    int* err;               // set to 1 by a CTA that timed out waiting for a tag
+    int part_n;             // partial-sum scratch (floats)
+    int wslot_floats, n_wslots;                // weight prefetch ring in shared memory (0 slots: read weights via L2)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -335,9 +341,404 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
         for (int s = tid; s < NS; s += GEN_NT) p.cur_idx[s] = idx_s[s];
 }
 
+// ================================================================================================ LL kernel
+// Same decomposition as gen_kernel, but no grid barriers: every exchanged float travels as an 8-byte {value, tag}
+// pair written with one volatile store; consumers spin on the pair itself until the tag they expect appears
+// (the NCCL "LL" idea).  Tags: ring slot of time tau carries tau+1; per-evaluation vectors carry t+1 and are
+// double-buffered by the parity of t.  A location is rewritten two evaluations (or one full ring period) after it
+// was last read, and a writer can only get there once every CTA has finished the evaluation in between -- each CTA
+// owns at least one dilation channel (G <= D) whose z every residual row needs -- so no reader is ever overtaken.
+// The weight rows a CTA needs for the next stages are prefetched into shared memory with cp.async.bulk (TMA) while
+// it waits for data; they are the same rows every evaluation, in the parameters' own (state_dict) layout.
+constexpr long long GEN_TIMEOUT_CYCLES = 6000000000LL;     // ~3 s: a missing tag aborts the launch instead of hanging
+
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_pair(uint2* p, float val, unsigned tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ float poll_pair(const uint2* p, unsigned tag, int* err, int* abort_s) {
+    uint2 v = ld_pair(p);
+    if (v.y != tag) {
+        const long long t0 = clock64();
+        do {
+            v = ld_pair(p);
+            if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+                *reinterpret_cast<volatile int*>(err) = 1;
+                *reinterpret_cast<volatile int*>(abort_s) = 1;
+                break;
+            }
+        } while (v.y != tag);
+    }
+    return __uint_as_float(v.x);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// partial dot products over K-range [k0, k1) (multiples of 4 when K%4==0) -- weights from shared or global memory
+template <int SB, bool W_SMEM>
+__device__ __forceinline__ void row_dot_part(const float* __restrict__ w, const float* __restrict__ xs, int K, int k0,
+                                             int k1, int NS, int s0, int lane, float (&acc)[SB]) {
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = 0.f;
+    if ((K & 3) == 0) {
+        const float4* w4p = reinterpret_cast<const float4*>(w);
+        for (int i4 = (k0 >> 2) + lane; i4 < (k1 >> 2); i4 += 32) {
+            float4 w4;
+            if constexpr (W_SMEM) w4 = w4p[i4];
+            else w4 = __ldg(w4p + i4);
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                if (s0 + j < NS) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)(s0 + j) * K + 4 * i4);
+                    float a = acc[j];
+                    a = fmaf(w4.x, x4.x, a); a = fmaf(w4.y, x4.y, a); a = fmaf(w4.z, x4.z, a); a = fmaf(w4.w, x4.w, a);
+                    acc[j] = a;
+                }
+            }
+        }
+    } else {
+        for (int i = k0 + lane; i < k1; i += 32) {
+            float wv;
+            if constexpr (W_SMEM) wv = w[i];
+            else wv = __ldg(w + i);
+#pragma unroll
+            for (int j = 0; j < SB; ++j)
+                if (s0 + j < NS) acc[j] = fmaf(wv, xs[(size_t)(s0 + j) * K + i], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = warp_sum(acc[j]);
+}
+
+// Rows of one stage for one CTA.  Stage numbering inside an evaluation: 2l = conv rows of layer l, 2l+1 = 1x1 rows
+// of layer l, 2NL = end_conv_1 rows, 2NL+1 = end_conv_2 rows.
+struct StageDesc {
+    int n, K;                 // rows, row length
+    int n_first;              // stage 2: residual rows come first (n_first of them), then skip rows
+};
+__device__ __forceinline__ StageDesc stage_desc(const GenParams& p, int st, bool want_head, int nD, int nR, int nS,
+                                                int nE, int nC) {
+    StageDesc d;
+    const int NL = p.n_layers;
+    if (st < 2 * NL) {
+        const int l = st >> 1;
+        if ((st & 1) == 0) { d.n = 2 * nD; d.K = p.k * p.R; d.n_first = d.n; }
+        else { d.n_first = (l + 1 < NL) ? nR : 0; d.n = d.n_first + (want_head ? nS : 0); d.K = p.D; }
+    } else if (st == 2 * NL) { d.n = nE; d.K = p.S; d.n_first = d.n; }
+    else { d.n = nC; d.K = p.E; d.n_first = d.n; }
+    return d;
+}
+__device__ __forceinline__ const float* stage_row(const GenParams& p, int st, const StageDesc& d, int i, int cta, int G) {
+    const int NL = p.n_layers;
+    if (st < 2 * NL) {
+        const GenLayer& L = p.layers[st >> 1];
+        if ((st & 1) == 0) return ((i & 1) ? L.wg : L.wf) + (size_t)((i >> 1) * G + cta) * d.K;
+        if (i < d.n_first) return L.wr + (size_t)(i * G + cta) * d.K;
+        return L.ws + (size_t)((i - d.n_first) * G + cta) * d.K;
+    }
+    if (st == 2 * NL) return p.e1w + (size_t)(i * G + cta) * d.K;
+    return p.e2w + (size_t)(i * G + cta) * d.K;
+}
+
+template <int SB, bool PREFETCH>
+__global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* regA = sm;                          // stage-1 inputs [NS][k*R] / head input [NS][S] / logits [NS][C]
+    float* regB = regA + p.regA;               // z [NS][D] / y1 [NS][E]
+    float* part = regB + p.regB;               // partial sums [item][kpart][NS]
+    float* skacc = part + p.part_n;            // running skip sums of the rows this CTA owns [rows][NS]
+    float* prob = skacc + p.skacc_n;           // [GEN_WARPS][C] softmax scratch
+    double* cdf = reinterpret_cast<double*>(prob + GEN_WARPS * p.C);   // [GEN_WARPS][C]
+    float* wbuf = reinterpret_cast<float*>(cdf + GEN_WARPS * p.C);     // [n_wslots][wslot_floats]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    int* idx_s = reinterpret_cast<int*>(fullb + 8);                     // current input index per stream [NS]
+    int* abort_s = idx_s + p.NS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int NS = p.NS, R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, k = p.k, NL = p.n_layers;
+    const int K1 = k * R;
+    const int nD = (D > cta) ? (D - cta + G - 1) / G : 0;
+    const int nR = (R > cta) ? (R - cta + G - 1) / G : 0;
+    const int nS = (S > cta) ? (S - cta + G - 1) / G : 0;
+    const int nE = (E > cta) ? (E - cta + G - 1) / G : 0;
+    const int nC = (C > cta) ? (C - cta + G - 1) / G : 0;
+    const int NSLOT = p.n_wslots;
+
+    for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.cur_idx[s];
+    if (tid == 0) {
+        *abort_s = 0;
+        if (PREFETCH)
+            for (int i = 0; i < NSLOT; ++i) mbar_init(fullb + i, 1);
+    }
+    if (PREFETCH) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // ---- weight prefetch pipeline (thread 0 produces): stage q of the launch lives in slot q % NSLOT
+    int pf_ev = 0, pf_st = 0;                 // producer cursor
+    long long pf_q = 0, cons_q = 0;
+    auto stages_in_eval = [&](int ev) { return (p.t0 + ev >= p.n_given - 1) ? 2 * NL + 2 : 2 * NL; };
+    auto produce_one = [&]() {                // thread 0 only
+        if (pf_ev >= p.n_evals) return;
+        const bool wh = (p.t0 + pf_ev >= p.n_given - 1);
+        const StageDesc d = stage_desc(p, pf_st, wh, nD, nR, nS, nE, nC);
+        const int slot = (int)(pf_q % NSLOT);
+        mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+        float* dst = wbuf + (size_t)slot * p.wslot_floats;
+        for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
+        ++pf_q;
+        if (++pf_st >= stages_in_eval(pf_ev)) { pf_st = 0; ++pf_ev; }
+    };
+    if (PREFETCH && tid == 0)
+        for (int i = 0; i < NSLOT; ++i) produce_one();
+
+    // One dot-product stage: rows of `st` times the vectors xs[s][0..K) -> part[item][kpart][s]; all 8 warps work,
+    // rows are split over nw = 8/items warps along K when there are fewer rows than warps.
+    auto run_stage = [&](int st, const StageDesc& d, const float* xs, int& nw_out) {
+        int nw = 1;
+        while (nw * 2 * d.n <= GEN_WARPS && (d.K / (nw * 2)) % 4 == 0 && d.K / (nw * 2) >= 32) nw *= 2;
+        if (d.n == 0) nw = 1;
+        nw_out = nw;
+        const float* wslot = nullptr;
+        if (PREFETCH) {
+            const int slot = (int)(cons_q % NSLOT);
+            mbar_wait(fullb + slot, (unsigned)((cons_q / NSLOT) & 1));
+            wslot = wbuf + (size_t)slot * p.wslot_floats;
+        }
+        const int kchunk = d.K / nw;
+        for (int wi = warp; wi < d.n * nw; wi += GEN_WARPS) {
+            const int it = wi / nw, kp = wi - it * nw;
+            const int k0 = kp * kchunk, k1 = (kp == nw - 1) ? d.K : k0 + kchunk;
+            for (int s0 = 0; s0 < NS; s0 += SB) {
+                float acc[SB];
+                if (PREFETCH) row_dot_part<SB, true>(wslot + (size_t)it * d.K, xs, d.K, k0, k1, NS, s0, lane, acc);
+                else row_dot_part<SB, false>(stage_row(p, st, d, it, cta, G), xs, d.K, k0, k1, NS, s0, lane, acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < SB; ++j)
+                        if (s0 + j < NS) part[(size_t)(it * nw + kp) * NS + s0 + j] = acc[j];
+                }
+            }
+        }
+        ++cons_q;
+    };
+    auto sum_parts = [&](int it, int nw, int s) {
+        float v = part[(size_t)(it * nw) * NS + s];
+        for (int kp = 1; kp < nw; ++kp) v += part[(size_t)(it * nw + kp) * NS + s];
+        return v;
+    };
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;
+        const unsigned tag = (unsigned)t + 1u;
+        const int par = t & 1;
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);
+        if (t < p.n_given) {
+            for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.first[(size_t)s * p.n_given + t];
+        } else if (p.forced != nullptr) {
+            for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.forced[(size_t)s * p.n_samples + (t - p.n_given)];
+        }
+        for (int i = tid; i < nS * NS; i += GEN_NT) skacc[i] = 0.f;
+        __syncthreads();
+        if (*abort_s) return;
+
+        for (int l = 0; l < NL; ++l) {
+            const GenLayer L = p.layers[l];
+            uint2* ring = p.ringLL + L.ring_off;
+            const int slot_t = t % L.ring_len;
+            // ---- stage-1 inputs: regA[s][r*k + j] = tap j of channel r (tap k-1 = the value just enqueued)
+            for (int i = tid; i < NS * K1; i += GEN_NT) {
+                const int s = i / K1, rem = i - s * K1, r = rem / k, j = rem - r * k;
+                float v;
+                if (j == k - 1 && l == 0) {
+                    int c = idx_s[s];
+                    c = c < 0 ? 0 : (c >= C ? C - 1 : c);
+                    v = __ldg(p.start_w + (size_t)r * C + c) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
+                    if (r % G == cta) st_pair(ring + ((size_t)slot_t * NS + s) * R + r, v, tag);       // enqueue
+                } else {
+                    const int tt = t - (k - 1 - j) * L.dil;
+                    if (tt < 0) v = 0.f;                                                             // zero history
+                    else v = poll_pair(ring + ((size_t)(tt % L.ring_len) * NS + s) * R + r, (unsigned)tt + 1u, p.err, abort_s);
+                }
+                regA[i] = v;
+            }
+            __syncthreads();
+            if (*abort_s) return;
+            // ---- stage 1: filter / gate rows -> z
+            int nw;
+            StageDesc d1 = stage_desc(p, 2 * l, want_head, nD, nR, nS, nE, nC);
+            run_stage(2 * l, d1, regA, nw);
+            __syncthreads();
+            if (PREFETCH && tid == 0) produce_one();
+            uint2* zl = p.zLL + ((size_t)(par * NL + l) * NS) * D;
+            for (int i = tid; i < nD * NS; i += GEN_NT) {
+                const int ci = i / NS, s = i - ci * NS, c = ci * G + cta;
+                const float f = sum_parts(2 * ci, nw, s) + (L.bf ? __ldg(L.bf + c) : 0.f);
+                const float g = sum_parts(2 * ci + 1, nw, s) + (L.bg ? __ldg(L.bg + c) : 0.f);
+                st_pair(zl + (size_t)s * D + c, tanhf(f) * sigmoid_(g), tag);
+            }
+            // ---- stage 2: residual rows (-> next layer's ring slot t) and skip rows (-> running sums)
+            StageDesc d2 = stage_desc(p, 2 * l + 1, want_head, nD, nR, nS, nE, nC);
+            if (d2.n > 0) {
+                for (int i = tid; i < NS * D; i += GEN_NT) regB[i] = poll_pair(zl + i, tag, p.err, abort_s);
+            }
+            __syncthreads();                       // also protects `part` (read above) against the next run_stage
+            if (*abort_s) return;
+            run_stage(2 * l + 1, d2, regB, nw);
+            __syncthreads();
+            if (PREFETCH && tid == 0) produce_one();
+            for (int i = tid; i < d2.n * NS; i += GEN_NT) {
+                const int it = i / NS, s = i - it * NS;
+                if (it < d2.n_first) {
+                    const int row = it * G + cta;
+                    const GenLayer& Ln = p.layers[l + 1];
+                    const float v = sum_parts(it, nw, s) + (L.br ? __ldg(L.br + row) : 0.f);
+                    const float cur = regA[(size_t)s * K1 + row * k + (k - 1)];
+                    st_pair(p.ringLL + Ln.ring_off + ((size_t)(t % Ln.ring_len) * NS + s) * R + row, v + cur, tag);
+                } else {
+                    const int li = it - d2.n_first, row = li * G + cta;
+                    const float v = sum_parts(it, nw, s) + (L.bs ? __ldg(L.bs + row) : 0.f);
+                    skacc[li * NS + s] = v + skacc[li * NS + s];
+                }
+            }
+            __syncthreads();                       // the epilogue read regA (cur) and part: done before the next gather
+        }
+        if (!want_head) continue;
+
+        // ---- head: skip -> end_conv_1 -> end_conv_2 -> choose
+        __syncthreads();
+        uint2* skl = p.skipLL + (size_t)par * NS * S;
+        for (int i = tid; i < nS * NS; i += GEN_NT) {
+            const int li = i / NS, s = i - li * NS;
+            st_pair(skl + (size_t)s * S + li * G + cta, skacc[i], tag);
+        }
+        int nw;
+        StageDesc dA = stage_desc(p, 2 * NL, true, nD, nR, nS, nE, nC);
+        if (dA.n > 0)
+            for (int i = tid; i < NS * S; i += GEN_NT) regA[i] = fmaxf(poll_pair(skl + i, tag, p.err, abort_s), 0.f);
+        __syncthreads();
+        if (*abort_s) return;
+        run_stage(2 * NL, dA, regA, nw);
+        __syncthreads();
+        if (PREFETCH && tid == 0) produce_one();
+        uint2* yl = p.y1LL + (size_t)par * NS * E;
+        for (int i = tid; i < nE * NS; i += GEN_NT) {
+            const int it = i / NS, s = i - it * NS, row = it * G + cta;
+            st_pair(yl + (size_t)s * E + row, fmaxf(sum_parts(it, nw, s) + __ldg(p.e1b + row), 0.f), tag);
+        }
+        StageDesc dB = stage_desc(p, 2 * NL + 1, true, nD, nR, nS, nE, nC);
+        if (dB.n > 0)
+            for (int i = tid; i < NS * E; i += GEN_NT) regB[i] = poll_pair(yl + i, tag, p.err, abort_s);
+        __syncthreads();
+        if (*abort_s) return;
+        run_stage(2 * NL + 1, dB, regB, nw);
+        __syncthreads();
+        if (PREFETCH && tid == 0) produce_one();
+        uint2* lgl = p.logitLL + (size_t)par * NS * C;
+        for (int i = tid; i < nC * NS; i += GEN_NT) {
+            const int it = i / NS, s = i - it * NS, row = it * G + cta;
+            const float dc = (float)row - (float)C / 2.f;
+            const float v = (sum_parts(it, nw, s) + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+            st_pair(lgl + (size_t)s * C + row, v, tag);
+            if (p.out_logits) p.out_logits[((size_t)s * p.n_samples + samp) * C + row] = v;
+        }
+        // ---- every CTA collects all logits and picks the next sample itself (no broadcast needed)
+        for (int i = tid; i < NS * C; i += GEN_NT) regA[i] = poll_pair(lgl + i, tag, p.err, abort_s);
+        __syncthreads();
+        if (*abort_s) return;
+        float* pw = prob + warp * C;
+        double* cw = cdf + warp * C;
+        for (int s = warp; s < NS; s += GEN_WARPS) {
+            const float* lg = regA + (size_t)s * C;
+            int choice;
+            if (p.temperature > 0.f) {
+                float m = -INFINITY;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = lg[c] / p.temperature;
+                    pw[c] = x;
+                    m = fmaxf(m, x);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int c = lane; c < C; c += 32) {
+                    const float e = expf(pw[c] - m);
+                    pw[c] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                for (int c = lane; c < C; c += 32) cw[c] = (double)(pw[c] / sum);
+                __syncwarp();
+                // numpy.random.choice: sequential float64 cumulative sum, normalised by its last element,
+                // searchsorted(side='right') == number of normalised entries <= u
+                if (lane == 0) {
+                    double run = 0.0;
+                    for (int c = 0; c < C; ++c) { run += cw[c]; cw[c] = run; }
+                }
+                __syncwarp();
+                const double total = cw[C - 1];
+                const double u = p.uniforms[(size_t)s * p.n_samples + samp];
+                int cnt = 0;
+                for (int c = lane; c < C; c += 32) cnt += ((cw[c] / total) <= u) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                choice = cnt < C ? cnt : C - 1;
+            } else {
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = lg[c];
+                    if (x > best || (x == best && c < bi)) { best = x; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                choice = bi == 0x7fffffff ? 0 : bi;
+            }
+            if (lane == 0) {
+                idx_s[s] = choice;
+                if (cta == 0) p.out_idx[(size_t)s * p.n_samples + samp] = choice;
+            }
+        }
+        __syncthreads();
+    }
+    if (cta == 0)
+        for (int s = tid; s < NS; s += GEN_NT) p.cur_idx[s] = idx_s[s];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
-    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, total;
+    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, total;
 };
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static ScratchLayout scratch_layout(const wn_gen_shape& s) {
@@ -350,6 +751,12 @@ static ScratchLayout scratch_layout(const wn_gen_shape& s) {
     o.skipbuf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.S, 256);
     o.y1buf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.E, 256);
     o.logitbuf = off; off = align_up(off + sizeof(float) * (size_t)s.n_streams * s.classes, 256);
+    o.err = off; off += 256;
+    o.zLL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_layers * s.n_streams * s.D, 256);
+    o.skipLL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.S, 256);
+    o.y1LL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.E, 256);
+    o.logitLL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.classes, 256);
+    o.ll_end = off;
     o.total = off;
     return o;
 }
@@ -378,6 +785,8 @@ struct wn_gen_handle {
     size_t smem;
     bool tables_uploaded;
     int cur_t;
+    int mode;               // 0 = flag-in-data exchange (default), 1 = grid-barrier kernel
+    size_t smem_ll;
 };
 
 static int validate_shape(const wn_gen_shape* s) {
@@ -391,7 +800,7 @@ static int validate_shape(const wn_gen_shape* s) {
 
 extern "C" int wn_gen_workspace_bytes(const wn_gen_shape* s, size_t* ring_bytes, size_t* scratch_bytes) {
     if (int rc = validate_shape(s)) return rc;
-    if (ring_bytes) *ring_bytes = sizeof(float) * ring_floats(*s, nullptr);
+    if (ring_bytes) *ring_bytes = sizeof(uint2) * ring_floats(*s, nullptr);   // {value, tag} pairs
     if (scratch_bytes) *scratch_bytes = scratch_layout(*s).total;
     return 0;
 }
@@ -416,7 +825,7 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     h->lay = scratch_layout(h->shape);
     h->scratch = (char*)d_scratch;
     std::vector<long long> offs;
-    h->ring_bytes = sizeof(float) * ring_floats(h->shape, &offs);
+    h->ring_bytes = sizeof(uint2) * ring_floats(h->shape, &offs);
     h->layers.resize(s->n_layers);
     for (int l = 0; l < s->n_layers; ++l) {
         GenLayer& L = h->layers[l];
@@ -472,6 +881,45 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
         return set_err(WN_E_UNSUPP, "wn_gen_create: %zu bytes of shared memory needed for %d streams, %d available", need,
                        NS, smem_optin);
     }
+    // ---- LL kernel: exchange regions, shared-memory carve, weight prefetch ring
+    p.ringLL = reinterpret_cast<uint2*>(d_rings);
+    p.zLL = reinterpret_cast<uint2*>(h->scratch + h->lay.zLL);
+    p.skipLL = reinterpret_cast<uint2*>(h->scratch + h->lay.skipLL);
+    p.y1LL = reinterpret_cast<uint2*>(h->scratch + h->lay.y1LL);
+    p.logitLL = reinterpret_cast<uint2*>(h->scratch + h->lay.logitLL);
+    p.err = reinterpret_cast<int*>(h->scratch + h->lay.err);
+    {
+        const int nDm = cdiv(s->D, G), nRm = cdiv(s->R, G), nSm = cdiv(s->S, G), nEm = cdiv(s->E, G), nCm = cdiv(s->classes, G);
+        int mxA = mx1 > s->classes ? mx1 : s->classes;
+        const int regA_ll = (NS * mxA + 3) / 4 * 4;
+        int items_max = 2 * nDm;
+        if (nRm + nSm > items_max) items_max = nRm + nSm;
+        if (nEm > items_max) items_max = nEm;
+        if (nCm > items_max) items_max = nCm;
+        p.part_n = ((items_max > GEN_WARPS ? items_max : GEN_WARPS) * NS + 3) / 4 * 4;
+        long long slot = (long long)2 * nDm * s->k * s->R;
+        if ((long long)(nRm + nSm) * s->D > slot) slot = (long long)(nRm + nSm) * s->D;
+        if ((long long)nEm * s->S > slot) slot = (long long)nEm * s->S;
+        if ((long long)nCm * s->E > slot) slot = (long long)nCm * s->E;
+        slot = (slot + 3) / 4 * 4;
+        const size_t base = sizeof(float) * ((size_t)regA_ll + p.regB + p.part_n + p.skacc_n + (size_t)GEN_WARPS * s->classes) +
+                            sizeof(double) * (size_t)GEN_WARPS * s->classes + 64 + sizeof(int) * (size_t)(NS + 4);
+        const bool k_ok = ((s->k * s->R) % 4 == 0) && (s->D % 4 == 0) && (s->S % 4 == 0) && (s->E % 4 == 0);
+        int nslots = 0;
+        if (k_ok && base < (size_t)smem_optin) {
+            long long fit = ((long long)smem_optin - (long long)base) / (slot * 4);
+            nslots = fit >= 4 ? 4 : (fit >= 2 ? (int)fit : 0);
+        }
+        p.wslot_floats = (int)slot;
+        p.n_wslots = nslots;
+        h->smem_ll = base + (size_t)nslots * slot * 4;
+        // regA of the LL kernel also stages the logits; keep one GenParams for both kernels
+        if (regA_ll > p.regA) {
+            p.regA = regA_ll;
+            h->smem = sizeof(float) * ((size_t)p.regA + p.regB + p.pre_n + p.skacc_n + NS + (size_t)GEN_WARPS * s->classes);
+        }
+        h->mode = (s->n_layers >= 2 && h->smem_ll <= (size_t)smem_optin) ? 0 : 1;
+    }
     h->tables_uploaded = false;
     h->cur_t = 0;
     *out = h;
@@ -483,6 +931,7 @@ extern "C" int wn_gen_reset(wn_gen_handle* h, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     WN_CUDA(cudaMemsetAsync(h->base.rings, 0, h->ring_bytes, st));
     WN_CUDA(cudaMemsetAsync(h->scratch + h->lay.cur_idx, 0, sizeof(int) * h->shape.n_streams, st));
+    WN_CUDA(cudaMemsetAsync(h->scratch + h->lay.err, 0, h->lay.ll_end - h->lay.err, st));
     if (!h->tables_uploaded) {
         WN_CUDA(cudaMemcpyAsync(h->scratch + h->lay.layers, h->layers.data(), sizeof(GenLayer) * h->layers.size(),
                                 cudaMemcpyHostToDevice, st));
@@ -501,6 +950,35 @@ static int launch_gen(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
     void* args[] = {(void*)&p};
     WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel<SB>, dim3(h->grid), dim3(GEN_NT), args, h->smem, st));
+    return 0;
+}
+
+template <int SB, bool PF>
+static int launch_gen_ll(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_ll<SB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ll));
+    int per_sm = 0;
+    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_ll<SB, PF>, GEN_NT, h->smem_ll));
+    WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
+    void* args[] = {(void*)&p};
+    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_ll<SB, PF>, dim3(h->grid), dim3(GEN_NT), args, h->smem_ll, st));
+    return 0;
+}
+
+extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_set_mode: null handle");
+    WN_REQUIRE(mode == 0 || mode == 1, WN_E_BADARG, "wn_gen_set_mode: mode must be 0 (flag exchange) or 1 (grid barrier)");
+    WN_REQUIRE(h->cur_t == 0, WN_E_STATE, "wn_gen_set_mode: switch kernels only right after wn_gen_reset");
+    if (mode == 0) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
+    h->mode = mode;
+    return 0;
+}
+
+extern "C" int wn_gen_check(wn_gen_handle* h, void* stream) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_check: null handle");
+    int flag = 0;
+    WN_CUDA(cudaMemcpyAsync(&flag, h->scratch + h->lay.err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    WN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    WN_REQUIRE(flag == 0, WN_E_STATE, "wn_gen_check: the sampler timed out waiting for an exchange tag (launch aborted)");
     return 0;
 }
 
@@ -529,7 +1007,15 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         p.out_idx = a->d_out_idx; p.out_logits = a->d_out_logits; p.n_samples = a->n_samples;
         p.t0 = a->t0 + done; p.n_evals = n; p.temperature = a->temperature; p.regularize = a->regularize;
         WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
-        int rc = (h->shape.n_streams == 1) ? launch_gen<1>(h, p, st) : launch_gen<8>(h, p, st);
+        int rc;
+        if (h->mode == 0) {
+            if (h->shape.n_streams == 1)
+                rc = p.n_wslots ? launch_gen_ll<1, true>(h, p, st) : launch_gen_ll<1, false>(h, p, st);
+            else
+                rc = p.n_wslots ? launch_gen_ll<8, true>(h, p, st) : launch_gen_ll<8, false>(h, p, st);
+        } else {
+            rc = (h->shape.n_streams == 1) ? launch_gen<1>(h, p, st) : launch_gen<8>(h, p, st);
+        }
         if (rc) return rc;
         done += n;
     }
@@ -546,6 +1032,6 @@ extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block,
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_launch_info: null handle");
     if (grid) *grid = h->grid;
     if (block) *block = GEN_NT;
-    if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;
+    if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
     return 0;
 }

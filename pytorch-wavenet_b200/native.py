@@ -21,7 +21,24 @@ class BlockArgs(C.Structure):
                 ("d_wfg_t", C.c_void_p), ("d_bfg", C.c_void_p), ("d_wrs_t", C.c_void_p), ("d_brs", C.c_void_p),
                 ("B", C.c_int), ("L", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("k", C.c_int),
                 ("dilation", C.c_int), ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int),
-                ("skip_init", C.c_int), ("mode", C.c_int)]
+                ("skip_init", C.c_int), ("mode", C.c_int), ("d_fg_save", C.c_void_p)]
+
+
+class BlockBwdArgs(C.Structure):
+    _fields_ = [("d_dh_out", C.c_void_p), ("d_dskip", C.c_void_p), ("d_fg", C.c_void_p),
+                ("d_dfg", C.c_void_p), ("d_z", C.c_void_p), ("d_dh_in", C.c_void_p),
+                ("d_wrs_rows", C.c_void_p), ("d_wfg_bwd", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("k", C.c_int),
+                ("dilation", C.c_int), ("in_start", C.c_int), ("out_start", C.c_int),
+                ("gs_out", C.c_int), ("ds_start", C.c_int), ("gz", C.c_int), ("gs_in", C.c_int)]
+
+
+class HeadBwdArgs(C.Structure):
+    _fields_ = [("d_dlogits", C.c_void_p), ("d_skip", C.c_void_p),
+                ("d_y1", C.c_void_p), ("d_dy1", C.c_void_p), ("d_dskip", C.c_void_p),
+                ("d_w1_t", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2_rows", C.c_void_p), ("d_w1_rows", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("S", C.c_int), ("E", C.c_int), ("classes", C.c_int),
+                ("skip_start", C.c_int), ("out_len", C.c_int)]
 
 
 class HeadArgs(C.Structure):
@@ -66,12 +83,16 @@ SIGNATURES = {
     "wn_start_fwd_index_i64": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_block_fwd": (C.c_int, [C.POINTER(BlockArgs), C.c_void_p]),
     "wn_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "wn_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p]),
+    "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
     "wn_gen_workspace_bytes": (C.c_int, [C.POINTER(GenShape), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "wn_gen_create": (C.c_int, [C.POINTER(GenShape), C.POINTER(GenWeights), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),
     "wn_gen_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wn_gen_run": (C.c_int, [C.c_void_p, C.POINTER(GenRunArgs), C.c_void_p]),
     "wn_gen_destroy": (C.c_int, [C.c_void_p]),
+    "wn_gen_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "wn_gen_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wn_gen_launch_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),
 }
 

@@ -115,9 +115,10 @@ class _Runtime:
         return out
 
     # ------------------------------------------------------------------ training-path forward
-    def stack_forward(self, x, out_len, index_input=False):
+    def stack_forward(self, x, out_len, index_input=False, save=None):
         """x: (B, classes, L) float32 one-hot/dense, or (B, L) uint8/int64 indices when index_input.
-        Returns logits (B*out_len, classes) for the last out_len frames (out_len=None: all T_final frames)."""
+        Returns logits (B*out_len, classes) for the last out_len frames (out_len=None: all T_final frames).
+        save: optional dict; filled with what the backward needs (every layer's input, tanh/sigmoid outputs, skip)."""
         m, lib = self.model, native.lib()
         dev = self.device()
         if x.device != dev:
@@ -142,13 +143,20 @@ class _Runtime:
         if out_len > plan.t_final:
             raise RuntimeError(f"output_length {out_len} exceeds the {plan.t_final} frames this input yields "
                                f"(shape '[{B * out_len}, {Cc}]' is invalid for input of size {B * plan.t_final * Cc})")
-        key = (B, L)
-        if key not in self.ws:
-            self.ws.clear()
-            f32 = dict(device=dev, dtype=torch.float32)
-            self.ws[key] = (torch.empty(B, L, R, **f32), torch.empty(B, L, R, **f32),
-                            torch.empty(B, plan.t_final, S, **f32))
-        h0, h1, skip = self.ws[key]
+        f32 = dict(device=dev, dtype=torch.float32)
+        n_layers = len(dil)
+        if save is not None:
+            h_all = torch.empty(n_layers + 1, B, L, R, **f32)      # h_all[i] = input of layer i
+            fg_all = torch.empty(n_layers, B, L, 2 * D, **f32)     # tanh / sigmoid outputs
+            skip = torch.empty(B, plan.t_final, S, **f32)
+            h0 = h_all[0]
+        else:
+            key = (B, L)
+            if key not in self.ws:
+                self.ws.clear()
+                self.ws[key] = (torch.empty(B, L, R, **f32), torch.empty(B, L, R, **f32),
+                                torch.empty(B, plan.t_final, S, **f32))
+            h0, h1, skip = self.ws[key]
         ws_t, bs_p = W["start"]
         if index_input:
             fn = lib.wn_start_fwd_index_u8 if x.dtype == torch.uint8 else lib.wn_start_fwd_index_i64
@@ -159,14 +167,23 @@ class _Runtime:
         a = native.BlockArgs()
         a.B, a.L, a.R, a.D, a.S, a.k, a.mode = B, L, R, D, S, k, 0
         a.d_skip, a.skip_start = skip.data_ptr(), plan.skip_start
-        src, dst = h0, h1
+        src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
+        ev = getattr(self, "block_events", None)      # optional (start, end) CUDA events around the block launches
+        if ev is not None:
+            ev[0].record(torch.cuda.current_stream(dev))
         for i, d in enumerate(dil):
             wfg, bfg, wrs, brs = W["layers"][i]
             a.d_h_in, a.d_h_out = src.data_ptr(), dst.data_ptr()
             a.d_wfg_t, a.d_bfg, a.d_wrs_t, a.d_brs = wfg.data_ptr(), bfg.data_ptr(), wrs.data_ptr(), brs.data_ptr()
             a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
+            a.d_fg_save = None if save is None else fg_all[i].data_ptr()
             native.check(lib.wn_block_fwd(ctypes.byref(a), stream), f"block {i}")
-            src, dst = dst, src
+            if save is None:
+                src, dst = dst, src
+            elif i + 1 < n_layers:
+                src, dst = h_all[i + 1], h_all[i + 2]
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(dev))
         logits = torch.empty(B * out_len, Cc, device=dev, dtype=torch.float32)
         hd = native.HeadArgs()
         hd.d_skip, hd.d_logits = skip.data_ptr(), logits.data_ptr()
@@ -175,7 +192,129 @@ class _Runtime:
         hd.B, hd.L, hd.S, hd.E, hd.classes, hd.skip_start, hd.out_len, hd.mode = B, L, S, E, Cc, plan.skip_start, out_len, 0
         native.check(lib.wn_head_fwd(ctypes.byref(hd), stream), "head")
         self.launches_last_forward = 1 + len(dil) + 1
+        if save is not None:
+            save.update(h_all=h_all, fg_all=fg_all, skip=skip, plan=plan, out_len=out_len, x=x,
+                        index_input=index_input, B=B, L=L)
         return logits
+
+    # ------------------------------------------------------------------ training-path backward
+    def stack_backward(self, saved, dlogits):
+        """Gradients of all parameters given d(loss)/d(logits) (B*out_len, classes).  Data gradients run on the
+        wn_*_bwd_data kernels; the weight gradients are plain GEMMs over the buffers those kernels produce.
+        Returns a dict name -> gradient tensor shaped like the parameter."""
+        m, lib = self.model, native.lib()
+        dev = self.device()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        W = self.packed_weights(stream)
+        P = self._params()
+        plan, B, L, OL = saved["plan"], saved["B"], saved["L"], saved["out_len"]
+        h_all, fg_all, skip = saved["h_all"], saved["fg_all"], saved["skip"]
+        R, D, S = m.residual_channels, m.dilation_channels, m.skip_channels
+        E, Cc, k = m.end_conv_1.out_channels, m.classes, m.kernel_size
+        dil = [d for d, _ in m.dilations]
+        n_layers = len(dil)
+        f32 = dict(device=dev, dtype=torch.float32)
+        pad_cols = lambda w2d, n: torch.nn.functional.pad(w2d, (0, n - w2d.shape[1])).contiguous()
+        grads = {}
+        dlogits = dlogits.contiguous().view(B, OL, Cc)
+        # ---------------- head
+        w1, b1 = P["end1"]
+        w2, b2 = P["end2"]
+        y1 = torch.empty(B, OL, E, **f32)
+        dy1 = torch.empty(B, OL, E, **f32)
+        dskip = torch.empty(B, OL, S, **f32)
+        w2_rows = pad_cols(w2.detach()[:, :, 0], lib.wn_n2p(E))
+        w1_rows = pad_cols(w1.detach()[:, :, 0], lib.wn_n2p(S))
+        hb = native.HeadBwdArgs()
+        hb.d_dlogits, hb.d_skip = dlogits.data_ptr(), skip.data_ptr()
+        hb.d_y1, hb.d_dy1, hb.d_dskip = y1.data_ptr(), dy1.data_ptr(), dskip.data_ptr()
+        hb.d_w1_t, hb.d_b1 = W["end1"][0].data_ptr(), W["end1"][1].data_ptr()
+        hb.d_w2_rows, hb.d_w1_rows = w2_rows.data_ptr(), w1_rows.data_ptr()
+        hb.B, hb.L, hb.S, hb.E, hb.classes, hb.skip_start, hb.out_len = B, L, S, E, Cc, plan.skip_start, OL
+        native.check(lib.wn_head_bwd_data(ctypes.byref(hb), stream), "head bwd")
+        ds_start = L - OL
+        rskip = torch.relu(skip[:, ds_start - plan.skip_start:, :])
+        grads["end_conv_2.weight"] = torch.einsum("btc,bte->ce", dlogits, y1).unsqueeze(-1)
+        grads["end_conv_2.bias"] = dlogits.sum((0, 1))
+        grads["end_conv_1.weight"] = torch.einsum("bte,bts->es", dy1, rskip).unsqueeze(-1)
+        grads["end_conv_1.bias"] = dy1.sum((0, 1))
+        reducer = getattr(self, "grad_reducer", None)      # data_parallel.GradientAverager or None
+        if reducer is not None:
+            reducer.reduce_async([grads[n] for n in ("end_conv_2.weight", "end_conv_2.bias", "end_conv_1.weight",
+                                                     "end_conv_1.bias")])
+        # ---------------- residual blocks, last to first
+        dfg = torch.empty(B, L, 2 * D, **f32)
+        zbuf = torch.empty(B, L, D, **f32)
+        dh_a, dh_b = torch.empty(B, L, R, **f32), torch.empty(B, L, R, **f32)
+        dh_out, gs_out = None, L
+        a = native.BlockBwdArgs()
+        a.B, a.L, a.R, a.D, a.S, a.k, a.ds_start = B, L, R, D, S, k, ds_start
+        a.d_dskip, a.d_dfg, a.d_z = dskip.data_ptr(), dfg.data_ptr(), zbuf.data_ptr()
+        for i in range(n_layers - 1, -1, -1):
+            d = dil[i]
+            in_s, out_s = plan.in_start[i], plan.out_start[i]
+            (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
+            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+            gz = max(out_s, min(gs_out, ds_start))
+            id_start = max(out_s, gs_out)
+            gs_in = max(in_s, min(id_start, gz - (k - 1) * d))
+            wrs_rows = pad_cols(torch.cat([wr.detach()[:, :, 0], wsk.detach()[:, :, 0]], 0), lib.wn_n2p(D))
+            wfg_bwd = pad_cols(torch.cat([wf.detach(), wg.detach()], 0).permute(2, 0, 1).reshape(k * 2 * D, R),
+                               lib.wn_n2p(R))
+            dh_in = dh_a if dh_out is not dh_a else dh_b
+            a.d_dh_out = None if dh_out is None else dh_out.data_ptr()
+            a.d_fg, a.d_dh_in = fg_all[i].data_ptr(), dh_in.data_ptr()
+            a.d_wrs_rows, a.d_wfg_bwd = wrs_rows.data_ptr(), wfg_bwd.data_ptr()
+            a.dilation, a.in_start, a.out_start = d, in_s, out_s
+            a.gs_out, a.gz, a.gs_in = gs_out, gz, gs_in
+            native.check(lib.wn_block_bwd_data(ctypes.byref(a), stream), f"block bwd {i}")
+            # weight gradients: plain GEMMs over (frames x channels) slices
+            zs = zbuf[:, ds_start:, :]
+            grads[f"skip_convs.{i}.weight"] = torch.einsum("bts,btc->sc", dskip, zs).unsqueeze(-1)
+            if bs is not None:
+                grads[f"skip_convs.{i}.bias"] = dskip.sum((0, 1))
+            if dh_out is not None and id_start < L:
+                grads[f"residual_convs.{i}.weight"] = torch.einsum("btr,btc->rc", dh_out[:, id_start:, :],
+                                                                   zbuf[:, id_start:, :]).unsqueeze(-1)
+                if br is not None:
+                    grads[f"residual_convs.{i}.bias"] = dh_out[:, id_start:, :].sum((0, 1))
+            else:
+                grads[f"residual_convs.{i}.weight"] = torch.zeros_like(wr)
+                if br is not None:
+                    grads[f"residual_convs.{i}.bias"] = torch.zeros_like(br)
+            gwf, gwg = torch.empty_like(wf), torch.empty_like(wg)
+            h_in = h_all[i]
+            for j in range(k):
+                sh = (k - 1 - j) * d
+                lo = max(gz, in_s + sh)                       # frames whose tap j lands on real (non-padded) input
+                if lo < L:
+                    g2 = torch.einsum("btn,btr->nr", dfg[:, lo:, :], h_in[:, lo - sh:L - sh, :])
+                else:
+                    g2 = torch.zeros(2 * D, R, **f32)
+                gwf[:, :, j], gwg[:, :, j] = g2[:D], g2[D:]
+            grads[f"filter_convs.{i}.weight"], grads[f"gate_convs.{i}.weight"] = gwf, gwg
+            if bf is not None:
+                bsum = dfg[:, gz:, :].sum((0, 1))
+                grads[f"filter_convs.{i}.bias"], grads[f"gate_convs.{i}.bias"] = bsum[:D].clone(), bsum[D:].clone()
+            if reducer is not None:
+                reducer.reduce_async([grads.get(f"{n}.{i}.{wb}") for n in ("filter_convs", "gate_convs", "residual_convs",
+                                                                         "skip_convs") for wb in ("weight", "bias")])
+            dh_out, gs_out = dh_in, gs_in
+        # ---------------- start conv
+        dh0 = dh_out[:, gs_out:, :]
+        x = saved["x"]
+        if saved["index_input"]:
+            table = torch.zeros(Cc, R, **f32)
+            table.index_add_(0, x[:, gs_out:].reshape(-1).long(), dh0.reshape(-1, R))
+            grads["start_conv.weight"] = table.t().contiguous().unsqueeze(-1)
+        else:
+            grads["start_conv.weight"] = torch.einsum("btr,bct->rc", dh0, x[:, :, gs_out:]).unsqueeze(-1)
+        if P["start"][1] is not None:
+            grads["start_conv.bias"] = dh0.sum((0, 1))
+        if reducer is not None:
+            reducer.reduce_async([grads["start_conv.weight"], grads.get("start_conv.bias")])
+            reducer.wait_all()
+        return grads
 
     # ------------------------------------------------------------------ sampler
     def sampler(self, n_streams):
@@ -215,19 +354,39 @@ class _Runtime:
         self.samplers[n_streams] = s
         return s
 
+    def generate_resident(self, s, d_first, n_given, num_samples, temperature, regularize, d_out, d_uni=None,
+                          d_forced=None, d_logits=None, t0=0, n_evals=None, reset=True):
+        """Launch the sampler on buffers that already live on the device (no host<->device traffic, no sync)."""
+        lib = native.lib()
+        stream = torch.cuda.current_stream(self.device()).cuda_stream
+        if reset:
+            native.check(lib.wn_gen_reset(s["handle"], stream), "gen reset")
+            mode = getattr(self, "gen_mode", None)            # None: library default (flag-in-data exchange)
+            if mode is not None:
+                native.check(lib.wn_gen_set_mode(s["handle"], int(mode)), "gen mode")
+        args = native.GenRunArgs()
+        args.d_first, args.n_given = d_first.data_ptr(), n_given
+        args.d_forced, args.d_uniforms = native.ptr(d_forced), native.ptr(d_uni)
+        args.d_out_idx, args.d_out_logits = d_out.data_ptr(), native.ptr(d_logits)
+        args.n_samples = num_samples
+        args.temperature, args.regularize = float(temperature), float(regularize)
+        total = n_given - 1 + num_samples
+        args.t0, args.n_evals = t0, (total - t0 if n_evals is None else n_evals)
+        if args.n_evals > 0:
+            native.check(lib.wn_gen_run(s["handle"], ctypes.byref(args), stream), "gen run")
+        return t0 + args.n_evals
+
     def generate(self, num_samples, first, temperature, regularize, uniforms=None, forced=None,
                  want_logits=False, callbacks=None):
         """first: (NS, n_given) int array.  Returns (indices (NS, num_samples) int64 ndarray, logits or None, t_end).
         callbacks: optional list of (eval_index, fn) -- fn() is called once evaluations <= eval_index are done."""
-        m, lib = self.model, native.lib()
+        m = self.model
         dev = self.device()
         first = np.ascontiguousarray(first, dtype=np.int32)
         NS, n_given = first.shape
         if n_given < 1:
             raise RuntimeError("first_samples must hold at least one sample")
         s = self.sampler(NS)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        native.check(lib.wn_gen_reset(s["handle"], stream), "gen reset")
         d_first = torch.from_numpy(first).to(dev, non_blocking=True)
         d_out = torch.zeros(NS, max(num_samples, 1), device=dev, dtype=torch.int32)
         d_uni = d_forced = d_logits = None
@@ -242,29 +401,48 @@ class _Runtime:
             d_forced = torch.from_numpy(forced).to(dev, non_blocking=True)
         if want_logits:
             d_logits = torch.zeros(NS, max(num_samples, 1), m.classes, device=dev, dtype=torch.float32)
-        args = native.GenRunArgs()
-        args.d_first, args.n_given = d_first.data_ptr(), n_given
-        args.d_forced, args.d_uniforms = native.ptr(d_forced), native.ptr(d_uni)
-        args.d_out_idx, args.d_out_logits = d_out.data_ptr(), native.ptr(d_logits)
-        args.n_samples = num_samples
-        args.temperature, args.regularize = float(temperature), float(regularize)
         total_evals = n_given - 1 + num_samples
-        t = 0
+        common = dict(d_uni=d_uni, d_forced=d_forced, d_logits=d_logits)
+        t, first_launch = 0, True
         for upto, fn in sorted(callbacks or [], key=lambda c: c[0]):
             n = min(upto + 1, total_evals) - t
-            if n > 0:
-                args.t0, args.n_evals = t, n
-                native.check(lib.wn_gen_run(s["handle"], ctypes.byref(args), stream), "gen run")
-                t += n
+            if n > 0 or first_launch:
+                t = self.generate_resident(s, d_first, n_given, num_samples, temperature, regularize, d_out,
+                                           t0=t, n_evals=max(n, 0), reset=first_launch, **common)
+                first_launch = False
             torch.cuda.current_stream(dev).synchronize()
             fn()
-        if total_evals - t > 0:
-            args.t0, args.n_evals = t, total_evals - t
-            native.check(lib.wn_gen_run(s["handle"], ctypes.byref(args), stream), "gen run")
+        if total_evals - t > 0 or first_launch:
+            self.generate_resident(s, d_first, n_given, num_samples, temperature, regularize, d_out,
+                                   t0=t, n_evals=total_evals - t, reset=first_launch, **common)
         idx = d_out[:, :num_samples].cpu().numpy().astype(np.int64)      # device->host read; synchronises
+        native.check(native.lib().wn_gen_check(s["handle"], torch.cuda.current_stream(dev).cuda_stream), "gen check")
         logits = d_logits[:, :num_samples].cpu().numpy() if want_logits else None
         self.last_run = dict(evals=total_evals, sampler=s)
+        self.h2d_bytes_last = first.nbytes + (uniforms.nbytes if d_uni is not None else 0) + \
+            (forced.nbytes if d_forced is not None else 0)
+        self.d2h_bytes_last = NS * num_samples * 4 + (logits.nbytes if want_logits else 0)
         return idx, logits, total_evals
+
+
+class _StackFunction(torch.autograd.Function):
+    """forward()/wavenet() as one autograd node: parameters in, logits out; the input carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, model, x, out_len, index_input, *params):
+        saved = {}
+        with torch.no_grad():
+            y = model._runtime().stack_forward(x, out_len, index_input=index_input, save=saved)
+        ctx.model, ctx.saved = model, saved
+        ctx.names = [n for n, _ in model.named_parameters()]
+        return y
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        with torch.no_grad():
+            g = ctx.model._runtime().stack_backward(ctx.saved, dlogits)
+        ctx.saved = None
+        return (None, None, None, None) + tuple(g.get(n) for n in ctx.names)
 
 
 class WaveNetModel(nn.Module):
@@ -364,13 +542,12 @@ class WaveNetModel(nn.Module):
         queue.enqueue(input.data[0])
         return queue.dequeue(num_deq=self.kernel_size, dilation=dilation).unsqueeze(0)
 
-    def _stack(self, input, out_len):
-        needs_grad = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad:
-            raise NotImplementedError(
-                "wavenet_b200: the backward kernels are not part of this build yet; call forward() under "
-                "torch.no_grad() (training forward + inference) ")
-        return self._runtime().stack_forward(input, out_len)
+    def _stack(self, input, out_len, index_input=False):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if input.requires_grad:
+                raise NotImplementedError("wavenet_b200: no gradient with respect to the input (it is one-hot data)")
+            return _StackFunction.apply(self, input, out_len, index_input, *self.parameters())
+        return self._runtime().stack_forward(input, out_len, index_input=index_input)
 
     def forward(self, input):
         """(N, classes, L) -> (N * output_length, classes): logits of the last ``output_length`` frames."""
@@ -379,9 +556,7 @@ class WaveNetModel(nn.Module):
     def forward_indices(self, indices):
         """Same as ``forward(one_hot(indices))`` bit for bit, from (N, L) uint8 / int64 mu-law indices:
         start_conv on a one-hot column is a gather of one weight column."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("wavenet_b200: backward kernels are not part of this build yet; use torch.no_grad()")
-        return self._runtime().stack_forward(indices, self.output_length, index_input=True)
+        return self._stack(indices, self.output_length, index_input=True)
 
     # ------------------------------------------------------------------ generation
     def generate(self, num_samples, first_samples=None, temperature=1.):

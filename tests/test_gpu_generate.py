@@ -126,3 +126,26 @@ def test_progress_callback_schedule_and_queue_export(golden):
     last_in = int(g["gen_argmax_idx"][22])               # input of the last evaluation = sample chosen before it
     col = q0.data[:, (evals - 1) % q0.max_length]
     assert torch.allclose(col, w[:, last_in] + b, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["odd_bias", "deep", "k3"])
+def test_exchange_modes_agree(golden, name):
+    """The flag-in-data kernel (default) and the grid-barrier kernel implement the same schedule."""
+    g = golden(f"net_{name}.npz")
+    m = build_model(g)
+    rng = np.random.RandomState(11)
+    firsts = rng.randint(0, 256, size=(3, 25))
+    uni = rng.random_sample((3, 40))
+    res = {}
+    for mode in (0, 1):
+        m._runtime().gen_mode = mode
+        res[mode] = m.generate_fast_batch(40, firsts, temperature=0.7, uniforms=uni, forced=None, return_logits=True)
+        _, lg = m.generate_fast_batch(24, g["first"][None, :], temperature=0.0, forced=g["gen_argmax_idx"][None, :],
+                                      return_logits=True)
+        assert rel_err(lg[0], g["gen_argmax_logits"]) < TOL
+    m._runtime().gen_mode = None
+    (i0, l0), (i1, l1) = res[0], res[1]
+    same = (i0 == i1).all(axis=1)
+    for s in range(3):                      # streams may only part ways after a step where the logits differ by rounding
+        n = 40 if same[s] else int(np.nonzero(i0[s] != i1[s])[0][0])
+        assert n >= 1 and rel_err(l0[s, :n + 1], l1[s, :n + 1]) < 1e-5
