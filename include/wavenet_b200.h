@@ -92,6 +92,26 @@ typedef struct wn_block_args {
 } wn_block_args;
 int wn_block_fwd(const wn_block_args* a, void* stream);
 
+/* ---------------------------------------------------------------- (T) the same block on the tensor cores
+ * tcgen05.mma kind::tf32 with 3xTF32 operand splitting (hi*hi + lo*hi + hi*lo, fp32 accumulation in tensor memory):
+ * fp32-class accuracy (~1e-6 relative) at tensor-core rate.  Two launches per block (conv+gate -> z, then the 1x1s);
+ * d_z is a caller-provided (B,L,D) workspace.  Shapes: R % 256 == 0, S % 256 == 0, D % 128 == 0 (wn_tc_supported).
+ * Weights are packed K-major and pre-split: d_wa [2][2D][k*R] (rows in 256-wide tiles: 128 filter channels then the
+ * same 128 gate channels; column j*R+r = tap j of input channel r; [0]=hi, [1]=lo), d_ba [2D] in the same row order,
+ * d_wb [2][R+S][D] (residual rows then skip rows), d_bb [R+S]. */
+int wn_tc_supported(int R, int D, int S, int k);
+int wn_tc_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
+                             const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
+                             int R, int D, int S, int k, float* d_wa, float* d_ba, float* d_wb, float* d_bb, void* stream);
+typedef struct wn_tc_block_args {
+    const float* d_h_in; float* d_h_out; float* d_skip; float* d_z;
+    const float* d_wa; const float* d_ba; const float* d_wb; const float* d_bb;
+    int B, L, R, D, S, k, dilation;
+    int in_start, out_start, skip_start, skip_init;
+    float* d_fg_save;
+} wn_tc_block_args;
+int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream);
+
 /* ---------------------------------------------------------------- (T) head
  * replaces relu -> end_conv_1 -> relu -> end_conv_2 (wavenet_model.py:167-169) and forward()'s
  * slice/transpose/view (:191-196): logits (B*out_len, classes) for the LAST out_len frames only.

@@ -17,6 +17,7 @@
 // Exchanged vectors are read with ld.global.cg (L2) because L1 is not coherent across SMs.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -352,19 +353,22 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
 // it waits for data; they are the same rows every evaluation, in the parameters' own (state_dict) layout.
 constexpr long long GEN_TIMEOUT_CYCLES = 6000000000LL;     // ~3 s: a missing tag aborts the launch instead of hanging
 
+// one naturally aligned 64-bit word = single-copy atomic; gpu scope keeps the traffic at the L2
 __device__ __forceinline__ uint2 ld_pair(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((unsigned)(w & 0xffffffffull), (unsigned)(w >> 32));
 }
 __device__ __forceinline__ void st_pair(uint2* p, float val, unsigned tag) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(tag) : "memory");
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(val);
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ float poll_pair(const uint2* p, unsigned tag, int* err, int* abort_s) {
     uint2 v = ld_pair(p);
     if (v.y != tag) {
         const long long t0 = clock64();
         do {
+            __nanosleep(40);                      // keep the polling storm off the L2 slice the producer writes to
             v = ld_pair(p);
             if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
                 *reinterpret_cast<volatile int*>(err) = 1;
@@ -454,10 +458,11 @@ __device__ __forceinline__ StageDesc stage_desc(const GenParams& p, int st, bool
     else { d.n = nC; d.K = p.E; d.n_first = d.n; }
     return d;
 }
-__device__ __forceinline__ const float* stage_row(const GenParams& p, int st, const StageDesc& d, int i, int cta, int G) {
+__device__ __forceinline__ const float* stage_row(const GenParams& p, const GenLayer* layers, int st, const StageDesc& d,
+                                                  int i, int cta, int G) {
     const int NL = p.n_layers;
     if (st < 2 * NL) {
-        const GenLayer& L = p.layers[st >> 1];
+        const GenLayer& L = layers[st >> 1];
         if ((st & 1) == 0) return ((i & 1) ? L.wg : L.wf) + (size_t)((i >> 1) * G + cta) * d.K;
         if (i < d.n_first) return L.wr + (size_t)(i * G + cta) * d.K;
         return L.ws + (size_t)((i - d.n_first) * G + cta) * d.K;
@@ -477,7 +482,8 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
     double* cdf = reinterpret_cast<double*>(prob + GEN_WARPS * p.C);   // [GEN_WARPS][C]
     float* wbuf = reinterpret_cast<float*>(cdf + GEN_WARPS * p.C);     // [n_wslots][wslot_floats]
     unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
-    int* idx_s = reinterpret_cast<int*>(fullb + 8);                     // current input index per stream [NS]
+    GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);           // per-layer table, copied from global once
+    int* idx_s = reinterpret_cast<int*>(lay_s + p.n_layers);            // current input index per stream [NS]
     int* abort_s = idx_s + p.NS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -492,6 +498,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
     const int NSLOT = p.n_wslots;
 
     for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.cur_idx[s];
+    {
+        const int* src = reinterpret_cast<const int*>(p.layers);
+        int* dst = reinterpret_cast<int*>(lay_s);
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT) dst[i] = src[i];
+    }
     if (tid == 0) {
         *abort_s = 0;
         if (PREFETCH)
@@ -504,18 +515,18 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
     int pf_ev = 0, pf_st = 0;                 // producer cursor
     long long pf_q = 0, cons_q = 0;
     auto stages_in_eval = [&](int ev) { return (p.t0 + ev >= p.n_given - 1) ? 2 * NL + 2 : 2 * NL; };
-    auto produce_one = [&]() {                // thread 0 only
+    auto produce_one = [&]() {                // the last thread only (it has no epilogue work)
         if (pf_ev >= p.n_evals) return;
         const bool wh = (p.t0 + pf_ev >= p.n_given - 1);
         const StageDesc d = stage_desc(p, pf_st, wh, nD, nR, nS, nE, nC);
         const int slot = (int)(pf_q % NSLOT);
         mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
         float* dst = wbuf + (size_t)slot * p.wslot_floats;
-        for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
+        for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
         ++pf_q;
         if (++pf_st >= stages_in_eval(pf_ev)) { pf_st = 0; ++pf_ev; }
     };
-    if (PREFETCH && tid == 0)
+    if (PREFETCH && tid == GEN_NT - 1)
         for (int i = 0; i < NSLOT; ++i) produce_one();
 
     // One dot-product stage: rows of `st` times the vectors xs[s][0..K) -> part[item][kpart][s]; all 8 warps work,
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
             for (int s0 = 0; s0 < NS; s0 += SB) {
                 float acc[SB];
                 if (PREFETCH) row_dot_part<SB, true>(wslot + (size_t)it * d.K, xs, d.K, k0, k1, NS, s0, lane, acc);
-                else row_dot_part<SB, false>(stage_row(p, st, d, it, cta, G), xs, d.K, k0, k1, NS, s0, lane, acc);
+                else row_dot_part<SB, false>(stage_row(p, lay_s, st, d, it, cta, G), xs, d.K, k0, k1, NS, s0, lane, acc);
                 if (lane == 0) {
 #pragma unroll
                     for (int j = 0; j < SB; ++j)
@@ -570,7 +581,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         if (*abort_s) return;
 
         for (int l = 0; l < NL; ++l) {
-            const GenLayer L = p.layers[l];
+            const GenLayer& L = lay_s[l];
             uint2* ring = p.ringLL + L.ring_off;
             const int slot_t = t % L.ring_len;
             // ---- stage-1 inputs: regA[s][r*k + j] = tap j of channel r (tap k-1 = the value just enqueued)
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
             StageDesc d1 = stage_desc(p, 2 * l, want_head, nD, nR, nS, nE, nC);
             run_stage(2 * l, d1, regA, nw);
             __syncthreads();
-            if (PREFETCH && tid == 0) produce_one();
+            if (PREFETCH && tid == GEN_NT - 1) produce_one();
             uint2* zl = p.zLL + ((size_t)(par * NL + l) * NS) * D;
             for (int i = tid; i < nD * NS; i += GEN_NT) {
                 const int ci = i / NS, s = i - ci * NS, c = ci * G + cta;
@@ -613,12 +624,12 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
             if (*abort_s) return;
             run_stage(2 * l + 1, d2, regB, nw);
             __syncthreads();
-            if (PREFETCH && tid == 0) produce_one();
+            if (PREFETCH && tid == GEN_NT - 1) produce_one();
             for (int i = tid; i < d2.n * NS; i += GEN_NT) {
                 const int it = i / NS, s = i - it * NS;
                 if (it < d2.n_first) {
                     const int row = it * G + cta;
-                    const GenLayer& Ln = p.layers[l + 1];
+                    const GenLayer& Ln = lay_s[l + 1];
                     const float v = sum_parts(it, nw, s) + (L.br ? __ldg(L.br + row) : 0.f);
                     const float cur = regA[(size_t)s * K1 + row * k + (k - 1)];
                     st_pair(p.ringLL + Ln.ring_off + ((size_t)(t % Ln.ring_len) * NS + s) * R + row, v + cur, tag);
@@ -647,7 +658,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         if (*abort_s) return;
         run_stage(2 * NL, dA, regA, nw);
         __syncthreads();
-        if (PREFETCH && tid == 0) produce_one();
+        if (PREFETCH && tid == GEN_NT - 1) produce_one();
         uint2* yl = p.y1LL + (size_t)par * NS * E;
         for (int i = tid; i < nE * NS; i += GEN_NT) {
             const int it = i / NS, s = i - it * NS, row = it * G + cta;
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         if (*abort_s) return;
         run_stage(2 * NL + 1, dB, regB, nw);
         __syncthreads();
-        if (PREFETCH && tid == 0) produce_one();
+        if (PREFETCH && tid == GEN_NT - 1) produce_one();
         uint2* lgl = p.logitLL + (size_t)par * NS * C;
         for (int i = tid; i < nC * NS; i += GEN_NT) {
             const int it = i / NS, s = i - it * NS, row = it * G + cta;
@@ -859,6 +870,10 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     const int per = ceil_div(rows_max, sms);
     int G = ceil_div(rows_max, per);
     if (G > sms) G = sms;
+    if (const char* e = getenv("WN_GEN_GRID")) {            // tuning knob: fewer, fatter CTAs
+        const int v = atoi(e);
+        if (v >= 1 && v <= G) G = v;
+    }
     if (G < 1) G = 1;
     h->grid = G;
     h->sm_count = sms;
@@ -903,13 +918,15 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
         if ((long long)nCm * s->E > slot) slot = (long long)nCm * s->E;
         slot = (slot + 3) / 4 * 4;
         const size_t base = sizeof(float) * ((size_t)regA_ll + p.regB + p.part_n + p.skacc_n + (size_t)GEN_WARPS * s->classes) +
-                            sizeof(double) * (size_t)GEN_WARPS * s->classes + 64 + sizeof(int) * (size_t)(NS + 4);
+                            sizeof(double) * (size_t)GEN_WARPS * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
+                            sizeof(int) * (size_t)(NS + 4);
         const bool k_ok = ((s->k * s->R) % 4 == 0) && (s->D % 4 == 0) && (s->S % 4 == 0) && (s->E % 4 == 0);
         int nslots = 0;
         if (k_ok && base < (size_t)smem_optin) {
             long long fit = ((long long)smem_optin - (long long)base) / (slot * 4);
             nslots = fit >= 4 ? 4 : (fit >= 2 ? (int)fit : 0);
         }
+        if (getenv("WN_GEN_NOPREFETCH")) nslots = 0;        // tuning knob: read weights through L2 instead
         p.wslot_floats = (int)slot;
         p.n_wslots = nslots;
         h->smem_ll = base + (size_t)nslots * slot * 4;

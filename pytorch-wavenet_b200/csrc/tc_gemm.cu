@@ -1,0 +1,474 @@
+// tc_gemm.cu -- tensor-core (tcgen05 / TMEM / TMA) form of the training block: exact-fp32-class numerics through
+// 3xTF32 (hi/lo split of both operands, fp32 accumulation in tensor memory).
+//
+// Same mathematics and frames layout as train_fwd.cu (reference wavenet_model.py:142-165), split in two launches
+// per block because the gated activation cannot stay on chip in split form (128 frames x 256 ch x {hi,lo} = 256 KB):
+//   pass A   FG[128 frames x 256] per tile = A[128 x kR] * Wa^T      A rows = taps of h_in (TMA boxes shifted by
+//            the dilation; frames left of in_start come back as zeros from the TMA out-of-bounds fill)
+//            epilogue: z = tanh(F+bf) * sigmoid(G+bg)  -> z (B,L,D)  [+ optional f,g for the backward]
+//   pass B   [O|S][128 x 256] per tile = z[128 x D] * Wb^T ;  h_out = O + br + h_in,  skip (+)= S + bs
+// Kernel anatomy (one CTA per SM, persistent over (sequence, 128-frame tile) items, 256 threads):
+//   warp 0      TMA producer: per K slab (32 fp32 = one 128B swizzle row) loads A raw, W_hi, W_lo
+//   warp 1      allocates TMEM, issues tcgen05.mma kind::tf32 (M128 N256 K8): hi*hi + lo*hi + hi*lo per k-step
+//   warps 2-3   splitter: rewrite the landed A slab as hi = rna_tf32(x) in place and lo = x - hi in a second buffer
+//   warps 4-7   epilogue: tcgen05.ld the finished accumulator (2 x 256 TMEM columns, double buffered) and store
+// mbarriers: full (TMA landed), split (lo ready), empty (MMAs of the stage retired), acc_full / acc_empty.
+#include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+
+namespace wn {
+namespace tc {
+
+constexpr int BM = 128;            // frames per tile (UMMA M)
+constexpr int BN = 256;            // output columns per tile (UMMA N)
+constexpr int BK = 32;             // fp32 per K slab = 128 bytes = one swizzle row
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;          // 16 KB
+constexpr int W_BYTES = BN * BK * 4;          // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 96 KB
+constexpr int NTHREADS = 256;
+constexpr unsigned SPIN_LIMIT = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned done, spins = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) asm volatile("trap;");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(unsigned* slot_in_smem, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot_in_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned addr, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc,
+                                          unsigned accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {       // arrives when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr >> 4) & 0x3fff);            // start address, 16-byte units
+    d |= (unsigned long long)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(1024 >> 4) << 32;                  // stride byte offset between 8-row atoms
+    d |= (unsigned long long)1 << 46;                            // descriptor version (Blackwell)
+    d |= (unsigned long long)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32, both K-major, M=128, N=256
+__host__ __device__ constexpr unsigned make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+enum { EPI_GATE = 0, EPI_RES_SKIP = 1 };
+
+struct TcParams {
+    int B, L, t_begin;            // frames [t_begin, L) of every sequence are produced
+    int taps, dil, C;             // A row = taps x C channels; tap j reads frame t - (taps-1-j)*dil
+    int a_origin;                 // frame that coordinate 0 of the A tensor map corresponds to
+    int n_tiles, n_total;         // output columns = n_tiles * BN; the W map holds hi rows [0,n_total) then lo rows
+    // epilogue
+    const float* bias;            // [n_total] in tile column order
+    float* out0;                  // GATE: z (B,L,D)            RES_SKIP: h_out (B,L,R)
+    float* out1;                  // GATE: fg_save (B,L,2D)|0   RES_SKIP: skip (B,L-skip_start,S)
+    const float* res;             // RES_SKIP: h_in (B,L,R)
+    int D, R, S, in_start, skip_start, skip_init;
+};
+
+__device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* stage_mem = base;                                           // STAGES * STAGE_BYTES
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + STAGES * STAGE_BYTES);
+    unsigned long long* full = bars;                 // [STAGES]
+    unsigned long long* split = bars + STAGES;       // [STAGES]
+    unsigned long long* empty = bars + 2 * STAGES;   // [STAGES]
+    unsigned long long* acc_full = bars + 3 * STAGES;      // [2]
+    unsigned long long* acc_empty = bars + 3 * STAGES + 2; // [2]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * STAGES + 4);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                   // [n_total]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_tiles = (p.L - p.t_begin + BM - 1) / BM;
+    const int items = p.B * m_tiles;
+    const int slabs_per_tap = p.C / BK;
+    const int slabs = p.taps * slabs_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, 64); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    for (int i = tid; i < p.n_total; i += NTHREADS) bias_s[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (elect_one()) {
+            unsigned it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int b = item / m_tiles, t0 = p.t_begin + (item % m_tiles) * BM;
+                for (int nt = 0; nt < p.n_tiles; ++nt)
+                    for (int sl = 0; sl < slabs; ++sl, ++it) {
+                        const int st = it % STAGES;
+                        const unsigned ph = (it / STAGES) & 1;
+                        mbar_wait(empty + st, ph ^ 1);
+                        unsigned char* sm = stage_mem + st * STAGE_BYTES;
+                        const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
+                        mbar_expect_tx(full + st, A_BYTES + 2 * W_BYTES);
+                        tma_load_3d(sm, &mapA, c0, t0 - (p.taps - 1 - j) * p.dil - p.a_origin, b, full + st);
+                        tma_load_2d(sm + 2 * A_BYTES, &mapW, sl * BK, nt * BN, full + st);
+                        tma_load_2d(sm + 2 * A_BYTES + W_BYTES, &mapW, sl * BK, p.n_total + nt * BN, full + st);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr unsigned idesc = make_idesc();
+        unsigned it = 0, tile = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x)
+            for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
+                const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
+                mbar_wait(acc_empty + ab, aph ^ 1);
+                tc_fence_after();
+                const unsigned d_tmem = tmem_base + ab * BN;
+                for (int sl = 0; sl < slabs; ++sl, ++it) {
+                    const int st = it % STAGES;
+                    const unsigned ph = (it / STAGES) & 1;
+                    mbar_wait(split + st, ph);                   // TMA landed and the splitter produced hi/lo
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const unsigned sa = s32(stage_mem + st * STAGE_BYTES);
+                        const unsigned long long a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_BYTES);
+                        const unsigned long long w_hi = smem_desc(sa + 2 * A_BYTES), w_lo = smem_desc(sa + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {    // 8 tf32 = 32 bytes = 2 descriptor units per k-step
+                            const unsigned long long o = (unsigned long long)(kk * 2);
+                            umma_tf32(d_tmem, a_hi + o, w_hi + o, idesc, (sl | kk) != 0);
+                            umma_tf32(d_tmem, a_lo + o, w_hi + o, idesc, 1);
+                            umma_tf32(d_tmem, a_hi + o, w_lo + o, idesc, 1);
+                        }
+                        umma_commit(empty + st);                 // stage reusable once these MMAs retire
+                        if (sl == slabs - 1) umma_commit(acc_full + ab);
+                    }
+                    __syncwarp();
+                }
+            }
+    } else if (warp < 4) {
+        // ================================================================= splitter (64 threads)
+        const int st_tid = tid - 64;
+        unsigned it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x)
+            for (int nt = 0; nt < p.n_tiles; ++nt)
+                for (int sl = 0; sl < slabs; ++sl, ++it) {
+                    const int st = it % STAGES;
+                    const unsigned ph = (it / STAGES) & 1;
+                    mbar_wait(full + st, ph);
+                    float4* hi = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES + A_BYTES);
+#pragma unroll 4
+                    for (int i = st_tid; i < A_BYTES / 16; i += 64) {
+                        const float4 x = hi[i];
+                        float4 h, l;
+                        unsigned u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                    mbar_arrive(split + st);
+                }
+    } else {
+        // ================================================================= epilogue (warps 4..7 = TMEM lane quadrants 0..3)
+        const int q = warp - 4, row = q * 32 + lane;
+        unsigned tile = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int b = item / m_tiles, t0 = p.t_begin + (item % m_tiles) * BM;
+            const int t = t0 + row;
+            const bool live = t < p.L;
+            for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
+                const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
+                mbar_wait(acc_full + ab, aph);
+                tc_fence_after();
+                const unsigned taddr = tmem_base + ab * BN + ((unsigned)(q * 32) << 16);
+                if (EPI == EPI_GATE) {
+                    // tile columns: [0,128) = F of channels 128*nt.., [128,256) = G of the same channels
+                    float* zrow = p.out0 + ((size_t)b * p.L + t) * p.D + nt * 128;
+                    float* fgrow = p.out1 ? p.out1 + ((size_t)b * p.L + t) * (2 * p.D) + nt * 128 : nullptr;
+                    const float* bt = bias_s + nt * BN;
+#pragma unroll 1
+                    for (int c = 0; c < 128; c += 16) {
+                        float f[16], g[16];
+                        tmem_ld16(taddr + c, f);
+                        tmem_ld16(taddr + 128 + c, g);
+                        tmem_ld_wait();
+                        if (live) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                f[i] = tanhf(f[i] + bt[c + i]);
+                                g[i] = sigmoid_tc(g[i] + bt[128 + c + i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(zrow + c + i) =
+                                    make_float4(f[i] * g[i], f[i + 1] * g[i + 1], f[i + 2] * g[i + 2], f[i + 3] * g[i + 3]);
+                            if (fgrow) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    *reinterpret_cast<float4*>(fgrow + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                                    *reinterpret_cast<float4*>(fgrow + p.D + c + i) = make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // tile columns: global output column n = nt*256 + c; n < R residual, else skip channel n - R
+                    const int n0 = nt * BN;
+                    const bool is_res = n0 < p.R;
+                    const float* bt = bias_s + n0;
+                    const bool skip_live = live && t >= p.skip_start;
+                    float* orow = is_res ? p.out0 + ((size_t)b * p.L + t) * p.R + n0
+                                         : p.out1 + ((size_t)b * (p.L - p.skip_start) + (t - p.skip_start)) * p.S + (n0 - p.R);
+                    const float* rrow = p.res + ((size_t)b * p.L + t) * p.R + n0;
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c, v);
+                        tmem_ld_wait();
+                        if (is_res ? live : skip_live) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float4 o = make_float4(v[i] + bt[c + i], v[i + 1] + bt[c + i + 1], v[i + 2] + bt[c + i + 2],
+                                                       v[i + 3] + bt[c + i + 3]);
+                                if (is_res) {
+                                    if (t >= p.in_start) {
+                                        const float4 x = __ldg(reinterpret_cast<const float4*>(rrow + c + i));
+                                        o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                                    }
+                                } else if (!p.skip_init) {
+                                    const float4 x = *reinterpret_cast<const float4*>(orow + c + i);
+                                    o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                                }
+                                *reinterpret_cast<float4*>(orow + c + i) = o;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty + ab);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- weight packing
+// pass A: rows in tile order (tile p: F channels 128p.., then G channels 128p..), columns kk = j*R + r; hi then lo copy
+__global__ void pack_a_kernel(const float* __restrict__ wf, const float* __restrict__ wg, const float* __restrict__ bf,
+                              const float* __restrict__ bg, int R, int D, int k, float* __restrict__ wa, float* __restrict__ ba) {
+    const int K = k * R, N = 2 * D;
+    const long long total = (long long)N * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / K), kk = (int)(i % K);
+        const int tile = n / 256, w = n % 256, ch = tile * 128 + (w & 127);
+        const bool is_g = w >= 128;
+        const int j = kk / R, r = kk % R;
+        const float v = (is_g ? wg : wf)[((size_t)ch * R + r) * k + j];
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float hi = __uint_as_float(u);
+        wa[i] = hi;
+        wa[total + i] = v - hi;
+        if (kk == 0) {
+            const float* bsrc = is_g ? bg : bf;
+            ba[n] = bsrc ? bsrc[ch] : 0.f;
+        }
+    }
+}
+// pass B: rows = residual outputs then skip outputs, columns = dilation channel; hi then lo copy
+__global__ void pack_b_kernel(const float* __restrict__ wr, const float* __restrict__ ws, const float* __restrict__ br,
+                              const float* __restrict__ bs, int R, int D, int S, float* __restrict__ wb, float* __restrict__ bb) {
+    const int N = R + S;
+    const long long total = (long long)N * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / D), c = (int)(i % D);
+        const float v = n < R ? wr[(size_t)n * D + c] : ws[(size_t)(n - R) * D + c];
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float hi = __uint_as_float(u);
+        wb[i] = hi;
+        wb[total + i] = v - hi;
+        if (c == 0) bb[n] = n < R ? (br ? br[n] : 0.f) : (bs ? bs[n - R] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// activations (B, L, C) fp32: dims {C, L - origin, B}, box {32, 128, 1}; frames left of `origin` are out of bounds -> zeros
+static int make_act_map(CUtensorMap* m, const float* base, int B, int L, int C, int origin) {
+    EncodeTiledFn fn = encode_fn();
+    WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)(L - origin), (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)L * C * 4};
+    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(base + (size_t)origin * C), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+    return 0;
+}
+// weights (rows, K) fp32 K-major: dims {K, rows}, box {32, 256}
+static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
+    EncodeTiledFn fn = encode_fn();
+    WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    return 0;
+}
+
+static size_t tc_smem_bytes(int n_total) { return 1024 + (size_t)STAGES * STAGE_BYTES + 256 + sizeof(float) * n_total; }
+
+template <int EPI>
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParams& p, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = tc_smem_bytes(p.n_total);
+    WN_CUDA(cudaFuncSetAttribute(frames_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int items = p.B * ((p.L - p.t_begin + BM - 1) / BM);
+    const int grid = items < sms ? items : sms;
+    frames_gemm_tc<EPI><<<grid, NTHREADS, smem, st>>>(mA, mW, p);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" int wn_tc_supported(int R, int D, int S, int k) {
+    return (R % 256 == 0) && (S % 256 == 0) && (D % 128 == 0) && k >= 1 && (R + S) <= 2048 && 2 * D <= 2048;
+}
+
+extern "C" int wn_tc_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
+                                        const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs, int R,
+                                        int D, int S, int k, float* d_wa, float* d_ba, float* d_wb, float* d_bb, void* stream) {
+    WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_wa && d_ba && d_wb && d_bb, WN_E_BADARG, "wn_tc_pack_block_weights: null pointer");
+    WN_REQUIRE(wn_tc_supported(R, D, S, k), WN_E_UNSUPP, "wn_tc_pack_block_weights: shape R=%d D=%d S=%d not supported", R, D, S);
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::pack_a_kernel<<<1024, 256, 0, st>>>(d_wf, d_wg, d_bf, d_bg, R, D, k, d_wa, d_ba);
+    tc::pack_b_kernel<<<512, 256, 0, st>>>(d_wr, d_ws, d_br, d_bs, R, D, S, d_wb, d_bb);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream) {
+    WN_REQUIRE(a, WN_E_BADARG, "wn_tc_block_fwd: null args");
+    WN_REQUIRE(a->d_h_in && a->d_h_out && a->d_skip && a->d_z && a->d_wa && a->d_ba && a->d_wb && a->d_bb, WN_E_BADARG,
+               "wn_tc_block_fwd: null pointer");
+    WN_REQUIRE(wn_tc_supported(a->R, a->D, a->S, a->k), WN_E_UNSUPP, "wn_tc_block_fwd: shape not supported by the tensor-core path");
+    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->in_start >= 0 && a->out_start >= a->in_start &&
+                   a->out_start < a->L && a->skip_start >= a->out_start && a->skip_start < a->L,
+               WN_E_BADARG, "wn_tc_block_fwd: bad frame ranges");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap mA, mWa, mZ, mWb;
+    if (int rc = tc::make_act_map(&mA, a->d_h_in, a->B, a->L, a->R, a->in_start)) return rc;
+    if (int rc = tc::make_w_map(&mWa, a->d_wa, 2 * 2 * a->D, a->k * a->R)) return rc;
+    if (int rc = tc::make_act_map(&mZ, a->d_z, a->B, a->L, a->D, a->out_start)) return rc;
+    if (int rc = tc::make_w_map(&mWb, a->d_wb, 2 * (a->R + a->S), a->D)) return rc;
+    tc::TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.L = a->L; p.t_begin = a->out_start;
+    p.D = a->D; p.R = a->R; p.S = a->S; p.in_start = a->in_start; p.skip_start = a->skip_start; p.skip_init = a->skip_init;
+    // pass A: conv taps + gate
+    p.taps = a->k; p.dil = a->dilation; p.C = a->R; p.a_origin = a->in_start;
+    p.n_total = 2 * a->D; p.n_tiles = p.n_total / tc::BN;
+    p.bias = a->d_ba; p.out0 = a->d_z; p.out1 = a->d_fg_save; p.res = nullptr;
+    if (int rc = tc::launch_tc<tc::EPI_GATE>(mA, mWa, p, st)) return rc;
+    // pass B: residual + skip 1x1
+    p.taps = 1; p.dil = 0; p.C = a->D; p.a_origin = a->out_start;
+    p.n_total = a->R + a->S; p.n_tiles = p.n_total / tc::BN;
+    p.bias = a->d_bb; p.out0 = a->d_h_out; p.out1 = a->d_skip; p.res = a->d_h_in;
+    return tc::launch_tc<tc::EPI_RES_SKIP>(mZ, mWb, p, st);
+}

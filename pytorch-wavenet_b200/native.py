@@ -41,6 +41,14 @@ class HeadBwdArgs(C.Structure):
                 ("skip_start", C.c_int), ("out_len", C.c_int)]
 
 
+class TcBlockArgs(C.Structure):
+    _fields_ = [("d_h_in", C.c_void_p), ("d_h_out", C.c_void_p), ("d_skip", C.c_void_p), ("d_z", C.c_void_p),
+                ("d_wa", C.c_void_p), ("d_ba", C.c_void_p), ("d_wb", C.c_void_p), ("d_bb", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("k", C.c_int),
+                ("dilation", C.c_int), ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int),
+                ("skip_init", C.c_int), ("d_fg_save", C.c_void_p)]
+
+
 class HeadArgs(C.Structure):
     _fields_ = [("d_skip", C.c_void_p), ("d_logits", C.c_void_p),
                 ("d_w1_t", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2_t", C.c_void_p), ("d_b2", C.c_void_p),
@@ -83,6 +91,9 @@ SIGNATURES = {
     "wn_start_fwd_index_i64": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_block_fwd": (C.c_int, [C.POINTER(BlockArgs), C.c_void_p]),
     "wn_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "wn_tc_supported": (C.c_int, [C.c_int] * 4),
+    "wn_tc_pack_block_weights": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p] * 5),
+    "wn_tc_block_fwd": (C.c_int, [C.POINTER(TcBlockArgs), C.c_void_p]),
     "wn_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p]),
     "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
     "wn_gen_workspace_bytes": (C.c_int, [C.POINTER(GenShape), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -58,6 +58,7 @@ class _Runtime:
         self.packed = None
         self.ws = {}
         self.samplers = {}
+        self.block_mode = "auto"     # "auto": tensor-core blocks when the shape allows, "ffma": exact-fp32 SIMT, "tc"
 
     # ------------------------------------------------------------------ weights
     def _params(self):
@@ -100,6 +101,16 @@ class _Runtime:
             native.check(lib.wn_pack_res_skip_weights(wr.data_ptr(), wsk.data_ptr(), native.ptr(br), native.ptr(bs),
                                                       R, D, S, wrs.data_ptr(), brs.data_ptr(), stream), "pack res/skip")
             out["layers"].append((wfg, bfg, wrs, brs))
+            if lib.wn_tc_supported(R, D, S, k):
+                wa = torch.empty(2, 2 * D, k * R, **f32)
+                ba = torch.empty(2 * D, **f32)
+                wb = torch.empty(2, R + S, D, **f32)
+                bb = torch.empty(R + S, **f32)
+                native.check(lib.wn_tc_pack_block_weights(
+                    wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
+                    native.ptr(br), native.ptr(bs), R, D, S, k, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
+                    bb.data_ptr(), stream), "pack tc")
+                out.setdefault("tc_layers", []).append((wa, ba, wb, bb))
 
         def pack1x1(w, b, N, K):
             wt = torch.empty(K, lib.wn_n2p(N), **f32)
@@ -164,20 +175,38 @@ class _Runtime:
         else:
             native.check(lib.wn_start_fwd_dense(x.data_ptr(), ws_t.data_ptr(), bs_p.data_ptr(), h0.data_ptr(),
                                                 B, Cc, L, R, stream), "start")
-        a = native.BlockArgs()
-        a.B, a.L, a.R, a.D, a.S, a.k, a.mode = B, L, R, D, S, k, 0
+        use_tc = self.block_mode != "ffma" and bool(lib.wn_tc_supported(R, D, S, k))
+        if self.block_mode == "tc" and not use_tc:
+            raise RuntimeError(f"wavenet_b200: tensor-core blocks need R%256==0, S%256==0, D%128==0 (got {R},{S},{D})")
+        self.last_block_mode = "tc" if use_tc else "ffma"
+        if use_tc:
+            zkey = ("z", B, L, D)
+            if zkey not in self.ws:
+                self.ws[zkey] = torch.empty(B, L, D, **f32)
+            zws = self.ws[zkey]
+            a = native.TcBlockArgs()
+            a.B, a.L, a.R, a.D, a.S, a.k = B, L, R, D, S, k
+            a.d_z = zws.data_ptr()
+        else:
+            a = native.BlockArgs()
+            a.B, a.L, a.R, a.D, a.S, a.k, a.mode = B, L, R, D, S, k, 0
         a.d_skip, a.skip_start = skip.data_ptr(), plan.skip_start
         src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
         ev = getattr(self, "block_events", None)      # optional (start, end) CUDA events around the block launches
         if ev is not None:
             ev[0].record(torch.cuda.current_stream(dev))
         for i, d in enumerate(dil):
-            wfg, bfg, wrs, brs = W["layers"][i]
             a.d_h_in, a.d_h_out = src.data_ptr(), dst.data_ptr()
-            a.d_wfg_t, a.d_bfg, a.d_wrs_t, a.d_brs = wfg.data_ptr(), bfg.data_ptr(), wrs.data_ptr(), brs.data_ptr()
             a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
             a.d_fg_save = None if save is None else fg_all[i].data_ptr()
-            native.check(lib.wn_block_fwd(ctypes.byref(a), stream), f"block {i}")
+            if use_tc:
+                wa, ba, wb, bb = W["tc_layers"][i]
+                a.d_wa, a.d_ba, a.d_wb, a.d_bb = wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr()
+                native.check(lib.wn_tc_block_fwd(ctypes.byref(a), stream), f"tc block {i}")
+            else:
+                wfg, bfg, wrs, brs = W["layers"][i]
+                a.d_wfg_t, a.d_bfg, a.d_wrs_t, a.d_brs = wfg.data_ptr(), bfg.data_ptr(), wrs.data_ptr(), brs.data_ptr()
+                native.check(lib.wn_block_fwd(ctypes.byref(a), stream), f"block {i}")
             if save is None:
                 src, dst = dst, src
             elif i + 1 < n_layers:
@@ -191,7 +220,7 @@ class _Runtime:
         hd.d_w1_t, hd.d_b1, hd.d_w2_t, hd.d_b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
         hd.B, hd.L, hd.S, hd.E, hd.classes, hd.skip_start, hd.out_len, hd.mode = B, L, S, E, Cc, plan.skip_start, out_len, 0
         native.check(lib.wn_head_fwd(ctypes.byref(hd), stream), "head")
-        self.launches_last_forward = 1 + len(dil) + 1
+        self.launches_last_forward = 1 + len(dil) * (2 if use_tc else 1) + 1
         if save is not None:
             save.update(h_all=h_all, fg_all=fg_all, skip=skip, plan=plan, out_len=out_len, x=x,
                         index_input=index_input, B=B, L=L)
@@ -613,13 +642,15 @@ class WaveNetModel(nn.Module):
         return (idx, logits) if return_logits else idx
 
     def _export_queues(self):
-        """Point ``dilated_queues[i].data`` at stream 0 of the sampler's device rings (a (C, max_length) view)."""
+        """Point ``dilated_queues[i].data`` at stream 0 of the sampler's device rings (a (C, max_length) view).
+        Ring elements are 8-byte {value, tag} pairs (see csrc/gen.cu); the view picks the values."""
         rt = self._runtime()
         s, evals = rt.last_run["sampler"], rt.last_run["evals"]
         R, NS, off = self.residual_channels, s["n_streams"], 0
+        pairs = s["rings"].view(-1, 2)
         for q in self.dilated_queues:
             n = q.max_length * NS * R
-            q.data = s["rings"][off:off + n].view(q.max_length, NS, R)[:, 0, :].t()
+            q.data = pairs[off:off + n, 0].view(q.max_length, NS, R)[:, 0, :].t()
             q.in_pos = q.out_pos = evals % q.max_length
             off += n
 

@@ -1,0 +1,72 @@
+"""Tensor-core (tcgen05, 3xTF32) residual blocks vs the exact-fp32 SIMT blocks, the golden reference outputs and the
+CPU oracle.  The 3xTF32 path must hold the same 1e-4 parity bar (it is expected around 1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from helpers import build_model, one_hot_cuda, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tc_blocks_match_ffma_and_oracle():
+    import wavenet_model as wmod
+    kw = dict(layers=4, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=300, kernel_size=2, bias=True)
+    torch.manual_seed(5)
+    m = wmod.WaveNetModel(**kw)
+    spec = O.NetSpec(**kw)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    idx = torch.randint(0, 256, (2, 700), generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = O.forward(p, spec, O.one_hot(idx, 256)).numpy()
+    m = m.cuda()
+    rt = m._runtime()
+    with torch.no_grad():
+        rt.block_mode = "ffma"
+        y0 = m.forward_indices(idx.cuda()).cpu().numpy()
+        assert rt.last_block_mode == "ffma"
+        rt.block_mode = "tc"
+        y1 = m.forward_indices(idx.cuda()).cpu().numpy()
+        assert rt.last_block_mode == "tc"
+        full = m.wavenet(one_hot_cuda(idx.numpy()), m.wavenet_dilate).cpu().numpy()
+    assert rel_err(y0, want) < 1e-4
+    assert rel_err(y1, want) < 1e-4, f"tc vs oracle {rel_err(y1, want):.3e}"
+    assert rel_err(y1, y0) < 2e-5, f"tc vs ffma {rel_err(y1, y0):.3e}"
+    with torch.no_grad():
+        want_full = O.stack_folded(p, spec, O.one_hot(idx, 256), lambda h, d, i0, i: O.fold_time(h, d, i0)).numpy()
+    assert rel_err(full, want_full) < 1e-4                      # incl. the zero-history (padding) region
+
+
+def test_tc_cfg2_golden_and_auto_mode(golden):
+    g = golden("net_cfg2.npz")
+    m = build_model(g)
+    rt = m._runtime()
+    assert rt.block_mode == "auto"
+    with torch.no_grad():
+        y = m(one_hot_cuda(g["idx"]))
+    assert rt.last_block_mode == "tc"                           # 256-channel nets take the tensor-core path by default
+    assert rel_err(y.cpu().numpy(), g["fwd"]) < 1e-4
+    small = build_model(golden("net_deep.npz"))
+    with torch.no_grad():
+        small(one_hot_cuda(golden("net_deep.npz")["idx"]))
+    assert small._runtime().last_block_mode == "ffma"           # 64 channels: SIMT path
+
+
+def test_tc_full_size_batch_independence():
+    import wavenet_model as wmod
+    torch.manual_seed(0)
+    m = wmod.WaveNetModel(layers=10, blocks=5, dilation_channels=256, residual_channels=256, skip_channels=256,
+                          end_channels=256, classes=256, output_length=5000, kernel_size=2).cuda()
+    idx = torch.randint(0, 256, (4, 16000), generator=torch.Generator().manual_seed(1234)).cuda()
+    rt = m._runtime()
+    with torch.no_grad():
+        rt.block_mode = "tc"
+        y = m.forward_indices(idx).view(4, -1, 256)
+        y2 = m.forward_indices(idx[2:3]).view(1, -1, 256)
+        rt.block_mode = "ffma"
+        y_ref = m.forward_indices(idx[2:3]).view(1, -1, 256)
+    assert bool(torch.isfinite(y).all())
+    assert torch.equal(y[2], y2[0])
+    assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) < 2e-5
