@@ -445,6 +445,7 @@ __device__ __forceinline__ void row_dot_part(const float* __restrict__ w, const 
 struct StageDesc {
     int n, K;                 // rows, row length
     int n_first;              // stage 2: residual rows come first (n_first of them), then skip rows
+    int n_nom;                // nominal row count of the stage (fixes the K split, whatever rows are active)
 };
 __device__ __forceinline__ StageDesc stage_desc(const GenParams& p, int st, bool want_head, int nD, int nR, int nS,
                                                 int nE, int nC) {
@@ -452,10 +453,10 @@ __device__ __forceinline__ StageDesc stage_desc(const GenParams& p, int st, bool
     const int NL = p.n_layers;
     if (st < 2 * NL) {
         const int l = st >> 1;
-        if ((st & 1) == 0) { d.n = 2 * nD; d.K = p.k * p.R; d.n_first = d.n; }
-        else { d.n_first = (l + 1 < NL) ? nR : 0; d.n = d.n_first + (want_head ? nS : 0); d.K = p.D; }
-    } else if (st == 2 * NL) { d.n = nE; d.K = p.S; d.n_first = d.n; }
-    else { d.n = nC; d.K = p.E; d.n_first = d.n; }
+        if ((st & 1) == 0) { d.n = 2 * nD; d.K = p.k * p.R; d.n_first = d.n; d.n_nom = d.n; }
+        else { d.n_first = (l + 1 < NL) ? nR : 0; d.n = d.n_first + (want_head ? nS : 0); d.K = p.D; d.n_nom = nR + nS; }
+    } else if (st == 2 * NL) { d.n = nE; d.K = p.S; d.n_first = d.n; d.n_nom = d.n; }
+    else { d.n = nC; d.K = p.E; d.n_first = d.n; d.n_nom = d.n; }
     return d;
 }
 __device__ __forceinline__ const float* stage_row(const GenParams& p, const GenLayer* layers, int st, const StageDesc& d,
@@ -533,8 +534,8 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
     // rows are split over nw = 8/items warps along K when there are fewer rows than warps.
     auto run_stage = [&](int st, const StageDesc& d, const float* xs, int& nw_out) {
         int nw = 1;
-        while (nw * 2 * d.n <= GEN_WARPS && (d.K / (nw * 2)) % 4 == 0 && d.K / (nw * 2) >= 32) nw *= 2;
-        if (d.n == 0) nw = 1;
+        while (nw * 2 * d.n_nom <= GEN_WARPS && (d.K / (nw * 2)) % 4 == 0 && d.K / (nw * 2) >= 32) nw *= 2;
+        if (d.n_nom == 0) nw = 1;
         nw_out = nw;
         const float* wslot = nullptr;
         if (PREFETCH) {
@@ -747,6 +748,382 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         for (int s = tid; s < NS; s += GEN_NT) p.cur_idx[s] = idx_s[s];
 }
 
+// ================================================================================================ fast kernel
+// Single stream, k = 2, power-of-two grid, every stage's rows a divisor of 8: the latency-critical special case
+// (cfg 2).  Same exchange protocol, same tags, same summation order as gen_kernel_ll, but the per-stage critical
+// path is stripped down: every warp owns one (row, K-part) pair for the whole launch, polls exactly the {value,tag}
+// pairs it multiplies straight into registers (no staging, no index arithmetic with divisions), and there is ONE
+// __syncthreads per stage (partial sums are double buffered).  Ring positions advance incrementally.
+struct Pair2 { uint2 a, b; };
+__device__ __forceinline__ Pair2 ld_pair2(const uint2* p) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    Pair2 r;
+    r.a = make_uint2((unsigned)(w0 & 0xffffffffull), (unsigned)(w0 >> 32));
+    r.b = make_uint2((unsigned)(w1 & 0xffffffffull), (unsigned)(w1 >> 32));
+    return r;
+}
+// two consecutive pairs carrying `tag`; spins (bounded) until both are there
+__device__ __forceinline__ void poll2(const uint2* p, unsigned tag, float& v0, float& v1, int* err, int* abort_s) {
+    Pair2 q = ld_pair2(p);
+    if (q.a.y != tag || q.b.y != tag) {
+        const long long t0 = clock64();
+        do {
+            q = ld_pair2(p);
+            if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+                *reinterpret_cast<volatile int*>(err) = 1;
+                *reinterpret_cast<volatile int*>(abort_s) = 1;
+                break;
+            }
+        } while (q.a.y != tag || q.b.y != tag);
+    }
+    v0 = __uint_as_float(q.a.x);
+    v1 = __uint_as_float(q.b.x);
+}
+
+template <bool PREFETCH>
+__global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* part = sm;                                   // [2][GEN_WARPS] partial sums, double buffered by stage parity
+    float* skacc = part + 2 * GEN_WARPS;                // [nS]
+    float* cur_own = skacc + ((p.S / (int)gridDim.x + 3) & ~3);      // [2][nR] layer input at the residual rows this CTA owns
+    float* logit_s = cur_own + 2 * ((p.R / (int)gridDim.x + 3) & ~3);  // [C]
+    double* cdf = reinterpret_cast<double*>(logit_s + ((p.C + 3) & ~3));       // [C]
+    float* wbuf = reinterpret_cast<float*>(cdf + p.C);                         // [n_wslots][wslot_floats]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);
+    int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);                  // [NL] ring slot of time t per layer
+    int* misc = slot_s + p.n_layers;                                           // [0] current index, [1] abort
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x, gmask = G - 1;
+    const int R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, NL = p.n_layers;
+    const int K1 = 2 * R;
+    const int nD = D / G, nR = R / G, nS = S / G, nE = E / G, nC = C / G;
+    const int NSLOT = p.n_wslots;
+    int g_shift = 0;
+    while ((1 << g_shift) < G) ++g_shift;
+    // fixed warp -> (row, K-part) assignment per stage kind
+    const int HS1 = GEN_WARPS / (2 * nD), HS2 = GEN_WARPS / (nR + nS), HSA = GEN_WARPS / nE, HSB = GEN_WARPS / nC;
+
+    {
+        const int* src = reinterpret_cast<const int*>(p.layers);
+        int* dst = reinterpret_cast<int*>(lay_s);
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        misc[0] = p.cur_idx[0];
+        misc[1] = 0;
+        if (PREFETCH)
+            for (int i = 0; i < NSLOT; ++i) mbar_init(fullb + i, 1);
+    }
+    if (PREFETCH) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    for (int l = tid; l < NL; l += GEN_NT) {          // slot of time t0-1, advanced at the top of every evaluation
+        const int len = lay_s[l].ring_len;
+        slot_s[l] = (p.t0 + len - 1) % len;
+    }
+    int* abort_s = misc + 1;
+
+    // ---- weight prefetch (same stage sequence as gen_kernel_ll; all rows of a stage are always fetched)
+    int pf_ev = 0, pf_st = 0;
+    long long pf_q = 0, cons_q = 0;
+    auto produce_one = [&]() {
+        if (pf_ev >= p.n_evals) return;
+        const bool wh = (p.t0 + pf_ev >= p.n_given - 1);
+        StageDesc d = stage_desc(p, pf_st, true, nD, nR, nS, nE, nC);
+        if (pf_st < 2 * NL && (pf_st & 1)) { d.n_first = nR; d.n = nR + nS; }      // fetch residual + skip rows always
+        const int slot = (int)(pf_q % NSLOT);
+        mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+        float* dst = wbuf + (size_t)slot * p.wslot_floats;
+        for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
+        ++pf_q;
+        if (++pf_st >= (wh ? 2 * NL + 2 : 2 * NL)) { pf_st = 0; ++pf_ev; }
+    };
+    if (PREFETCH && tid == GEN_NT - 1)
+        for (int i = 0; i < NSLOT; ++i) produce_one();
+    // weights of (stage, row): shared-memory slot when prefetching, else the parameter tensor itself
+    auto stage_weights = [&](int st, int row, int K) -> const float* {
+        if (PREFETCH) {
+            const int slot = (int)(cons_q % NSLOT);
+            mbar_wait(fullb + slot, (unsigned)((cons_q / NSLOT) & 1));
+            return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * K;
+        }
+        StageDesc d = stage_desc(p, st, true, nD, nR, nS, nE, nC);
+        if (st < 2 * NL && (st & 1)) { d.n_first = nR; d.n = nR + nS; }
+        return stage_row(p, lay_s, st, d, row, cta, G);
+    };
+    auto ldw = [&](const float* w, int i4) -> float4 {
+        if (PREFETCH) return reinterpret_cast<const float4*>(w)[i4];
+        return __ldg(reinterpret_cast<const float4*>(w) + i4);
+    };
+    unsigned stage_par = 0;
+    __syncthreads();
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;
+        const unsigned tag = (unsigned)t + 1u;
+        const int par = t & 1;
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);
+        if (tid == 0) {
+            if (t < p.n_given) misc[0] = p.first[t];
+            else if (p.forced != nullptr) misc[0] = p.forced[t - p.n_given];
+        }
+        for (int l = tid; l < NL; l += GEN_NT) {
+            const int s1 = slot_s[l] + 1;
+            slot_s[l] = (s1 == lay_s[l].ring_len) ? 0 : s1;
+        }
+        for (int i = tid; i < nS; i += GEN_NT) skacc[i] = 0.f;
+        __syncthreads();
+        if (*abort_s) return;
+        int idx = misc[0];
+        idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
+
+        for (int l = 0; l < NL; ++l) {
+            const GenLayer& L = lay_s[l];
+            uint2* ring = p.ringLL + L.ring_off;
+            const int slot_t = slot_s[l];
+            float* cur_l = cur_own + (l & 1) * ((nR + 3) & ~3);
+            const int slot_old = (slot_t + 1 == L.ring_len) ? 0 : slot_t + 1;          // time t-d with len = d+1
+            const bool have_old = (t >= L.dil);
+            // ================= stage 1: filter/gate rows, K = 2R interleaved (old, cur) per channel
+            {
+                const int row = warp / HS1, kp = warp - row * HS1, Kp = K1 / HS1;
+                const float* w = stage_weights(2 * l, row, K1);
+                float acc = 0.f;
+                for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
+                    const int g4 = (kp * Kp >> 2) + i4;            // float4 index within the row
+                    const int r0 = 2 * g4;                         // channels r0, r0+1
+                    float o0 = 0.f, o1 = 0.f, c0, c1;
+                    if (have_old) poll2(ring + (size_t)slot_old * R + r0, (unsigned)(t - L.dil) + 1u, o0, o1, p.err, abort_s);
+                    if (l == 0) {
+                        c0 = __ldg(p.start_w + (size_t)r0 * C + idx) + (p.start_b ? __ldg(p.start_b + r0) : 0.f);
+                        c1 = __ldg(p.start_w + (size_t)(r0 + 1) * C + idx) + (p.start_b ? __ldg(p.start_b + r0 + 1) : 0.f);
+                        if (row == 0) {                            // one warp row covers every channel once: it enqueues
+                            if ((r0 & gmask) == cta) st_pair(ring + (size_t)slot_t * R + r0, c0, tag);
+                            if (((r0 + 1) & gmask) == cta) st_pair(ring + (size_t)slot_t * R + r0 + 1, c1, tag);
+                        }
+                    } else {
+                        poll2(ring + (size_t)slot_t * R + r0, tag, c0, c1, p.err, abort_s);
+                    }
+                    if (row == 0) {
+                        if ((r0 & gmask) == cta) cur_l[r0 >> g_shift] = c0;
+                        if (((r0 + 1) & gmask) == cta) cur_l[(r0 + 1) >> g_shift] = c1;
+                    }
+                    const float4 w4 = ldw(w, g4);
+                    acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, c0, acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, c1, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                ++cons_q;
+            }
+            __syncthreads();
+            if (*abort_s) return;
+            if (PREFETCH && tid == GEN_NT - 1) produce_one();
+            uint2* zl = p.zLL + (size_t)(par * NL + l) * D;
+            if (tid < nD) {
+                const int c = tid * G + cta;
+                const float* pf = part + stage_par * GEN_WARPS + (2 * tid) * HS1;
+                float f = pf[0], g = pf[HS1];
+                for (int q = 1; q < HS1; ++q) { f += pf[q]; g += pf[HS1 + q]; }
+                f += L.bf ? __ldg(L.bf + c) : 0.f;
+                g += L.bg ? __ldg(L.bg + c) : 0.f;
+                st_pair(zl + c, tanhf(f) * sigmoid_(g), tag);
+            }
+            stage_par ^= 1;
+            // ================= stage 2: residual rows (first nR) and skip rows (next nS), K = D
+            {
+                const int row = warp / HS2, kp = warp - row * HS2, Kp = D / HS2;
+                const bool is_res = row < nR;
+                const bool active = is_res ? (l + 1 < NL) : want_head;
+                const float* w = stage_weights(2 * l + 1, row, D);
+                float acc = 0.f;
+                if (active) {
+                    for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
+                        const int g4 = (kp * Kp >> 2) + i4;
+                        float z0, z1, z2, z3;
+                        poll2(zl + 4 * g4, tag, z0, z1, p.err, abort_s);
+                        poll2(zl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
+                        const float4 w4 = ldw(w, g4);
+                        acc = fmaf(w4.x, z0, acc); acc = fmaf(w4.y, z1, acc); acc = fmaf(w4.z, z2, acc); acc = fmaf(w4.w, z3, acc);
+                    }
+                    acc = warp_sum(acc);
+                }
+                if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                ++cons_q;
+            }
+            __syncthreads();
+            if (*abort_s) return;
+            if (PREFETCH && tid == GEN_NT - 1) produce_one();
+            if (tid < nR + nS) {
+                const float* ps = part + stage_par * GEN_WARPS + tid * HS2;
+                float v = ps[0];
+                for (int q = 1; q < HS2; ++q) v += ps[q];
+                if (tid < nR) {
+                    if (l + 1 < NL) {
+                        const int row = tid * G + cta;
+                        const GenLayer& Ln = lay_s[l + 1];
+                        v += L.br ? __ldg(L.br + row) : 0.f;
+                        st_pair(p.ringLL + Ln.ring_off + (size_t)slot_s[l + 1] * R + row, v + cur_l[tid], tag);
+                    }
+                } else if (want_head) {
+                    const int li = tid - nR, row = li * G + cta;
+                    v += L.bs ? __ldg(L.bs + row) : 0.f;
+                    skacc[li] = v + skacc[li];
+                }
+            }
+            stage_par ^= 1;
+            // no barrier here: part and cur_own are double buffered, and their next writers sit behind the next
+            // stage's __syncthreads, which this epilogue's threads must reach first
+        }
+        if (!want_head) continue;
+
+        // ================= head
+        uint2* skl = p.skipLL + (size_t)par * S;
+        if (tid >= nR && tid < nR + nS) st_pair(skl + (tid - nR) * G + cta, skacc[tid - nR], tag);   // same thread that summed it
+        uint2* yl = p.y1LL + (size_t)par * E;
+        {
+            const int row = warp / HSA, kp = warp - row * HSA, Kp = S / HSA;
+            const float* w = stage_weights(2 * NL, row, S);
+            float acc = 0.f;
+            for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
+                const int g4 = (kp * Kp >> 2) + i4;
+                float z0, z1, z2, z3;
+                poll2(skl + 4 * g4, tag, z0, z1, p.err, abort_s);
+                poll2(skl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
+                const float4 w4 = ldw(w, g4);
+                acc = fmaf(w4.x, fmaxf(z0, 0.f), acc); acc = fmaf(w4.y, fmaxf(z1, 0.f), acc);
+                acc = fmaf(w4.z, fmaxf(z2, 0.f), acc); acc = fmaf(w4.w, fmaxf(z3, 0.f), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            ++cons_q;
+        }
+        __syncthreads();
+        if (*abort_s) return;
+        if (PREFETCH && tid == GEN_NT - 1) produce_one();
+        if (tid < nE) {
+            const int row = tid * G + cta;
+            const float* ps = part + stage_par * GEN_WARPS + tid * HSA;
+            float v = ps[0];
+            for (int q = 1; q < HSA; ++q) v += ps[q];
+            st_pair(yl + row, fmaxf(v + __ldg(p.e1b + row), 0.f), tag);
+        }
+        stage_par ^= 1;
+        uint2* lgl = p.logitLL + (size_t)par * C;
+        {
+            const int row = warp / HSB, kp = warp - row * HSB, Kp = E / HSB;
+            const float* w = stage_weights(2 * NL + 1, row, E);
+            float acc = 0.f;
+            for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
+                const int g4 = (kp * Kp >> 2) + i4;
+                float z0, z1, z2, z3;
+                poll2(yl + 4 * g4, tag, z0, z1, p.err, abort_s);
+                poll2(yl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
+                const float4 w4 = ldw(w, g4);
+                acc = fmaf(w4.x, z0, acc); acc = fmaf(w4.y, z1, acc); acc = fmaf(w4.z, z2, acc); acc = fmaf(w4.w, z3, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            ++cons_q;
+        }
+        __syncthreads();
+        if (*abort_s) return;
+        if (PREFETCH && tid == GEN_NT - 1) produce_one();
+        if (tid < nC) {
+            const int row = tid * G + cta;
+            const float* ps = part + stage_par * GEN_WARPS + tid * HSB;
+            float v = ps[0];
+            for (int q = 1; q < HSB; ++q) v += ps[q];
+            const float dc = (float)row - (float)C / 2.f;
+            v = (v + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+            st_pair(lgl + row, v, tag);
+            if (p.out_logits) p.out_logits[(size_t)samp * C + row] = v;
+        }
+        stage_par ^= 1;
+        // ---- all logits -> shared memory, then warp 0 chooses
+        for (int c2 = tid; 2 * c2 < C; c2 += GEN_NT) {
+            float a, b;
+            poll2(lgl + 2 * c2, tag, a, b, p.err, abort_s);
+            logit_s[2 * c2] = a;
+            logit_s[2 * c2 + 1] = b;
+        }
+        __syncthreads();
+        if (*abort_s) return;
+        if (warp == 0) {
+            int choice;
+            if (p.temperature > 0.f) {
+                float m = -INFINITY;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = logit_s[c] / p.temperature;
+                    logit_s[c] = x;
+                    m = fmaxf(m, x);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int c = lane; c < C; c += 32) {
+                    const float e = expf(logit_s[c] - m);
+                    logit_s[c] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                __syncwarp();
+                // numpy.random.choice: float64 cumulative sum of the float32 probabilities, normalised by its last element,
+                // searchsorted(side='right').  The running sum is taken per lane over a contiguous chunk plus a warp scan
+                // (equal to the sequential sum up to float64 rounding, i.e. ~1e-16 relative on the CDF).
+                const int per = (C + 31) / 32;
+                const int c_lo = lane * per, c_hi = min(C, c_lo + per);
+                double run = 0.0;
+                for (int c = c_lo; c < c_hi; ++c) { run += (double)(logit_s[c] / sum); cdf[c] = run; }
+                double incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 0.0;
+                const double total = __shfl_sync(0xffffffffu, incl, 31);
+                const double u = p.uniforms[samp];
+                const double ut = u * total;
+                int cnt = 0;
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const double v = cdf[c] + excl;
+                    bool le = v <= ut;
+                    if (fabs(v - ut) <= 1e-9 * total) le = (v / total) <= u;       // exact rule only where it can matter
+                    cnt += le ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                choice = cnt < C ? cnt : C - 1;
+            } else {
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < C; c += 32) {
+                    const float x = logit_s[c];
+                    if (x > best || (x == best && c < bi)) { best = x; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                choice = bi == 0x7fffffff ? 0 : bi;
+            }
+            if (lane == 0) {
+                misc[0] = choice;
+                if (cta == 0) p.out_idx[samp] = choice;
+            }
+        }
+        // the top-of-evaluation __syncthreads publishes misc[0]
+    }
+    __syncthreads();
+    if (cta == 0 && tid == 0) p.cur_idx[0] = misc[0];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
     size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, total;
@@ -796,8 +1173,11 @@ struct wn_gen_handle {
     size_t smem;
     bool tables_uploaded;
     int cur_t;
-    int mode;               // 0 = flag-in-data exchange (default), 1 = grid-barrier kernel
+    int mode;               // 0 = best flag-in-data kernel (default), 1 = grid-barrier kernel, 2 = generic flag-in-data kernel
     size_t smem_ll;
+    bool fast_ok;           // single stream, k=2, power-of-two grid, rows per stage divide 8: gen_kernel_fast applies
+    size_t smem_fast;
+    int n_wslots_fast;
 };
 
 static int validate_shape(const wn_gen_shape* s) {
@@ -936,6 +1316,34 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
             h->smem = sizeof(float) * ((size_t)p.regA + p.regB + p.pre_n + p.skacc_n + NS + (size_t)GEN_WARPS * s->classes);
         }
         h->mode = (s->n_layers >= 2 && h->smem_ll <= (size_t)smem_optin) ? 0 : 1;
+        // ---- fast kernel eligibility (same K split as the generic kernel so both sum in the same order)
+        auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+        auto split_ok = [&](int rows, int K) {
+            if (!(rows == 1 || rows == 2 || rows == 4 || rows == 8)) return false;
+            const int hs = GEN_WARPS / rows;
+            return K % hs == 0 && (K / hs) % 4 == 0 && (K / hs) >= 32;
+        };
+        bool ok = NS == 1 && s->k == 2 && pow2(G) && G >= 2 && s->n_layers >= 2 && s->D % G == 0 && s->R % G == 0 &&
+                  s->S % G == 0 && s->E % G == 0 && s->classes % G == 0;
+        if (ok)
+            ok = split_ok(2 * (s->D / G), 2 * s->R) && split_ok((s->R + s->S) / G, s->D) && split_ok(s->E / G, s->S) &&
+                 split_ok(s->classes / G, s->E);
+        h->fast_ok = false;
+        if (ok) {
+            const size_t fbase = sizeof(float) * (2 * GEN_WARPS + ((s->S / G + 3) & ~3) + 2 * ((s->R / G + 3) & ~3) +
+                                                  ((s->classes + 3) & ~3)) +
+                                 sizeof(double) * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
+                                 sizeof(int) * (size_t)(s->n_layers + 4);
+            int fs = 0;
+            if (fbase < (size_t)smem_optin) {
+                long long fit = ((long long)smem_optin - (long long)fbase) / (slot * 4);
+                fs = fit >= 4 ? 4 : (fit >= 2 ? (int)fit : 0);
+            }
+            if (getenv("WN_GEN_NOPREFETCH")) fs = 0;
+            h->n_wslots_fast = fs;
+            h->smem_fast = fbase + (size_t)fs * slot * 4;
+            h->fast_ok = h->smem_fast <= (size_t)smem_optin;
+        }
     }
     h->tables_uploaded = false;
     h->cur_t = 0;
@@ -981,11 +1389,23 @@ static int launch_gen_ll(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     return 0;
 }
 
+template <bool PF>
+static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
+    int per_sm = 0;
+    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_fast<PF>, GEN_NT, h->smem_fast));
+    WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
+    void* args[] = {(void*)&p};
+    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_fast<PF>, dim3(h->grid), dim3(GEN_NT), args, h->smem_fast, st));
+    return 0;
+}
+
 extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_set_mode: null handle");
-    WN_REQUIRE(mode == 0 || mode == 1, WN_E_BADARG, "wn_gen_set_mode: mode must be 0 (flag exchange) or 1 (grid barrier)");
+    WN_REQUIRE(mode >= 0 && mode <= 2, WN_E_BADARG,
+               "wn_gen_set_mode: mode must be 0 (best flag-exchange kernel), 1 (grid barrier) or 2 (generic flag exchange)");
     WN_REQUIRE(h->cur_t == 0, WN_E_STATE, "wn_gen_set_mode: switch kernels only right after wn_gen_reset");
-    if (mode == 0) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
+    if (mode != 1) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
     h->mode = mode;
     return 0;
 }
@@ -1025,7 +1445,10 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         p.t0 = a->t0 + done; p.n_evals = n; p.temperature = a->temperature; p.regularize = a->regularize;
         WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
         int rc;
-        if (h->mode == 0) {
+        if (h->mode == 0 && h->fast_ok) {
+            p.n_wslots = h->n_wslots_fast;
+            rc = p.n_wslots ? launch_gen_fast<true>(h, p, st) : launch_gen_fast<false>(h, p, st);
+        } else if (h->mode == 0 || h->mode == 2) {
             if (h->shape.n_streams == 1)
                 rc = p.n_wslots ? launch_gen_ll<1, true>(h, p, st) : launch_gen_ll<1, false>(h, p, st);
             else

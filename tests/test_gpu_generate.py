@@ -137,7 +137,7 @@ def test_exchange_modes_agree(golden, name):
     firsts = rng.randint(0, 256, size=(3, 25))
     uni = rng.random_sample((3, 40))
     res = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         m._runtime().gen_mode = mode
         res[mode] = m.generate_fast_batch(40, firsts, temperature=0.7, uniforms=uni, forced=None, return_logits=True)
         _, lg = m.generate_fast_batch(24, g["first"][None, :], temperature=0.0, forced=g["gen_argmax_idx"][None, :],
@@ -149,3 +149,32 @@ def test_exchange_modes_agree(golden, name):
     for s in range(3):                      # streams may only part ways after a step where the logits differ by rounding
         n = 40 if same[s] else int(np.nonzero(i0[s] != i1[s])[0][0])
         assert n >= 1 and rel_err(l0[s, :n + 1], l1[s, :n + 1]) < 1e-5
+
+
+def test_fast_kernel_equals_generic_kernel_bitwise(golden):
+    """cfg 2 net, single stream: the register-polling kernel (mode 0) and the generic flag-exchange kernel (mode 2)
+    share the K split and summation order, so logits and indices are identical bit for bit; a 3-stream run (generic
+    kernel) reproduces the single-stream run of each stream."""
+    g = golden("net_cfg2.npz")
+    m = build_model(g)
+    rt = m._runtime()
+    rng = np.random.RandomState(3)
+    first = rng.randint(0, 256, size=(3, 7))
+    uni = rng.random_sample((3, 40))
+    out = {}
+    for mode in (0, 2):
+        rt.gen_mode = mode
+        out[mode] = [m.generate_fast_batch(40, first[s:s + 1], temperature=1.0, uniforms=uni[s:s + 1], return_logits=True)
+                     for s in range(3)]
+    rt.gen_mode = None
+    for s in range(3):
+        assert np.array_equal(out[0][s][0], out[2][s][0]) and np.array_equal(out[0][s][1], out[2][s][1])
+    multi_idx, multi_lg = m.generate_fast_batch(40, first, temperature=1.0, uniforms=uni, return_logits=True)
+    for s in range(3):
+        assert np.array_equal(multi_idx[s], out[0][s][0][0]) and np.array_equal(multi_lg[s], out[0][s][1][0])
+    # argmax + warm-up + chunked launches (progress callback) through the fast kernel
+    calls = []
+    a = m.generate_fast(30, first_samples=first[0], temperature=0.0, progress_callback=lambda i, n: calls.append(i),
+                        progress_interval=7)
+    b = m.generate_fast(30, first_samples=first[0], temperature=0.0)
+    assert np.array_equal(a, b) and len(calls) > 3
