@@ -40,13 +40,15 @@ TEMPERATURE = 1.0
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def measured_peaks():
+def measured_peaks(what="hbm"):
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
+        if what == "tensor":
+            return float(d["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return (1400.0 if what == "tensor" else 6650.0), "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -300,20 +302,35 @@ def bench_train(args, world, rank):
     n_layers = len(per_layer)
     peak, peak_src = measured_peaks()
     ach = (sum(per_layer) / n_layers) / (block_ms / n_layers / 1e3) / 1e9
-    roof = {"kernel": "block_fwd_kernel<128> (fused residual block, exact fp32 FFMA)", "bound": "hbm",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "peak_source": peak_src, "launches_per_step": n_layers, "avg_launch_ms": block_ms / n_layers,
-            "alg_bytes_per_launch": sum(per_layer) / n_layers,
-            "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L),
-            "tflops_fp32_achieved": flops / (block_ms / 1e3) / 1e12,
-            "note": "exact-fp32 mode is bound by the fp32 FMA pipe, not by HBM (AI ~196 FLOP/B)"}
+    tflops = flops / (block_ms / 1e3) / 1e12
+    mode = getattr(rt, "last_block_mode", "ffma")
+    if mode == "tc":
+        tpeak, tsrc = measured_peaks("tensor")
+        roof = {"kernel": "frames_gemm_tc<GATE> + frames_gemm_tc<RES_SKIP> (tcgen05 kind::tf32, 3xTF32, one block = 2 launches)",
+                "bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                "traffic": None, "peak_source": tsrc, "launches_per_step": 2 * n_layers,
+                "avg_block_ms": block_ms / n_layers,
+                "note": "achieved counts the algorithmic fp32 FLOPs once; every FLOP costs 3 tf32 MMAs (= 6 bf16-rate "
+                        "equivalents), so frac*6 is the share of the measured tensor peak the kernel keeps busy",
+                "tensor_pipe_equiv_frac": 6 * tflops / tpeak,
+                "hbm_achieved_gbs": ach, "hbm_peak_gbs": peak, "hbm_frac": ach / peak,
+                "alg_bytes_per_block": sum(per_layer) / n_layers,
+                "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L)}
+    else:
+        roof = {"kernel": "block_fwd_kernel<128> (fused residual block, exact fp32 FFMA)", "bound": "hbm",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": n_layers, "avg_launch_ms": block_ms / n_layers,
+                "alg_bytes_per_launch": sum(per_layer) / n_layers,
+                "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L),
+                "tflops_fp32_achieved": tflops,
+                "note": "exact-fp32 mode is bound by the fp32 FMA pipe, not by HBM (AI ~196 FLOP/B)"}
     return dict(metric="training-forward mu-law frames/sec", value=value, unit="frames/s", ms_per_step=ms / args.steps,
                 clocks=clk, e2e=e2e, e2e_index_api={"value": world * B * L * e2e_steps / e2e_idx_s, "unit": "frames/s",
                                                    "h2d_bytes_per_step": int(idx_host.numel()),
                                                    "d2h_bytes_per_step": int(am.numel() * 8)},
                 roofline=roof, dtype="f32", scaling="weak",
                 config={"workload": "cfg3 forward: layers=10 blocks=5 ch=256, B=8 per GPU, L=16000, output_length=10885, "
-                                    "uint8 index input resident in HBM", "global_batch": world * B, "seq_len": L,
+                                    "uint8 index input resident in HBM", "block_kernels": mode, "global_batch": world * B, "seq_len": L,
                         "parallelism": f"dp{world} (batch shards, no collective in forward)"},
                 launches=args.steps * rt.launches_last_forward)
 

@@ -62,6 +62,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Row ownership: CTA c owns the contiguous rows [c*per, min(N, (c+1)*per)), per = ceil(N/G).  Contiguous (not
+// interleaved) so that what a CTA publishes per stage is one run of {value,tag} pairs: with >= 4 rows per CTA the
+// stores of one warp instruction fill whole 32-byte sectors, which measured 2.6x faster to exchange than 16-byte
+// partial-sector writes from twice as many CTAs (tools/lat_probe.cu).
+__device__ __forceinline__ int own_per(int N, int G) { return (N + G - 1) / G; }
+__device__ __forceinline__ int own_cnt(int N, int G, int cta) {
+    const int per = own_per(N, G), n = N - cta * per;
+    return n < 0 ? 0 : (n < per ? n : per);
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target, unsigned G) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -127,11 +137,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
     unsigned bar_target = 0;
 
     // owned rows per stage: row r belongs to CTA (r mod G); local index r / G
-    const int nD = (D > cta) ? (D - cta + G - 1) / G : 0;
-    const int nR = (R > cta) ? (R - cta + G - 1) / G : 0;
-    const int nS = (S > cta) ? (S - cta + G - 1) / G : 0;
-    const int nE = (E > cta) ? (E - cta + G - 1) / G : 0;
-    const int nC = (C > cta) ? (C - cta + G - 1) / G : 0;
+    const int nD = own_cnt(D, G, cta), oD = cta * own_per(D, G);
+    const int nR = own_cnt(R, G, cta), oR = cta * own_per(R, G);
+    const int nS = own_cnt(S, G, cta), oS = cta * own_per(S, G);
+    const int nE = own_cnt(E, G, cta), oE = cta * own_per(E, G);
+    const int nC = own_cnt(C, G, cta), oC = cta * own_per(C, G);
 
     // the index chosen by the evaluation before t0 (continuation of a previous launch)
     for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.cur_idx[s];
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
                     int c = idx_s[s];
                     c = c < 0 ? 0 : (c >= C ? C - 1 : c);
                     v = __ldg(p.start_w + (size_t)r * C + c) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
-                    if (r % G == cta) ring[((size_t)slot_t * NS + s) * R + r] = v;       // enqueue (owner writes)
+                    if (r >= oR && r < oR + nR) ring[((size_t)slot_t * NS + s) * R + r] = v;       // enqueue (owner writes)
                 } else {
                     int tt = t - (k - 1 - j) * L.dil;        // time of tap j
                     int slot = tt % L.ring_len;
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
             __syncthreads();
             // ---- stage 1: filter / gate rows of the owned dilation channels
             for (int it = warp; it < 2 * nD; it += GEN_WARPS) {
-                const int c = (it >> 1) * G + cta;
+                const int c = oD + (it >> 1);
                 const float* w = ((it & 1) ? L.wg : L.wf) + (size_t)c * K1;
                 const float* bp = (it & 1) ? L.bg : L.bf;
                 const float bias = bp ? __ldg(bp + c) : 0.f;
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
             for (int i = tid; i < nD * NS; i += GEN_NT) {
                 const int ci = i / NS, s = i - ci * NS;
                 const float z = tanhf(pre[(2 * ci) * NS + s]) * sigmoid_(pre[(2 * ci + 1) * NS + s]);
-                p.zbuf[(size_t)s * D + ci * G + cta] = z;
+                p.zbuf[(size_t)s * D + oD + ci] = z;
             }
             grid_barrier(p.bar, bar_target, G);
             // ---- stage 2: residual rows (not needed after the last layer) and skip rows (not needed in warm-up)
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
             for (int it = warp; it < nres + nskp; it += GEN_WARPS) {
                 const bool is_res = it < nres;
                 const int li = is_res ? it : it - nres;
-                const int row = li * G + cta;
+                const int row = (is_res ? oR : oS) + li;
                 const float* w = (is_res ? L.wr : L.ws) + (size_t)row * D;
                 const float* bp = is_res ? L.br : L.bs;
                 const float bias = bp ? __ldg(bp + row) : 0.f;
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
                 __syncthreads();
                 for (int i = tid; i < nS * NS; i += GEN_NT) {
                     const int li = i / NS, s = i - li * NS;
-                    p.skipbuf[(size_t)s * S + li * G + cta] = skacc[i];
+                    p.skipbuf[(size_t)s * S + oS + li] = skacc[i];
                 }
             }
             grid_barrier(p.bar, bar_target, G);
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
         for (int i = tid; i < NS * S; i += GEN_NT) regA[i] = fmaxf(__ldcg(p.skipbuf + i), 0.f);
         __syncthreads();
         for (int it = warp; it < nE; it += GEN_WARPS) {
-            const int row = it * G + cta;
+            const int row = oE + it;
             const float bias = __ldg(p.e1b + row);
             for (int s0 = 0; s0 < NS; s0 += SB) {
                 float acc[SB];
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
         for (int i = tid; i < NS * E; i += GEN_NT) regB[i] = __ldcg(p.y1buf + i);
         __syncthreads();
         for (int it = warp; it < nC; it += GEN_WARPS) {
-            const int row = it * G + cta;
+            const int row = oC + it;
             const float bias = __ldg(p.e2b + row);
             const float dc = (float)row - (float)C / 2.f;
             const float reg = (dc * dc) * p.regularize;
@@ -464,12 +474,12 @@ __device__ __forceinline__ const float* stage_row(const GenParams& p, const GenL
     const int NL = p.n_layers;
     if (st < 2 * NL) {
         const GenLayer& L = layers[st >> 1];
-        if ((st & 1) == 0) return ((i & 1) ? L.wg : L.wf) + (size_t)((i >> 1) * G + cta) * d.K;
-        if (i < d.n_first) return L.wr + (size_t)(i * G + cta) * d.K;
-        return L.ws + (size_t)((i - d.n_first) * G + cta) * d.K;
+        if ((st & 1) == 0) return ((i & 1) ? L.wg : L.wf) + (size_t)(cta * own_per(p.D, G) + (i >> 1)) * d.K;
+        if (i < d.n_first) return L.wr + (size_t)(cta * own_per(p.R, G) + i) * d.K;
+        return L.ws + (size_t)(cta * own_per(p.S, G) + (i - d.n_first)) * d.K;
     }
-    if (st == 2 * NL) return p.e1w + (size_t)(i * G + cta) * d.K;
-    return p.e2w + (size_t)(i * G + cta) * d.K;
+    if (st == 2 * NL) return p.e1w + (size_t)(cta * own_per(p.E, G) + i) * d.K;
+    return p.e2w + (size_t)(cta * own_per(p.C, G) + i) * d.K;
 }
 
 template <int SB, bool PREFETCH>
@@ -491,11 +501,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
     const int cta = blockIdx.x, G = gridDim.x;
     const int NS = p.NS, R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, k = p.k, NL = p.n_layers;
     const int K1 = k * R;
-    const int nD = (D > cta) ? (D - cta + G - 1) / G : 0;
-    const int nR = (R > cta) ? (R - cta + G - 1) / G : 0;
-    const int nS = (S > cta) ? (S - cta + G - 1) / G : 0;
-    const int nE = (E > cta) ? (E - cta + G - 1) / G : 0;
-    const int nC = (C > cta) ? (C - cta + G - 1) / G : 0;
+    const int nD = own_cnt(D, G, cta), oD = cta * own_per(D, G);
+    const int nR = own_cnt(R, G, cta), oR = cta * own_per(R, G);
+    const int nS = own_cnt(S, G, cta), oS = cta * own_per(S, G);
+    const int nE = own_cnt(E, G, cta), oE = cta * own_per(E, G);
+    const int nC = own_cnt(C, G, cta), oC = cta * own_per(C, G);
     const int NSLOT = p.n_wslots;
 
     for (int s = tid; s < NS; s += GEN_NT) idx_s[s] = p.cur_idx[s];
@@ -593,7 +603,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
                     int c = idx_s[s];
                     c = c < 0 ? 0 : (c >= C ? C - 1 : c);
                     v = __ldg(p.start_w + (size_t)r * C + c) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
-                    if (r % G == cta) st_pair(ring + ((size_t)slot_t * NS + s) * R + r, v, tag);       // enqueue
+                    if (r >= oR && r < oR + nR) st_pair(ring + ((size_t)slot_t * NS + s) * R + r, v, tag);       // enqueue
                 } else {
                     const int tt = t - (k - 1 - j) * L.dil;
                     if (tt < 0) v = 0.f;                                                             // zero history
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
             if (PREFETCH && tid == GEN_NT - 1) produce_one();
             uint2* zl = p.zLL + ((size_t)(par * NL + l) * NS) * D;
             for (int i = tid; i < nD * NS; i += GEN_NT) {
-                const int ci = i / NS, s = i - ci * NS, c = ci * G + cta;
+                const int ci = i / NS, s = i - ci * NS, c = oD + ci;
                 const float f = sum_parts(2 * ci, nw, s) + (L.bf ? __ldg(L.bf + c) : 0.f);
                 const float g = sum_parts(2 * ci + 1, nw, s) + (L.bg ? __ldg(L.bg + c) : 0.f);
                 st_pair(zl + (size_t)s * D + c, tanhf(f) * sigmoid_(g), tag);
@@ -629,13 +639,13 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
             for (int i = tid; i < d2.n * NS; i += GEN_NT) {
                 const int it = i / NS, s = i - it * NS;
                 if (it < d2.n_first) {
-                    const int row = it * G + cta;
+                    const int row = oR + it;
                     const GenLayer& Ln = lay_s[l + 1];
                     const float v = sum_parts(it, nw, s) + (L.br ? __ldg(L.br + row) : 0.f);
                     const float cur = regA[(size_t)s * K1 + row * k + (k - 1)];
                     st_pair(p.ringLL + Ln.ring_off + ((size_t)(t % Ln.ring_len) * NS + s) * R + row, v + cur, tag);
                 } else {
-                    const int li = it - d2.n_first, row = li * G + cta;
+                    const int li = it - d2.n_first, row = oS + li;
                     const float v = sum_parts(it, nw, s) + (L.bs ? __ldg(L.bs + row) : 0.f);
                     skacc[li * NS + s] = v + skacc[li * NS + s];
                 }
@@ -649,7 +659,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         uint2* skl = p.skipLL + (size_t)par * NS * S;
         for (int i = tid; i < nS * NS; i += GEN_NT) {
             const int li = i / NS, s = i - li * NS;
-            st_pair(skl + (size_t)s * S + li * G + cta, skacc[i], tag);
+            st_pair(skl + (size_t)s * S + oS + li, skacc[i], tag);
         }
         int nw;
         StageDesc dA = stage_desc(p, 2 * NL, true, nD, nR, nS, nE, nC);
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         if (PREFETCH && tid == GEN_NT - 1) produce_one();
         uint2* yl = p.y1LL + (size_t)par * NS * E;
         for (int i = tid; i < nE * NS; i += GEN_NT) {
-            const int it = i / NS, s = i - it * NS, row = it * G + cta;
+            const int it = i / NS, s = i - it * NS, row = oE + it;
             st_pair(yl + (size_t)s * E + row, fmaxf(sum_parts(it, nw, s) + __ldg(p.e1b + row), 0.f), tag);
         }
         StageDesc dB = stage_desc(p, 2 * NL + 1, true, nD, nR, nS, nE, nC);
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
         if (PREFETCH && tid == GEN_NT - 1) produce_one();
         uint2* lgl = p.logitLL + (size_t)par * NS * C;
         for (int i = tid; i < nC * NS; i += GEN_NT) {
-            const int it = i / NS, s = i - it * NS, row = it * G + cta;
+            const int it = i / NS, s = i - it * NS, row = oC + it;
             const float dc = (float)row - (float)C / 2.f;
             const float v = (sum_parts(it, nw, s) + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
             st_pair(lgl + (size_t)s * C + row, v, tag);
@@ -781,6 +791,77 @@ __device__ __forceinline__ void poll2(const uint2* p, unsigned tag, float& v0, f
     v1 = __uint_as_float(q.b.x);
 }
 
+constexpr int FAST_MAXI = 4;      // float4 iterations per lane per row part (K part <= 512)
+
+// All the pairs one lane multiplies in a stage, fetched with every load in flight at once (one L2 round trip when the
+// data is already there) and re-fetched as a batch until all tags match.  Iteration `it` covers pairs
+// [first + it*128, +4) of `base` (4 consecutive values = one float4 of the weight row).
+__device__ __forceinline__ void poll_quads(const uint2* base, int first, int n_iter, unsigned tag, float (&v)[FAST_MAXI][4],
+                                           int* err, int* abort_s) {
+    Pair2 a[FAST_MAXI], b[FAST_MAXI];
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll
+        for (int it = 0; it < FAST_MAXI; ++it)
+            if (it < n_iter) {
+                a[it] = ld_pair2(base + first + it * 128);
+                b[it] = ld_pair2(base + first + it * 128 + 2);
+            }
+        bool ok = true;
+#pragma unroll
+        for (int it = 0; it < FAST_MAXI; ++it)
+            if (it < n_iter) ok = ok && a[it].a.y == tag && a[it].b.y == tag && b[it].a.y == tag && b[it].b.y == tag;
+        if (ok) break;
+        if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+            *reinterpret_cast<volatile int*>(err) = 1;
+            *reinterpret_cast<volatile int*>(abort_s) = 1;
+            break;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < FAST_MAXI; ++it)
+        if (it < n_iter) {
+            v[it][0] = __uint_as_float(a[it].a.x); v[it][1] = __uint_as_float(a[it].b.x);
+            v[it][2] = __uint_as_float(b[it].a.x); v[it][3] = __uint_as_float(b[it].b.x);
+        }
+}
+// Same for the 2-tap conv input: iteration `it` needs channels (r0, r0+1), r0 = first_r + it*64, from two ring slots
+// (time t-d with tag_old unless the history is still empty, time t with tag_cur unless `cur` comes from elsewhere).
+__device__ __forceinline__ void poll_taps(const uint2* old_slot, unsigned tag_old, bool have_old, const uint2* cur_slot,
+                                          unsigned tag_cur, bool have_cur, int first_r, int n_iter,
+                                          float (&o)[FAST_MAXI][2], float (&c)[FAST_MAXI][2], int* err, int* abort_s) {
+    Pair2 a[FAST_MAXI], b[FAST_MAXI];
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll
+        for (int it = 0; it < FAST_MAXI; ++it)
+            if (it < n_iter) {
+                if (have_old) a[it] = ld_pair2(old_slot + first_r + it * 64);
+                if (have_cur) b[it] = ld_pair2(cur_slot + first_r + it * 64);
+            }
+        bool ok = true;
+#pragma unroll
+        for (int it = 0; it < FAST_MAXI; ++it)
+            if (it < n_iter) {
+                if (have_old) ok = ok && a[it].a.y == tag_old && a[it].b.y == tag_old;
+                if (have_cur) ok = ok && b[it].a.y == tag_cur && b[it].b.y == tag_cur;
+            }
+        if (ok) break;
+        if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+            *reinterpret_cast<volatile int*>(err) = 1;
+            *reinterpret_cast<volatile int*>(abort_s) = 1;
+            break;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < FAST_MAXI; ++it)
+        if (it < n_iter) {
+            o[it][0] = have_old ? __uint_as_float(a[it].a.x) : 0.f;
+            o[it][1] = have_old ? __uint_as_float(a[it].b.x) : 0.f;
+            if (have_cur) { c[it][0] = __uint_as_float(b[it].a.x); c[it][1] = __uint_as_float(b[it].b.x); }
+        }
+}
+
 template <bool PREFETCH>
 __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -796,13 +877,12 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
     int* misc = slot_s + p.n_layers;                                           // [0] current index, [1] abort
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cta = blockIdx.x, G = gridDim.x, gmask = G - 1;
+    const int cta = blockIdx.x, G = gridDim.x;
     const int R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, NL = p.n_layers;
     const int K1 = 2 * R;
     const int nD = D / G, nR = R / G, nS = S / G, nE = E / G, nC = C / G;
+    const int oD = cta * nD, oR = cta * nR, oS = cta * nS, oE = cta * nE, oC = cta * nC;
     const int NSLOT = p.n_wslots;
-    int g_shift = 0;
-    while ((1 << g_shift) < G) ++g_shift;
     // fixed warp -> (row, K-part) assignment per stage kind
     const int HS1 = GEN_WARPS / (2 * nD), HS2 = GEN_WARPS / (nR + nS), HSA = GEN_WARPS / nE, HSB = GEN_WARPS / nC;
 
@@ -891,29 +971,32 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             {
                 const int row = warp / HS1, kp = warp - row * HS1, Kp = K1 / HS1;
                 const float* w = stage_weights(2 * l, row, K1);
+                const int g4_0 = (kp * Kp >> 2) + lane;            // first float4 of this lane; next ones are +32
+                const int n_iter = ((Kp >> 2) - lane + 31) / 32;   // float4 iterations of this lane (may be 0)
+                float o[FAST_MAXI][2], c[FAST_MAXI][2];
+                poll_taps(ring + (size_t)slot_old * R, (unsigned)(t - L.dil) + 1u, have_old, ring + (size_t)slot_t * R, tag,
+                          l != 0, 2 * g4_0, n_iter, o, c, p.err, abort_s);
                 float acc = 0.f;
-                for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
-                    const int g4 = (kp * Kp >> 2) + i4;            // float4 index within the row
-                    const int r0 = 2 * g4;                         // channels r0, r0+1
-                    float o0 = 0.f, o1 = 0.f, c0, c1;
-                    if (have_old) poll2(ring + (size_t)slot_old * R + r0, (unsigned)(t - L.dil) + 1u, o0, o1, p.err, abort_s);
-                    if (l == 0) {
-                        c0 = __ldg(p.start_w + (size_t)r0 * C + idx) + (p.start_b ? __ldg(p.start_b + r0) : 0.f);
-                        c1 = __ldg(p.start_w + (size_t)(r0 + 1) * C + idx) + (p.start_b ? __ldg(p.start_b + r0 + 1) : 0.f);
-                        if (row == 0) {                            // one warp row covers every channel once: it enqueues
-                            if ((r0 & gmask) == cta) st_pair(ring + (size_t)slot_t * R + r0, c0, tag);
-                            if (((r0 + 1) & gmask) == cta) st_pair(ring + (size_t)slot_t * R + r0 + 1, c1, tag);
+#pragma unroll
+                for (int it = 0; it < FAST_MAXI; ++it)
+                    if (it < n_iter) {
+                        const int g4 = g4_0 + it * 32, r0 = 2 * g4;
+                        if (l == 0) {
+                            c[it][0] = __ldg(p.start_w + (size_t)r0 * C + idx) + (p.start_b ? __ldg(p.start_b + r0) : 0.f);
+                            c[it][1] = __ldg(p.start_w + (size_t)(r0 + 1) * C + idx) + (p.start_b ? __ldg(p.start_b + r0 + 1) : 0.f);
+                            if (row == 0) {                        // one warp row covers every channel once: it enqueues
+                                if (r0 >= oR && r0 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0, c[it][0], tag);
+                                if (r0 + 1 >= oR && r0 + 1 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0 + 1, c[it][1], tag);
+                            }
                         }
-                    } else {
-                        poll2(ring + (size_t)slot_t * R + r0, tag, c0, c1, p.err, abort_s);
+                        if (row == 0) {
+                            if (r0 >= oR && r0 < oR + nR) cur_l[r0 - oR] = c[it][0];
+                            if (r0 + 1 >= oR && r0 + 1 < oR + nR) cur_l[r0 + 1 - oR] = c[it][1];
+                        }
+                        const float4 w4 = ldw(w, g4);
+                        acc = fmaf(w4.x, o[it][0], acc); acc = fmaf(w4.y, c[it][0], acc);
+                        acc = fmaf(w4.z, o[it][1], acc); acc = fmaf(w4.w, c[it][1], acc);
                     }
-                    if (row == 0) {
-                        if ((r0 & gmask) == cta) cur_l[r0 >> g_shift] = c0;
-                        if (((r0 + 1) & gmask) == cta) cur_l[(r0 + 1) >> g_shift] = c1;
-                    }
-                    const float4 w4 = ldw(w, g4);
-                    acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, c0, acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, c1, acc);
-                }
                 acc = warp_sum(acc);
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
                 ++cons_q;
@@ -923,7 +1006,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             if (PREFETCH && tid == GEN_NT - 1) produce_one();
             uint2* zl = p.zLL + (size_t)(par * NL + l) * D;
             if (tid < nD) {
-                const int c = tid * G + cta;
+                const int c = oD + tid;
                 const float* pf = part + stage_par * GEN_WARPS + (2 * tid) * HS1;
                 float f = pf[0], g = pf[HS1];
                 for (int q = 1; q < HS1; ++q) { f += pf[q]; g += pf[HS1 + q]; }
@@ -940,14 +1023,16 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                 const float* w = stage_weights(2 * l + 1, row, D);
                 float acc = 0.f;
                 if (active) {
-                    for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
-                        const int g4 = (kp * Kp >> 2) + i4;
-                        float z0, z1, z2, z3;
-                        poll2(zl + 4 * g4, tag, z0, z1, p.err, abort_s);
-                        poll2(zl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
-                        const float4 w4 = ldw(w, g4);
-                        acc = fmaf(w4.x, z0, acc); acc = fmaf(w4.y, z1, acc); acc = fmaf(w4.z, z2, acc); acc = fmaf(w4.w, z3, acc);
-                    }
+                    const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
+                    float z[FAST_MAXI][4];
+                    poll_quads(zl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
+#pragma unroll
+                    for (int it = 0; it < FAST_MAXI; ++it)
+                        if (it < n_iter) {
+                            const float4 w4 = ldw(w, g4_0 + it * 32);
+                            acc = fmaf(w4.x, z[it][0], acc); acc = fmaf(w4.y, z[it][1], acc);
+                            acc = fmaf(w4.z, z[it][2], acc); acc = fmaf(w4.w, z[it][3], acc);
+                        }
                     acc = warp_sum(acc);
                 }
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
@@ -962,13 +1047,13 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                 for (int q = 1; q < HS2; ++q) v += ps[q];
                 if (tid < nR) {
                     if (l + 1 < NL) {
-                        const int row = tid * G + cta;
+                        const int row = oR + tid;
                         const GenLayer& Ln = lay_s[l + 1];
                         v += L.br ? __ldg(L.br + row) : 0.f;
                         st_pair(p.ringLL + Ln.ring_off + (size_t)slot_s[l + 1] * R + row, v + cur_l[tid], tag);
                     }
                 } else if (want_head) {
-                    const int li = tid - nR, row = li * G + cta;
+                    const int li = tid - nR, row = oS + li;
                     v += L.bs ? __ldg(L.bs + row) : 0.f;
                     skacc[li] = v + skacc[li];
                 }
@@ -981,20 +1066,23 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
 
         // ================= head
         uint2* skl = p.skipLL + (size_t)par * S;
-        if (tid >= nR && tid < nR + nS) st_pair(skl + (tid - nR) * G + cta, skacc[tid - nR], tag);   // same thread that summed it
+        if (tid >= nR && tid < nR + nS) st_pair(skl + oS + (tid - nR), skacc[tid - nR], tag);   // same thread that summed it
         uint2* yl = p.y1LL + (size_t)par * E;
         {
             const int row = warp / HSA, kp = warp - row * HSA, Kp = S / HSA;
             const float* w = stage_weights(2 * NL, row, S);
             float acc = 0.f;
-            for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
-                const int g4 = (kp * Kp >> 2) + i4;
-                float z0, z1, z2, z3;
-                poll2(skl + 4 * g4, tag, z0, z1, p.err, abort_s);
-                poll2(skl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
-                const float4 w4 = ldw(w, g4);
-                acc = fmaf(w4.x, fmaxf(z0, 0.f), acc); acc = fmaf(w4.y, fmaxf(z1, 0.f), acc);
-                acc = fmaf(w4.z, fmaxf(z2, 0.f), acc); acc = fmaf(w4.w, fmaxf(z3, 0.f), acc);
+            {
+                const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
+                float z[FAST_MAXI][4];
+                poll_quads(skl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
+#pragma unroll
+                for (int it = 0; it < FAST_MAXI; ++it)
+                    if (it < n_iter) {
+                        const float4 w4 = ldw(w, g4_0 + it * 32);
+                        acc = fmaf(w4.x, fmaxf(z[it][0], 0.f), acc); acc = fmaf(w4.y, fmaxf(z[it][1], 0.f), acc);
+                        acc = fmaf(w4.z, fmaxf(z[it][2], 0.f), acc); acc = fmaf(w4.w, fmaxf(z[it][3], 0.f), acc);
+                    }
             }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
@@ -1004,7 +1092,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         if (*abort_s) return;
         if (PREFETCH && tid == GEN_NT - 1) produce_one();
         if (tid < nE) {
-            const int row = tid * G + cta;
+            const int row = oE + tid;
             const float* ps = part + stage_par * GEN_WARPS + tid * HSA;
             float v = ps[0];
             for (int q = 1; q < HSA; ++q) v += ps[q];
@@ -1016,13 +1104,17 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             const int row = warp / HSB, kp = warp - row * HSB, Kp = E / HSB;
             const float* w = stage_weights(2 * NL + 1, row, E);
             float acc = 0.f;
-            for (int i4 = lane; i4 < (Kp >> 2); i4 += 32) {
-                const int g4 = (kp * Kp >> 2) + i4;
-                float z0, z1, z2, z3;
-                poll2(yl + 4 * g4, tag, z0, z1, p.err, abort_s);
-                poll2(yl + 4 * g4 + 2, tag, z2, z3, p.err, abort_s);
-                const float4 w4 = ldw(w, g4);
-                acc = fmaf(w4.x, z0, acc); acc = fmaf(w4.y, z1, acc); acc = fmaf(w4.z, z2, acc); acc = fmaf(w4.w, z3, acc);
+            {
+                const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
+                float z[FAST_MAXI][4];
+                poll_quads(yl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
+#pragma unroll
+                for (int it = 0; it < FAST_MAXI; ++it)
+                    if (it < n_iter) {
+                        const float4 w4 = ldw(w, g4_0 + it * 32);
+                        acc = fmaf(w4.x, z[it][0], acc); acc = fmaf(w4.y, z[it][1], acc);
+                        acc = fmaf(w4.z, z[it][2], acc); acc = fmaf(w4.w, z[it][3], acc);
+                    }
             }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
@@ -1032,7 +1124,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         if (*abort_s) return;
         if (PREFETCH && tid == GEN_NT - 1) produce_one();
         if (tid < nC) {
-            const int row = tid * G + cta;
+            const int row = oC + tid;
             const float* ps = part + stage_par * GEN_WARPS + tid * HSB;
             float v = ps[0];
             for (int q = 1; q < HSB; ++q) v += ps[q];
@@ -1246,10 +1338,16 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     p.bar = reinterpret_cast<unsigned*>(h->scratch + h->lay.bar);
 
     // grid: as many CTAs as keep the per-stage row count per CTA minimal, at most one per SM
-    const int rows_max = s->D;
-    const int per = ceil_div(rows_max, sms);
-    int G = ceil_div(rows_max, per);
-    if (G > sms) G = sms;
+    // grid: a power of two, at most one CTA per SM, and -- when the net is wide enough -- at least 4 rows of every
+    // exchanged vector per CTA so that a CTA's published pairs fill whole 32-byte sectors (see own_per above)
+    int mind = s->D;
+    if (s->R < mind) mind = s->R;
+    if (s->E < mind) mind = s->E;
+    if (s->classes < mind) mind = s->classes;
+    int G = 1;
+    while (G * 2 <= sms && G * 2 * 4 <= mind) G *= 2;
+    if (G == 1)
+        while (G * 2 <= sms && G * 2 <= s->D) G *= 2;
     if (const char* e = getenv("WN_GEN_GRID")) {            // tuning knob: fewer, fatter CTAs
         const int v = atoi(e);
         if (v >= 1 && v <= G) G = v;
@@ -1321,7 +1419,7 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
         auto split_ok = [&](int rows, int K) {
             if (!(rows == 1 || rows == 2 || rows == 4 || rows == 8)) return false;
             const int hs = GEN_WARPS / rows;
-            return K % hs == 0 && (K / hs) % 4 == 0 && (K / hs) >= 32;
+            return K % hs == 0 && (K / hs) % 4 == 0 && (K / hs) >= 32 && (K / hs) <= FAST_MAXI * 128;
         };
         bool ok = NS == 1 && s->k == 2 && pow2(G) && G >= 2 && s->n_layers >= 2 && s->D % G == 0 && s->R % G == 0 &&
                   s->S % G == 0 && s->E % G == 0 && s->classes % G == 0;
