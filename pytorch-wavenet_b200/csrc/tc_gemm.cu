@@ -7,11 +7,11 @@
 //            the dilation; frames left of in_start come back as zeros from the TMA out-of-bounds fill)
 //            epilogue: z = tanh(F+bf) * sigmoid(G+bg)  -> z (B,L,D)  [+ optional f,g for the backward]
 //   pass B   [O|S][128 x 256] per tile = z[128 x D] * Wb^T ;  h_out = O + br + h_in,  skip (+)= S + bs
-// Kernel anatomy (one CTA per SM, persistent over (sequence, 128-frame tile) items, 256 threads):
-//   warp 0      TMA producer: per K slab (32 fp32 = one 128B swizzle row) loads A raw, W_hi, W_lo
-//   warp 1      allocates TMEM, issues tcgen05.mma kind::tf32 (M128 N256 K8): hi*hi + lo*hi + hi*lo per k-step
-//   warps 2-3   splitter: rewrite the landed A slab as hi = rna_tf32(x) in place and lo = x - hi in a second buffer
-//   warps 4-7   epilogue: tcgen05.ld the finished accumulator (2 x 256 TMEM columns, double buffered) and store
+// Kernel anatomy (one CTA per SM, persistent over (sequence, 128-frame tile) items, 320 threads):
+//   warp 0        TMA producer: per K slab (16 fp32 = one 64-byte swizzle row) loads A raw, W_hi, W_lo (4-stage ring)
+//   warp 1        allocates TMEM, issues tcgen05.mma kind::tf32 (M128 N256 K8): hi*hi + lo*hi + hi*lo per k-step
+//   warps 2,3,8,9 splitter: rewrite the landed A slab as hi = rna_tf32(x) in place and lo = x - hi in a second buffer
+//   warps 4-7     epilogue: tcgen05.ld the finished accumulator (2 x 256 TMEM columns, double buffered) and store
 // mbarriers: full (TMA landed), split (lo ready), empty (MMAs of the stage retired), acc_full / acc_empty.
 #include "common.cuh"
 #include <cuda.h>
@@ -22,12 +22,13 @@ namespace tc {
 
 constexpr int BM = 128;            // frames per tile (UMMA M)
 constexpr int BN = 256;            // output columns per tile (UMMA N)
-constexpr int BK = 32;             // fp32 per K slab = 128 bytes = one swizzle row
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4;          // 16 KB
-constexpr int W_BYTES = BN * BK * 4;          // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 96 KB
-constexpr int NTHREADS = 256;
+constexpr int BK = 16;             // fp32 per K slab = 64 bytes = one 64B-swizzle row (two k-steps of 8)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;          // 8 KB
+constexpr int W_BYTES = BN * BK * 4;          // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
+constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
+constexpr int SPLIT_THREADS = 128;
 constexpr unsigned SPIN_LIMIT = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -91,14 +92,17 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major rows of BK*4 bytes with the matching swizzle
+// (64B rows -> SWIZZLE_64B, 128B rows -> SWIZZLE_128B); 8-row atoms are 8*row_bytes apart
 __device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
+    constexpr unsigned row_bytes = BK * 4;
+    constexpr unsigned long long layout = (row_bytes == 128) ? 2ull : 4ull;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
     unsigned long long d = 0;
     d |= (unsigned long long)((saddr >> 4) & 0x3fff);            // start address, 16-byte units
     d |= (unsigned long long)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (unsigned long long)(1024 >> 4) << 32;                  // stride byte offset between 8-row atoms
+    d |= (unsigned long long)((8 * row_bytes) >> 4) << 32;       // stride byte offset between 8-row atoms
     d |= (unsigned long long)1 << 46;                            // descriptor version (Blackwell)
-    d |= (unsigned long long)2 << 61;                            // SWIZZLE_128B
+    d |= layout << 61;
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32, both K-major, M=128, N=256
@@ -146,7 +150,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int slabs = p.taps * slabs_per_tap;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, 64); mbar_init(empty + i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -211,9 +215,9 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     __syncwarp();
                 }
             }
-    } else if (warp < 4) {
-        // ================================================================= splitter (64 threads)
-        const int st_tid = tid - 64;
+    } else if (warp < 4 || warp >= 8) {
+        // ================================================================= splitter (warps 2,3,8,9 = 128 threads)
+        const int st_tid = warp < 4 ? tid - 64 : tid - 192;
         unsigned it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x)
             for (int nt = 0; nt < p.n_tiles; ++nt)
@@ -223,8 +227,8 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(full + st, ph);
                     float4* hi = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES);
                     float4* lo = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES + A_BYTES);
-#pragma unroll 4
-                    for (int i = st_tid; i < A_BYTES / 16; i += 64) {
+#pragma unroll
+                    for (int i = st_tid; i < A_BYTES / 16; i += SPLIT_THREADS) {
                         const float4 x = hi[i];
                         float4 h, l;
                         unsigned u;
@@ -291,25 +295,26 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                          : p.out1 + ((size_t)b * (p.L - p.skip_start) + (t - p.skip_start)) * p.S + (n0 - p.R);
                     const float* rrow = p.res + ((size_t)b * p.L + t) * p.R + n0;
 #pragma unroll 1
-                    for (int c = 0; c < BN; c += 16) {
-                        float v[16];
-                        tmem_ld16(taddr + c, v);
-                        tmem_ld_wait();
-                        if (is_res ? live : skip_live) {
+                    for (int c = 0; c < BN; c += 32) {
+                        float v[32];
+                        float4 x[8];
+                        const bool on = is_res ? live : skip_live;
+                        const bool need_x = on && (is_res ? (t >= p.in_start) : !p.skip_init);
+                        tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+                        tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                        if (need_x) {                                  // residual h_in(t) or running skip: all 8 loads in flight
+                            const float* src = is_res ? rrow + c : orow + c;
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                float4 o = make_float4(v[i] + bt[c + i], v[i + 1] + bt[c + i + 1], v[i + 2] + bt[c + i + 2],
-                                                       v[i + 3] + bt[c + i + 3]);
-                                if (is_res) {
-                                    if (t >= p.in_start) {
-                                        const float4 x = __ldg(reinterpret_cast<const float4*>(rrow + c + i));
-                                        o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                                    }
-                                } else if (!p.skip_init) {
-                                    const float4 x = *reinterpret_cast<const float4*>(orow + c + i);
-                                    o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                                }
-                                *reinterpret_cast<float4*>(orow + c + i) = o;
+                            for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(src + 4 * i);
+                        }
+                        tmem_ld_wait();
+                        if (on) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4 o = make_float4(v[4 * i] + bt[c + 4 * i], v[4 * i + 1] + bt[c + 4 * i + 1],
+                                                       v[4 * i + 2] + bt[c + 4 * i + 2], v[4 * i + 3] + bt[c + 4 * i + 3]);
+                                if (need_x) { o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w; }
+                                *reinterpret_cast<float4*>(orow + c + 4 * i) = o;
                             }
                         }
                     }
@@ -387,7 +392,7 @@ static int make_act_map(CUtensorMap* m, const float* base, int B, int L, int C, 
     cuuint32_t box[3] = {BK, BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(base + (size_t)origin * C), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
     return 0;
@@ -401,7 +406,8 @@ static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
     cuuint32_t box[2] = {BK, BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
     return 0;
 }
