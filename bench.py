@@ -298,6 +298,32 @@ def bench_train(args, world, rank):
             am_host.copy_(am, non_blocking=True)
             torch.cuda.synchronize()
         e2e_idx_s = max_over_ranks(time.perf_counter() - t0, world)
+    # full training step on the same shapes: forward (saving activations) + backward + per-block gradient all-reduce
+    import torch.nn.functional as F
+    import data_parallel as dp
+    red = dp.make_data_parallel(model)
+    target = torch.randint(0, 256, (B * model.output_length,), generator=torch.Generator().manual_seed(99 + rank)).cuda()
+    step_ms = []
+    for i in range(1 + max(1, min(args.steps, 3))):
+        model.zero_grad(set_to_none=True)
+        barrier_sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = F.cross_entropy(model.forward_indices(d_idx), target)
+        loss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            step_ms.append(e0.elapsed_time(e1))
+    step_t = max_over_ranks(sum(step_ms) / len(step_ms), world)
+    train_step = {"ms_per_step": step_t, "frames_per_s": world * B * L / (step_t / 1e3), "loss": float(loss),
+                  "grad_allreduce_bytes_per_step": red.bytes_reduced // max(1, 1 + len(step_ms)) if world > 1 else 0,
+                  "grad_buckets_per_step": red.buckets // max(1, 1 + len(step_ms)) if world > 1 else 0,
+                  "note": "forward (tensor-core blocks, activations saved) + backward data kernels (fp32 SIMT) + weight-gradient "
+                          "GEMMs (cuBLAS fp32) + NCCL all-reduce per block overlapped with the backward"}
+    model._runtime().grad_reducer = None
+    del loss
+    model.zero_grad(set_to_none=True)
     per_layer, start_b, head_b, flops = train_alg_bytes(model, B, L, dense_input=False)
     n_layers = len(per_layer)
     peak, peak_src = measured_peaks()
@@ -328,7 +354,7 @@ def bench_train(args, world, rank):
                 clocks=clk, e2e=e2e, e2e_index_api={"value": world * B * L * e2e_steps / e2e_idx_s, "unit": "frames/s",
                                                    "h2d_bytes_per_step": int(idx_host.numel()),
                                                    "d2h_bytes_per_step": int(am.numel() * 8)},
-                roofline=roof, dtype="f32", scaling="weak",
+                roofline=roof, train_step=train_step, dtype="f32", scaling="weak",
                 config={"workload": "cfg3 forward: layers=10 blocks=5 ch=256, B=8 per GPU, L=16000, output_length=10885, "
                                     "uint8 index input resident in HBM", "block_kernels": mode, "global_batch": world * B, "seq_len": L,
                         "parallelism": f"dp{world} (batch shards, no collective in forward)"},

@@ -800,6 +800,7 @@ __device__ __forceinline__ void poll_quads(const uint2* base, int first, int n_i
                                            int* err, int* abort_s) {
     Pair2 a[FAST_MAXI], b[FAST_MAXI];
     const long long t0 = clock64();
+    unsigned spins = 0;
     for (;;) {
 #pragma unroll
         for (int it = 0; it < FAST_MAXI; ++it)
@@ -812,7 +813,8 @@ __device__ __forceinline__ void poll_quads(const uint2* base, int first, int n_i
         for (int it = 0; it < FAST_MAXI; ++it)
             if (it < n_iter) ok = ok && a[it].a.y == tag && a[it].b.y == tag && b[it].a.y == tag && b[it].b.y == tag;
         if (ok) break;
-        if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+        if ((++spins & 255u) == 0 &&
+            (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0)) {
             *reinterpret_cast<volatile int*>(err) = 1;
             *reinterpret_cast<volatile int*>(abort_s) = 1;
             break;
@@ -873,7 +875,8 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
     float* wbuf = reinterpret_cast<float*>(cdf + p.C);                         // [n_wslots][wslot_floats]
     unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
     GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);
-    int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);                  // [NL] ring slot of time t per layer
+    uint2* old_s = reinterpret_cast<uint2*>(lay_s + p.n_layers);               // [2][R] prefetched old taps (see below)
+    int* slot_s = reinterpret_cast<int*>(old_s + 2 * p.R);                     // [NL] ring slot of time t per layer
     int* misc = slot_s + p.n_layers;                                           // [0] current index, [1] abort
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -907,13 +910,14 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
 
     // ---- weight prefetch (same stage sequence as gen_kernel_ll; all rows of a stage are always fetched)
     int pf_ev = 0, pf_st = 0;
-    long long pf_q = 0, cons_q = 0;
+    unsigned pf_q = 0, cons_q = 0;                 // NSLOT is 2 or 4: slot = q & (NSLOT-1), phase = (q / NSLOT) & 1
+    const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
     auto produce_one = [&]() {
         if (pf_ev >= p.n_evals) return;
         const bool wh = (p.t0 + pf_ev >= p.n_given - 1);
         StageDesc d = stage_desc(p, pf_st, true, nD, nR, nS, nE, nC);
         if (pf_st < 2 * NL && (pf_st & 1)) { d.n_first = nR; d.n = nR + nS; }      // fetch residual + skip rows always
-        const int slot = (int)(pf_q % NSLOT);
+        const int slot = (int)(pf_q & smask);
         mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
         float* dst = wbuf + (size_t)slot * p.wslot_floats;
         for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
@@ -925,8 +929,8 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
     // weights of (stage, row): shared-memory slot when prefetching, else the parameter tensor itself
     auto stage_weights = [&](int st, int row, int K) -> const float* {
         if (PREFETCH) {
-            const int slot = (int)(cons_q % NSLOT);
-            mbar_wait(fullb + slot, (unsigned)((cons_q / NSLOT) & 1));
+            const int slot = (int)(cons_q & smask);
+            mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
             return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * K;
         }
         StageDesc d = stage_desc(p, st, true, nD, nR, nS, nE, nC);
@@ -938,6 +942,26 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         return __ldg(reinterpret_cast<const float4*>(w) + i4);
     };
     unsigned stage_par = 0;
+    __syncthreads();
+    // Old taps (the ring slot of time t-d) were written >= 1 evaluation ago and have usually left the L2 by the time
+    // they are needed (the weight stream evicts them), so reading them inside the stage would put an HBM round trip on
+    // the critical path of every layer.  They are fetched one stage ahead with cp.async into shared memory instead:
+    // during stage 2 of layer l for layer l+1 (or for layer 0 of the next evaluation).
+    auto prefetch_old = [&](int ln, int te, int slot_te) {        // slot_te = ring slot of time te in layer ln
+        const GenLayer& Lp = lay_s[ln];
+        if (te >= Lp.dil && tid < R / 2) {
+            const int so = (slot_te + 1 == Lp.ring_len) ? 0 : slot_te + 1;
+            const uint2* src = p.ringLL + Lp.ring_off + (size_t)so * R + 2 * tid;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(old_s + (ln & 1) * R + 2 * tid);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    {
+        const int len0 = lay_s[0].ring_len;
+        prefetch_old(0, p.t0, p.t0 % len0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
 
     for (int ev = 0; ev < p.n_evals; ++ev) {
@@ -974,8 +998,30 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                 const int g4_0 = (kp * Kp >> 2) + lane;            // first float4 of this lane; next ones are +32
                 const int n_iter = ((Kp >> 2) - lane + 31) / 32;   // float4 iterations of this lane (may be 0)
                 float o[FAST_MAXI][2], c[FAST_MAXI][2];
-                poll_taps(ring + (size_t)slot_old * R, (unsigned)(t - L.dil) + 1u, have_old, ring + (size_t)slot_t * R, tag,
-                          l != 0, 2 * g4_0, n_iter, o, c, p.err, abort_s);
+                bool old_ok = true;
+                const unsigned tag_old = (unsigned)(t - L.dil) + 1u;
+                if (have_old) {
+                    const uint2* os = old_s + (l & 1) * R;
+#pragma unroll
+                    for (int it = 0; it < FAST_MAXI; ++it)
+                        if (it < n_iter) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(os + 2 * g4_0 + it * 64);
+                            old_ok = old_ok && q.y == tag_old && q.w == tag_old;
+                            o[it][0] = __uint_as_float(q.x);
+                            o[it][1] = __uint_as_float(q.z);
+                        }
+                }
+                // current taps are polled from L2; the old ones only if the prefetched copy was not there yet (rare)
+                {
+                    float o2[FAST_MAXI][2];
+                    const bool refetch = have_old && !old_ok;
+                    poll_taps(ring + (size_t)slot_old * R, tag_old, refetch, ring + (size_t)slot_t * R, tag, l != 0, 2 * g4_0,
+                              n_iter, o2, c, p.err, abort_s);
+                    if (!have_old || refetch) {
+#pragma unroll
+                        for (int it = 0; it < FAST_MAXI; ++it) { o[it][0] = o2[it][0]; o[it][1] = o2[it][1]; }
+                    }
+                }
                 float acc = 0.f;
 #pragma unroll
                 for (int it = 0; it < FAST_MAXI; ++it)
@@ -1020,6 +1066,8 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                 const int row = warp / HS2, kp = warp - row * HS2, Kp = D / HS2;
                 const bool is_res = row < nR;
                 const bool active = is_res ? (l + 1 < NL) : want_head;
+                if (l + 1 < NL) prefetch_old(l + 1, t, slot_s[l + 1]);
+                else if (ev + 1 < p.n_evals) prefetch_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
                 const float* w = stage_weights(2 * l + 1, row, D);
                 float acc = 0.f;
                 if (active) {
@@ -1037,6 +1085,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                 }
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
                 ++cons_q;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");      // the old taps for the next stage 1 have landed
             }
             __syncthreads();
             if (*abort_s) return;
@@ -1431,11 +1480,11 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
             const size_t fbase = sizeof(float) * (2 * GEN_WARPS + ((s->S / G + 3) & ~3) + 2 * ((s->R / G + 3) & ~3) +
                                                   ((s->classes + 3) & ~3)) +
                                  sizeof(double) * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
-                                 sizeof(int) * (size_t)(s->n_layers + 4);
+                                 sizeof(uint2) * 2 * (size_t)s->R + sizeof(int) * (size_t)(s->n_layers + 4);
             int fs = 0;
             if (fbase < (size_t)smem_optin) {
                 long long fit = ((long long)smem_optin - (long long)fbase) / (slot * 4);
-                fs = fit >= 4 ? 4 : (fit >= 2 ? (int)fit : 0);
+                fs = fit >= 4 ? 4 : (fit >= 2 ? 2 : 0);
             }
             if (getenv("WN_GEN_NOPREFETCH")) fs = 0;
             h->n_wslots_fast = fs;

@@ -29,6 +29,7 @@ constexpr int W_BYTES = BN * BK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
 constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
 constexpr int SPLIT_THREADS = 128;
+constexpr int TP = 36;                      // pitch of the 32x32 epilogue transpose tile (conflict-free 128-bit access)
 constexpr unsigned SPIN_LIMIT = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -142,6 +143,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned long long* acc_empty = bars + 3 * STAGES + 2; // [2]
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * STAGES + 4);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                   // [n_total]
+    float* stage_t = bias_s + ((p.n_total + 3) & ~3);                          // [4 warps][32][TP] epilogue transpose tiles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_tiles = (p.L - p.t_begin + BM - 1) / BM;
@@ -244,43 +246,58 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
     } else {
         // ================================================================= epilogue (warps 4..7 = TMEM lane quadrants 0..3)
-        const int q = warp - 4, row = q * 32 + lane;
+        const int q = warp - 4;
         unsigned tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int b = item / m_tiles, t0 = p.t_begin + (item % m_tiles) * BM;
-            const int t = t0 + row;
-            const bool live = t < p.L;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                 const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
                 mbar_wait(acc_full + ab, aph);
                 tc_fence_after();
                 const unsigned taddr = tmem_base + ab * BN + ((unsigned)(q * 32) << 16);
+                // Each epilogue warp owns 32 accumulator rows (frames).  A 32-column chunk is read from TMEM row-per-thread,
+                // turned through a 32x32 shared-memory tile, and leaves for global memory as whole 128-byte lines
+                // (instruction i: lane -> frame 4i + lane/8, 16-byte piece lane%8): 4 full lines per warp instruction.
+                float* tt = stage_t + q * 32 * TP;
+                const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+                const int tbase = t0 + q * 32;                                   // first frame of this warp's rows
                 if (EPI == EPI_GATE) {
                     // tile columns: [0,128) = F of channels 128*nt.., [128,256) = G of the same channels
-                    float* zrow = p.out0 + ((size_t)b * p.L + t) * p.D + nt * 128;
-                    float* fgrow = p.out1 ? p.out1 + ((size_t)b * p.L + t) * (2 * p.D) + nt * 128 : nullptr;
                     const float* bt = bias_s + nt * BN;
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 16) {
-                        float f[16], g[16];
-                        tmem_ld16(taddr + c, f);
-                        tmem_ld16(taddr + 128 + c, g);
+                    for (int c = 0; c < 128; c += 32) {
+                        float f[32], g[32];
+                        tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&f[0]));
+                        tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&f[16]));
+                        tmem_ld16(taddr + 128 + c, *reinterpret_cast<float(*)[16]>(&g[0]));
+                        tmem_ld16(taddr + 128 + c + 16, *reinterpret_cast<float(*)[16]>(&g[16]));
                         tmem_ld_wait();
-                        if (live) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                f[i] = tanhf(f[i] + bt[c + i]);
-                                g[i] = sigmoid_tc(g[i] + bt[128 + c + i]);
+                        for (int i = 0; i < 32; ++i) {
+                            f[i] = tanhf(f[i] + bt[c + i]);
+                            g[i] = sigmoid_tc(g[i] + bt[128 + c + i]);
+                        }
+                        // three passes through the tile: z, then (optionally) f and g for the backward
+                        const int n_pass = p.out1 ? 3 : 1;
+                        for (int ps = 0; ps < n_pass; ++ps) {
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 v;
+                                if (ps == 0) v = make_float4(f[i] * g[i], f[i + 1] * g[i + 1], f[i + 2] * g[i + 2], f[i + 3] * g[i + 3]);
+                                else if (ps == 1) v = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                                else v = make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]);
+                                *reinterpret_cast<float4*>(tt + lane * TP + i) = v;
                             }
+                            __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4*>(zrow + c + i) =
-                                    make_float4(f[i] * g[i], f[i + 1] * g[i + 1], f[i + 2] * g[i + 2], f[i + 3] * g[i + 3]);
-                            if (fgrow) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4) {
-                                    *reinterpret_cast<float4*>(fgrow + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                                    *reinterpret_cast<float4*>(fgrow + p.D + c + i) = make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]);
+                            for (int i = 0; i < 8; ++i) {
+                                const int fr = tbase + 4 * i + sub_r;
+                                if (fr < p.L) {
+                                    const float4 v = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
+                                    float* dst = (ps == 0) ? p.out0 + ((size_t)b * p.L + fr) * p.D + nt * 128 + c + sub_c
+                                                           : p.out1 + ((size_t)b * p.L + fr) * (2 * p.D) + (ps == 2 ? p.D : 0) + nt * 128 + c + sub_c;
+                                    *reinterpret_cast<float4*>(dst) = v;
                                 }
                             }
                         }
@@ -290,32 +307,44 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int n0 = nt * BN;
                     const bool is_res = n0 < p.R;
                     const float* bt = bias_s + n0;
-                    const bool skip_live = live && t >= p.skip_start;
-                    float* orow = is_res ? p.out0 + ((size_t)b * p.L + t) * p.R + n0
-                                         : p.out1 + ((size_t)b * (p.L - p.skip_start) + (t - p.skip_start)) * p.S + (n0 - p.R);
-                    const float* rrow = p.res + ((size_t)b * p.L + t) * p.R + n0;
+                    const int Tsk = p.L - p.skip_start;
 #pragma unroll 1
                     for (int c = 0; c < BN; c += 32) {
                         float v[32];
-                        float4 x[8];
-                        const bool on = is_res ? live : skip_live;
-                        const bool need_x = on && (is_res ? (t >= p.in_start) : !p.skip_init);
                         tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&v[0]));
                         tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-                        if (need_x) {                                  // residual h_in(t) or running skip: all 8 loads in flight
-                            const float* src = is_res ? rrow + c : orow + c;
+                        // the values this lane will add in the coalesced domain (residual h_in(t) or the running skip)
+                        float4 x[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(src + 4 * i);
+                        for (int i = 0; i < 8; ++i) {
+                            const int fr = tbase + 4 * i + sub_r;
+                            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (fr < p.L) {
+                                if (is_res) {
+                                    if (fr >= p.in_start)
+                                        x[i] = __ldg(reinterpret_cast<const float4*>(p.res + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c));
+                                } else if (!p.skip_init && fr >= p.skip_start) {
+                                    x[i] = *reinterpret_cast<const float4*>(p.out1 + ((size_t)b * Tsk + (fr - p.skip_start)) * p.S + (n0 - p.R) + c + sub_c);
+                                }
+                            }
                         }
                         tmem_ld_wait();
-                        if (on) {
+                        __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float4 o = make_float4(v[4 * i] + bt[c + 4 * i], v[4 * i + 1] + bt[c + 4 * i + 1],
-                                                       v[4 * i + 2] + bt[c + 4 * i + 2], v[4 * i + 3] + bt[c + 4 * i + 3]);
-                                if (need_x) { o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w; }
-                                *reinterpret_cast<float4*>(orow + c + 4 * i) = o;
-                            }
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(tt + lane * TP + i) =
+                                make_float4(v[i] + bt[c + i], v[i + 1] + bt[c + i + 1], v[i + 2] + bt[c + i + 2], v[i + 3] + bt[c + i + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int fr = tbase + 4 * i + sub_r;
+                            if (fr >= p.L) continue;
+                            float4 o = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
+                            o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w;
+                            if (is_res)
+                                *reinterpret_cast<float4*>(p.out0 + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c) = o;
+                            else if (fr >= p.skip_start)
+                                *reinterpret_cast<float4*>(p.out1 + ((size_t)b * Tsk + (fr - p.skip_start)) * p.S + (n0 - p.R) + c + sub_c) = o;
                         }
                     }
                 }
@@ -412,7 +441,9 @@ static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
     return 0;
 }
 
-static size_t tc_smem_bytes(int n_total) { return 1024 + (size_t)STAGES * STAGE_BYTES + 256 + sizeof(float) * n_total; }
+static size_t tc_smem_bytes(int n_total) {
+    return 1024 + (size_t)STAGES * STAGE_BYTES + 256 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 4 * 32 * TP;
+}
 
 template <int EPI>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParams& p, cudaStream_t st) {
