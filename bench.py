@@ -298,6 +298,34 @@ def bench_train(args, world, rank):
             am_host.copy_(am, non_blocking=True)
             torch.cuda.synchronize()
         e2e_idx_s = max_over_ranks(time.perf_counter() - t0, world)
+    # opt-in single-pass TF32 blocks (outside the 1e-4 parity bar; reported for the HBM-bound regime only)
+    fast = None
+    if getattr(rt, "last_block_mode", "") == "tc":
+        with torch.no_grad():
+            y_exact = model.forward_indices(d_idx)
+            rt.fast_tf32 = True
+            for _ in range(2):
+                y_fast = model.forward_indices(d_idx)
+            fe = []
+            for _ in range(max(1, min(args.steps, 3))):
+                flush()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                rt.block_events = (b0, b1)
+                y_fast = model.forward_indices(d_idx)
+                torch.cuda.synchronize()
+                fe.append(b0.elapsed_time(b1))
+            rt.block_events = None
+            rt.fast_tf32 = False
+            err = float((y_fast - y_exact).abs().max() / y_exact.abs().max())
+        fms = sum(fe) / len(fe)
+        per_layer_f, _, _, _ = train_alg_bytes(model, B, L, dense_input=False)
+        hbm_peak, _ = measured_peaks()
+        # pass A writes z and pass B reads it back: 2 more activation passes than the fused algorithmic minimum
+        fast = {"mode": "single-pass TF32 blocks (opt-in, NOT the parity path)", "blocks_ms_per_step": fms,
+                "logits_max_rel_err_vs_exact": err,
+                "hbm_algorithmic_gbs": sum(per_layer_f) / (fms / 1e3) / 1e9,
+                "hbm_frac_of_measured_peak": sum(per_layer_f) / (fms / 1e3) / 1e9 / hbm_peak}
+        del y_exact, y_fast
     # full training step on the same shapes: forward (saving activations) + backward + per-block gradient all-reduce
     import torch.nn.functional as F
     import data_parallel as dp
@@ -354,7 +382,7 @@ def bench_train(args, world, rank):
                 clocks=clk, e2e=e2e, e2e_index_api={"value": world * B * L * e2e_steps / e2e_idx_s, "unit": "frames/s",
                                                    "h2d_bytes_per_step": int(idx_host.numel()),
                                                    "d2h_bytes_per_step": int(am.numel() * 8)},
-                roofline=roof, train_step=train_step, dtype="f32", scaling="weak",
+                roofline=roof, train_step=train_step, fast_tf32=fast, dtype="f32", scaling="weak",
                 config={"workload": "cfg3 forward: layers=10 blocks=5 ch=256, B=8 per GPU, L=16000, output_length=10885, "
                                     "uint8 index input resident in HBM", "block_kernels": mode, "global_batch": world * B, "seq_len": L,
                         "parallelism": f"dp{world} (batch shards, no collective in forward)"},

@@ -864,8 +864,13 @@ __device__ __forceinline__ void poll_taps(const uint2* old_slot, unsigned tag_ol
         }
 }
 
+#define WORKER_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+__device__ __forceinline__ void mbar_arrive_(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
 template <bool PREFETCH>
-__global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) {
+__global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParams p) {
     extern __shared__ __align__(16) float sm[];
     float* part = sm;                                   // [2][GEN_WARPS] partial sums, double buffered by stage parity
     float* skacc = part + 2 * GEN_WARPS;                // [nS]
@@ -874,6 +879,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
     double* cdf = reinterpret_cast<double*>(logit_s + ((p.C + 3) & ~3));       // [C]
     float* wbuf = reinterpret_cast<float*>(cdf + p.C);                         // [n_wslots][wslot_floats]
     unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    unsigned long long* emptyb = fullb + 4;             // consumers -> producer: slot may be refilled (8 warps arrive)
     GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);
     uint2* old_s = reinterpret_cast<uint2*>(lay_s + p.n_layers);               // [2][R] prefetched old taps (see below)
     int* slot_s = reinterpret_cast<int*>(old_s + 2 * p.R);                     // [NL] ring slot of time t per layer
@@ -892,13 +898,13 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
     {
         const int* src = reinterpret_cast<const int*>(p.layers);
         int* dst = reinterpret_cast<int*>(lay_s);
-        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT) dst[i] = src[i];
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
     }
     if (tid == 0) {
         misc[0] = p.cur_idx[0];
         misc[1] = 0;
         if (PREFETCH)
-            for (int i = 0; i < NSLOT; ++i) mbar_init(fullb + i, 1);
+            for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
     }
     if (PREFETCH) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -906,26 +912,41 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         const int len = lay_s[l].ring_len;
         slot_s[l] = (p.t0 + len - 1) % len;
     }
+    // ---- weight prefetch: a dedicated producer warp (warp 8) runs ahead of the 8 worker warps through the same stage
+    // sequence as gen_kernel_ll (all rows of a stage are always fetched); full[slot] = bytes landed, empty[slot] = all
+    // worker warps are done with the slot.  Keeping the producer off the worker warps matters: every stage needs every
+    // worker warp's row, so anything a worker lane does besides its row is on the critical path of the whole GPU.
     int* abort_s = misc + 1;
-
-    // ---- weight prefetch (same stage sequence as gen_kernel_ll; all rows of a stage are always fetched)
-    int pf_ev = 0, pf_st = 0;
-    unsigned pf_q = 0, cons_q = 0;                 // NSLOT is 2 or 4: slot = q & (NSLOT-1), phase = (q / NSLOT) & 1
     const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
-    auto produce_one = [&]() {
-        if (pf_ev >= p.n_evals) return;
-        const bool wh = (p.t0 + pf_ev >= p.n_given - 1);
-        StageDesc d = stage_desc(p, pf_st, true, nD, nR, nS, nE, nC);
-        if (pf_st < 2 * NL && (pf_st & 1)) { d.n_first = nR; d.n = nR + nS; }      // fetch residual + skip rows always
-        const int slot = (int)(pf_q & smask);
-        mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
-        float* dst = wbuf + (size_t)slot * p.wslot_floats;
-        for (int i = 0; i < d.n; ++i) bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, pf_st, d, i, cta, G), d.K * 4, fullb + slot);
-        ++pf_q;
-        if (++pf_st >= (wh ? 2 * NL + 2 : 2 * NL)) { pf_st = 0; ++pf_ev; }
-    };
-    if (PREFETCH && tid == GEN_NT - 1)
-        for (int i = 0; i < NSLOT; ++i) produce_one();
+    if (warp == GEN_WARPS) {
+        if (PREFETCH && lane == 0) {
+            unsigned q = 0;
+            for (int ev = 0; ev < p.n_evals; ++ev) {
+                const bool wh = (p.t0 + ev >= p.n_given - 1);
+                const int n_st = wh ? 2 * NL + 2 : 2 * NL;
+                for (int st = 0; st < n_st; ++st, ++q) {
+                    StageDesc d = stage_desc(p, st, true, nD, nR, nS, nE, nC);
+                    if (st < 2 * NL && (st & 1)) { d.n_first = nR; d.n = nR + nS; }
+                    const int slot = (int)(q & smask);
+                    if (q >= (unsigned)NSLOT) {                       // wait until the workers released this slot
+                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                            if (!done && (++spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(abort_s)) return;
+                        }
+                    }
+                    mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+                    float* dst = wbuf + (size_t)slot * p.wslot_floats;
+                    for (int i = 0; i < d.n; ++i)
+                        bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, st, d, i, cta, G), d.K * 4, fullb + slot);
+                }
+            }
+        }
+        return;
+    }
+    unsigned cons_q = 0;
     // weights of (stage, row): shared-memory slot when prefetching, else the parameter tensor itself
     auto stage_weights = [&](int st, int row, int K) -> const float* {
         if (PREFETCH) {
@@ -942,7 +963,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         return __ldg(reinterpret_cast<const float4*>(w) + i4);
     };
     unsigned stage_par = 0;
-    __syncthreads();
+    WORKER_SYNC();
     // Old taps (the ring slot of time t-d) were written >= 1 evaluation ago and have usually left the L2 by the time
     // they are needed (the weight stream evicts them), so reading them inside the stage would put an HBM round trip on
     // the critical path of every layer.  They are fetched one stage ahead with cp.async into shared memory instead:
@@ -962,7 +983,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         prefetch_old(0, p.t0, p.t0 % len0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
+    WORKER_SYNC();
 
     for (int ev = 0; ev < p.n_evals; ++ev) {
         const int t = p.t0 + ev;
@@ -979,7 +1000,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             slot_s[l] = (s1 == lay_s[l].ring_len) ? 0 : s1;
         }
         for (int i = tid; i < nS; i += GEN_NT) skacc[i] = 0.f;
-        __syncthreads();
+        WORKER_SYNC();
         if (*abort_s) return;
         int idx = misc[0];
         idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
@@ -1045,11 +1066,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                     }
                 acc = warp_sum(acc);
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
                 ++cons_q;
             }
-            __syncthreads();
+            WORKER_SYNC();
             if (*abort_s) return;
-            if (PREFETCH && tid == GEN_NT - 1) produce_one();
             uint2* zl = p.zLL + (size_t)(par * NL + l) * D;
             if (tid < nD) {
                 const int c = oD + tid;
@@ -1084,12 +1105,12 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
                     acc = warp_sum(acc);
                 }
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
                 ++cons_q;
                 asm volatile("cp.async.wait_group 0;" ::: "memory");      // the old taps for the next stage 1 have landed
             }
-            __syncthreads();
+            WORKER_SYNC();
             if (*abort_s) return;
-            if (PREFETCH && tid == GEN_NT - 1) produce_one();
             if (tid < nR + nS) {
                 const float* ps = part + stage_par * GEN_WARPS + tid * HS2;
                 float v = ps[0];
@@ -1135,11 +1156,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
             ++cons_q;
         }
-        __syncthreads();
+        WORKER_SYNC();
         if (*abort_s) return;
-        if (PREFETCH && tid == GEN_NT - 1) produce_one();
         if (tid < nE) {
             const int row = oE + tid;
             const float* ps = part + stage_par * GEN_WARPS + tid * HSA;
@@ -1167,11 +1188,11 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
             ++cons_q;
         }
-        __syncthreads();
+        WORKER_SYNC();
         if (*abort_s) return;
-        if (PREFETCH && tid == GEN_NT - 1) produce_one();
         if (tid < nC) {
             const int row = oC + tid;
             const float* ps = part + stage_par * GEN_WARPS + tid * HSB;
@@ -1190,7 +1211,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
             logit_s[2 * c2] = a;
             logit_s[2 * c2 + 1] = b;
         }
-        __syncthreads();
+        WORKER_SYNC();
         if (*abort_s) return;
         if (warp == 0) {
             int choice;
@@ -1261,7 +1282,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_fast(const GenParams p) 
         }
         // the top-of-evaluation __syncthreads publishes misc[0]
     }
-    __syncthreads();
+    WORKER_SYNC();
     if (cta == 0 && tid == 0) p.cur_idx[0] = misc[0];
 }
 
@@ -1540,10 +1561,10 @@ template <bool PF>
 static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
     int per_sm = 0;
-    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_fast<PF>, GEN_NT, h->smem_fast));
+    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_fast<PF>, GEN_NT + 32, h->smem_fast));
     WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
     void* args[] = {(void*)&p};
-    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_fast<PF>, dim3(h->grid), dim3(GEN_NT), args, h->smem_fast, st));
+    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_fast<PF>, dim3(h->grid), dim3(GEN_NT + 32), args, h->smem_fast, st));
     return 0;
 }
 

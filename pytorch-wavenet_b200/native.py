@@ -46,7 +46,7 @@ class TcBlockArgs(C.Structure):
                 ("d_wa", C.c_void_p), ("d_ba", C.c_void_p), ("d_wb", C.c_void_p), ("d_bb", C.c_void_p),
                 ("B", C.c_int), ("L", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("k", C.c_int),
                 ("dilation", C.c_int), ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int),
-                ("skip_init", C.c_int), ("d_fg_save", C.c_void_p)]
+                ("skip_init", C.c_int), ("d_fg_save", C.c_void_p), ("fast_tf32", C.c_int)]
 
 
 class HeadArgs(C.Structure):

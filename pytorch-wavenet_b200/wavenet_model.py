@@ -59,6 +59,7 @@ class _Runtime:
         self.ws = {}
         self.samplers = {}
         self.block_mode = "auto"     # "auto": tensor-core blocks when the shape allows, "ffma": exact-fp32 SIMT, "tc"
+        self.fast_tf32 = False       # opt-in single-pass TF32 blocks (~1e-3 on the logits: outside the parity bar)
 
     # ------------------------------------------------------------------ weights
     def _params(self):
@@ -187,6 +188,7 @@ class _Runtime:
             a = native.TcBlockArgs()
             a.B, a.L, a.R, a.D, a.S, a.k = B, L, R, D, S, k
             a.d_z = zws.data_ptr()
+            a.fast_tf32 = int(bool(self.fast_tf32))
         else:
             a = native.BlockArgs()
             a.B, a.L, a.R, a.D, a.S, a.k, a.mode = B, L, R, D, S, k, 0

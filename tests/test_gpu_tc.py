@@ -70,3 +70,23 @@ def test_tc_full_size_batch_independence():
     assert bool(torch.isfinite(y).all())
     assert torch.equal(y[2], y2[0])
     assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) < 2e-5
+
+
+def test_fast_tf32_mode_is_opt_in_and_close():
+    """Single-pass TF32 blocks: not the parity path (error ~1e-3 through a deep stack), but must stay close."""
+    import wavenet_model as wmod
+    torch.manual_seed(0)
+    m = wmod.WaveNetModel(layers=10, blocks=5, dilation_channels=256, residual_channels=256, skip_channels=256,
+                          end_channels=256, classes=256, output_length=512, kernel_size=2).cuda()
+    idx = torch.randint(0, 256, (2, 6000), generator=torch.Generator().manual_seed(4)).cuda()
+    rt = m._runtime()
+    assert rt.fast_tf32 is False
+    with torch.no_grad():
+        exact = m.forward_indices(idx).cpu().numpy()
+        rt.fast_tf32 = True
+        fast = m.forward_indices(idx).cpu().numpy()
+        rt.fast_tf32 = False
+        again = m.forward_indices(idx).cpu().numpy()
+    assert np.array_equal(exact, again)
+    err = rel_err(fast, exact)
+    assert 1e-6 < err < 2e-2, err
