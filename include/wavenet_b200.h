@@ -217,6 +217,9 @@ int wn_gen_destroy(wn_gen_handle* h);
 int wn_gen_set_mode(wn_gen_handle* h, int mode);
 /* Synchronise the stream and report whether a launch aborted (a CTA waited > ~3 s for a tag): 0 = fine. */
 int wn_gen_check(wn_gen_handle* h, void* stream);
+/* Debug aid: with WN_GEN_TRACE=1 in the environment at wn_gen_create, CTA 0 stamps clock64() at 8 points of every layer
+ * of the LAST evaluation of a launch (single-stream kernel only); this copies the first n stamps to the host. */
+int wn_gen_read_trace(wn_gen_handle* h, long long* host_out, int n, void* stream);
 /* how wn_gen_run launches: grid size, block size, dependent exchange stages per evaluation */
 int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval);
 

@@ -54,6 +54,7 @@ struct GenParams {
     int* err;               // set to 1 by a CTA that timed out waiting for a tag
     int part_n;             // partial-sum scratch (floats)
     int wslot_floats, n_wslots;                // weight prefetch ring in shared memory (0 slots: read weights via L2)
+    long long* trace;       // optional: clock64 stamps of CTA 0 / thread 0 during the last evaluation (wn_gen_read_trace)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -118,7 +119,11 @@ __device__ __forceinline__ void row_dot(const float* __restrict__ w, const float
     for (int j = 0; j < SB; ++j) acc[j] = warp_sum(acc[j]);
 }
 
-__device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
+// Activations of the sampler kernels (all three kernels use these, so they stay bit-identical to each other):
+// ex2-based exp and fast division, absolute error ~2e-7 -- the same order as the difference between expf and the
+// reference's CPU math, at a fraction of the instructions on the latency-critical path.
+__device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return 2.f * sigmoid_(2.f * x) - 1.f; }
 
 template <int SB>
 __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel(const GenParams p) {
             __syncthreads();
             for (int i = tid; i < nD * NS; i += GEN_NT) {
                 const int ci = i / NS, s = i - ci * NS;
-                const float z = tanhf(pre[(2 * ci) * NS + s]) * sigmoid_(pre[(2 * ci + 1) * NS + s]);
+                const float z = tanh_(pre[(2 * ci) * NS + s]) * sigmoid_(pre[(2 * ci + 1) * NS + s]);
                 p.zbuf[(size_t)s * D + oD + ci] = z;
             }
             grid_barrier(p.bar, bar_target, G);
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(GEN_NT, 1) gen_kernel_ll(const GenParams p) {
                 const int ci = i / NS, s = i - ci * NS, c = oD + ci;
                 const float f = sum_parts(2 * ci, nw, s) + (L.bf ? __ldg(L.bf + c) : 0.f);
                 const float g = sum_parts(2 * ci + 1, nw, s) + (L.bg ? __ldg(L.bg + c) : 0.f);
-                st_pair(zl + (size_t)s * D + c, tanhf(f) * sigmoid_(g), tag);
+                st_pair(zl + (size_t)s * D + c, tanh_(f) * sigmoid_(g), tag);
             }
             // ---- stage 2: residual rows (-> next layer's ring slot t) and skip rows (-> running sums)
             StageDesc d2 = stage_desc(p, 2 * l + 1, want_head, nD, nR, nS, nE, nC);
@@ -778,9 +783,11 @@ __device__ __forceinline__ void poll2(const uint2* p, unsigned tag, float& v0, f
     Pair2 q = ld_pair2(p);
     if (q.a.y != tag || q.b.y != tag) {
         const long long t0 = clock64();
+        unsigned spins = 0;
         do {
             q = ld_pair2(p);
-            if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0) {
+            if ((++spins & 255u) == 0 &&
+                (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0)) {
                 *reinterpret_cast<volatile int*>(err) = 1;
                 *reinterpret_cast<volatile int*>(abort_s) = 1;
                 break;
@@ -869,14 +876,82 @@ __device__ __forceinline__ void mbar_arrive_(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 
+// argmax (first index wins ties) or numpy.random.choice's inverse-CDF draw, by one warp over C logits in shared memory.
+// Kept out of line so that its fp64 code does not sit in the instruction stream of the per-layer loop.
+__device__ __noinline__ int choose_sample(float* logit_s, double* cdf, int C, int lane, float temperature, const double* u_ptr) {
+    int choice;
+    if (temperature > 0.f) {
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) {
+            const float x = logit_s[c] / temperature;
+            logit_s[c] = x;
+            m = fmaxf(m, x);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float e = expf(logit_s[c] - m);
+            logit_s[c] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        // numpy.random.choice: float64 cumulative sum of the float32 probabilities, normalised by its last element,
+        // searchsorted(side='right').  The running sum is taken per lane over a contiguous chunk plus a warp scan
+        // (equal to the sequential sum up to float64 rounding, i.e. ~1e-16 relative on the CDF).
+        const int per = (C + 31) / 32;
+        const int c_lo = lane * per, c_hi = min(C, c_lo + per);
+        double run = 0.0;
+        for (int c = c_lo; c < c_hi; ++c) { run += (double)(logit_s[c] / sum); cdf[c] = run; }
+        double incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        const double total = __shfl_sync(0xffffffffu, incl, 31);
+        const double u = *u_ptr;
+        const double ut = u * total;
+        int cnt = 0;
+        for (int c = c_lo; c < c_hi; ++c) {
+            const double v = cdf[c] + excl;
+            bool le = v <= ut;
+            if (fabs(v - ut) <= 1e-9 * total) le = (v / total) <= u;       // exact rule only where it can matter
+            cnt += le ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        choice = cnt < C ? cnt : C - 1;
+    } else {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float x = logit_s[c];
+            if (x > best || (x == best && c < bi)) { best = x; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        choice = bi == 0x7fffffff ? 0 : bi;
+    }
+    return choice;
+}
+
 template <bool PREFETCH>
 __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParams p) {
     extern __shared__ __align__(16) float sm[];
     float* part = sm;                                   // [2][GEN_WARPS] partial sums, double buffered by stage parity
     float* skacc = part + 2 * GEN_WARPS;                // [nS]
     float* cur_own = skacc + ((p.S / (int)gridDim.x + 3) & ~3);      // [2][nR] layer input at the residual rows this CTA owns
-    float* logit_s = cur_own + 2 * ((p.R / (int)gridDim.x + 3) & ~3);  // [C]
-    double* cdf = reinterpret_cast<double*>(logit_s + ((p.C + 3) & ~3));       // [C]
+    float* xin = cur_own + 2 * ((p.R / (int)gridDim.x + 3) & ~3);    // [2][XN] the polled input vector of a stage
+    const int XN = p.regA;                              // max(R, D, S, E, C) rounded to 4 (set by the host)
+    double* cdf = reinterpret_cast<double*>(xin + 2 * XN);                     // [C]
     float* wbuf = reinterpret_cast<float*>(cdf + p.C);                         // [n_wslots][wslot_floats]
     unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
     unsigned long long* emptyb = fullb + 4;             // consumers -> producer: slot may be refilled (8 warps arrive)
@@ -892,8 +967,12 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
     const int nD = D / G, nR = R / G, nS = S / G, nE = E / G, nC = C / G;
     const int oD = cta * nD, oR = cta * nR, oS = cta * nS, oE = cta * nE, oC = cta * nC;
     const int NSLOT = p.n_wslots;
-    // fixed warp -> (row, K-part) assignment per stage kind
+    // fixed warp -> (row, K-part) assignment per stage kind, and this lane's float4 range inside the part
     const int HS1 = GEN_WARPS / (2 * nD), HS2 = GEN_WARPS / (nR + nS), HSA = GEN_WARPS / nE, HSB = GEN_WARPS / nC;
+    const int row1 = warp / HS1, g1 = ((warp - row1 * HS1) * (K1 / HS1) >> 2) + lane, n1 = (((K1 / HS1) >> 2) - lane + 31) / 32;
+    const int row2 = warp / HS2, g2 = ((warp - row2 * HS2) * (D / HS2) >> 2) + lane, n2 = (((D / HS2) >> 2) - lane + 31) / 32;
+    const int rowA = warp / HSA, gA = ((warp - rowA * HSA) * (S / HSA) >> 2) + lane, nA = (((S / HSA) >> 2) - lane + 31) / 32;
+    const int rowB = warp / HSB, gB = ((warp - rowB * HSB) * (E / HSB) >> 2) + lane, nB = (((E / HSB) >> 2) - lane + 31) / 32;
 
     {
         const int* src = reinterpret_cast<const int*>(p.layers);
@@ -962,12 +1041,27 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
         if (PREFETCH) return reinterpret_cast<const float4*>(w)[i4];
         return __ldg(reinterpret_cast<const float4*>(w) + i4);
     };
+    auto release_slot = [&]() {                       // this warp is done reading the weight slot of the current stage
+        if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
+        ++cons_q;
+    };
+    // One CTA-wide poll of a published vector: warps 4..7 (which never have epilogue work, so they are free the moment
+    // the dot barrier opens) fetch N {value,tag} pairs ONCE per CTA -- 8x fewer L2 requests on the hot lines than every
+    // warp polling its own operands, which measured as the dominant cost -- and leave the values in shared memory.
+    auto poll_vector = [&](const uint2* src, int N, unsigned tg, float* dst, bool relu) {
+        if (warp >= 4) {
+            for (int j = tid - 128; 2 * j < N; j += 128) {
+                float a, b;
+                poll2(src + 2 * j, tg, a, b, p.err, abort_s);
+                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                *reinterpret_cast<float2*>(dst + 2 * j) = make_float2(a, b);
+            }
+        }
+    };
     unsigned stage_par = 0;
     WORKER_SYNC();
-    // Old taps (the ring slot of time t-d) were written >= 1 evaluation ago and have usually left the L2 by the time
-    // they are needed (the weight stream evicts them), so reading them inside the stage would put an HBM round trip on
-    // the critical path of every layer.  They are fetched one stage ahead with cp.async into shared memory instead:
-    // during stage 2 of layer l for layer l+1 (or for layer 0 of the next evaluation).
+    // Old taps (the ring slot of time t-d) were written >= 1 evaluation ago; they are fetched one stage ahead with
+    // cp.async into shared memory: during stage 2 of layer l for layer l+1 (or for layer 0 of the next evaluation).
     auto prefetch_old = [&](int ln, int te, int slot_te) {        // slot_te = ring slot of time te in layer ln
         const GenLayer& Lp = lay_s[ln];
         if (te >= Lp.dil && tid < R / 2) {
@@ -1004,72 +1098,79 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
         if (*abort_s) return;
         int idx = misc[0];
         idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
+        const bool tr_on = p.trace != nullptr && cta == 0 && tid == 0 && ev == p.n_evals - 1;
+        int tr_n = 0;
+#define TR() do { if (tr_on && tr_n < 2040) p.trace[tr_n++] = clock64(); } while (0)
+        TR();
 
         for (int l = 0; l < NL; ++l) {
             const GenLayer& L = lay_s[l];
             uint2* ring = p.ringLL + L.ring_off;
             const int slot_t = slot_s[l];
-            float* cur_l = cur_own + (l & 1) * ((nR + 3) & ~3);
             const int slot_old = (slot_t + 1 == L.ring_len) ? 0 : slot_t + 1;          // time t-d with len = d+1
             const bool have_old = (t >= L.dil);
+            const unsigned tag_old = (unsigned)(t - L.dil) + 1u;
+            float* cur_l = cur_own + (l & 1) * ((nR + 3) & ~3);
+            float* xc = xin + stage_par * XN;
+            // ================= stage 1 inputs: the layer's current input vector (R values) -> xc
+            if (warp >= 4) {
+                for (int j = tid - 128; 2 * j < R; j += 128) {
+                    const int r0 = 2 * j;
+                    float c0, c1;
+                    if (l == 0) {                                  // start conv column of the current sample index
+                        c0 = __ldg(p.start_w + (size_t)r0 * C + idx) + (p.start_b ? __ldg(p.start_b + r0) : 0.f);
+                        c1 = __ldg(p.start_w + (size_t)(r0 + 1) * C + idx) + (p.start_b ? __ldg(p.start_b + r0 + 1) : 0.f);
+                        if (r0 >= oR && r0 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0, c0, tag);          // enqueue
+                        if (r0 + 1 >= oR && r0 + 1 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0 + 1, c1, tag);
+                    } else {
+                        poll2(ring + (size_t)slot_t * R + r0, tag, c0, c1, p.err, abort_s);
+                    }
+                    if (r0 >= oR && r0 < oR + nR) cur_l[r0 - oR] = c0;
+                    if (r0 + 1 >= oR && r0 + 1 < oR + nR) cur_l[r0 + 1 - oR] = c1;
+                    *reinterpret_cast<float2*>(xc + r0) = make_float2(c0, c1);
+                }
+            }
+            const float* w1 = stage_weights(2 * l, row1, K1);
+            TR();          // 1: own share of the inputs polled (pollers) / weights ready
+            WORKER_SYNC();
             // ================= stage 1: filter/gate rows, K = 2R interleaved (old, cur) per channel
             {
-                const int row = warp / HS1, kp = warp - row * HS1, Kp = K1 / HS1;
-                const float* w = stage_weights(2 * l, row, K1);
-                const int g4_0 = (kp * Kp >> 2) + lane;            // first float4 of this lane; next ones are +32
-                const int n_iter = ((Kp >> 2) - lane + 31) / 32;   // float4 iterations of this lane (may be 0)
-                float o[FAST_MAXI][2], c[FAST_MAXI][2];
-                bool old_ok = true;
-                const unsigned tag_old = (unsigned)(t - L.dil) + 1u;
-                if (have_old) {
-                    const uint2* os = old_s + (l & 1) * R;
-#pragma unroll
-                    for (int it = 0; it < FAST_MAXI; ++it)
-                        if (it < n_iter) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(os + 2 * g4_0 + it * 64);
-                            old_ok = old_ok && q.y == tag_old && q.w == tag_old;
-                            o[it][0] = __uint_as_float(q.x);
-                            o[it][1] = __uint_as_float(q.z);
-                        }
-                }
-                // current taps are polled from L2; the old ones only if the prefetched copy was not there yet (rare)
-                {
-                    float o2[FAST_MAXI][2];
-                    const bool refetch = have_old && !old_ok;
-                    poll_taps(ring + (size_t)slot_old * R, tag_old, refetch, ring + (size_t)slot_t * R, tag, l != 0, 2 * g4_0,
-                              n_iter, o2, c, p.err, abort_s);
-                    if (!have_old || refetch) {
-#pragma unroll
-                        for (int it = 0; it < FAST_MAXI; ++it) { o[it][0] = o2[it][0]; o[it][1] = o2[it][1]; }
-                    }
-                }
+                const uint2* os = old_s + (l & 1) * R;
                 float acc = 0.f;
+                bool old_ok = true;
 #pragma unroll
                 for (int it = 0; it < FAST_MAXI; ++it)
-                    if (it < n_iter) {
-                        const int g4 = g4_0 + it * 32, r0 = 2 * g4;
-                        if (l == 0) {
-                            c[it][0] = __ldg(p.start_w + (size_t)r0 * C + idx) + (p.start_b ? __ldg(p.start_b + r0) : 0.f);
-                            c[it][1] = __ldg(p.start_w + (size_t)(r0 + 1) * C + idx) + (p.start_b ? __ldg(p.start_b + r0 + 1) : 0.f);
-                            if (row == 0) {                        // one warp row covers every channel once: it enqueues
-                                if (r0 >= oR && r0 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0, c[it][0], tag);
-                                if (r0 + 1 >= oR && r0 + 1 < oR + nR) st_pair(ring + (size_t)slot_t * R + r0 + 1, c[it][1], tag);
-                            }
+                    if (it < n1) {
+                        const int g4 = g1 + it * 32, r0 = 2 * g4;
+                        float o0 = 0.f, o1 = 0.f;
+                        if (have_old) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(os + r0);
+                            old_ok = old_ok && q.y == tag_old && q.w == tag_old;
+                            o0 = __uint_as_float(q.x);
+                            o1 = __uint_as_float(q.z);
                         }
-                        if (row == 0) {
-                            if (r0 >= oR && r0 < oR + nR) cur_l[r0 - oR] = c[it][0];
-                            if (r0 + 1 >= oR && r0 + 1 < oR + nR) cur_l[r0 + 1 - oR] = c[it][1];
-                        }
-                        const float4 w4 = ldw(w, g4);
-                        acc = fmaf(w4.x, o[it][0], acc); acc = fmaf(w4.y, c[it][0], acc);
-                        acc = fmaf(w4.z, o[it][1], acc); acc = fmaf(w4.w, c[it][1], acc);
+                        const float2 c = *reinterpret_cast<const float2*>(xc + r0);
+                        const float4 w4 = ldw(w1, g4);
+                        acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, c.x, acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, c.y, acc);
                     }
+                if (!__all_sync(0xffffffffu, old_ok)) {            // prefetched copy not there yet (rare): poll the ring itself
+                    acc = 0.f;
+                    for (int it = 0; it < n1; ++it) {
+                        const int g4 = g1 + it * 32, r0 = 2 * g4;
+                        float o0, o1;
+                        poll2(ring + (size_t)slot_old * R + r0, tag_old, o0, o1, p.err, abort_s);
+                        const float2 c = *reinterpret_cast<const float2*>(xc + r0);
+                        const float4 w4 = ldw(w1, g4);
+                        acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, c.x, acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, c.y, acc);
+                    }
+                }
                 acc = warp_sum(acc);
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
-                if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
-                ++cons_q;
+                release_slot();
             }
+            TR();          // 2: stage-1 dot done
             WORKER_SYNC();
+            TR();          // 3: barrier passed
             if (*abort_s) return;
             uint2* zl = p.zLL + (size_t)(par * NL + l) * D;
             if (tid < nD) {
@@ -1079,37 +1180,39 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
                 for (int q = 1; q < HS1; ++q) { f += pf[q]; g += pf[HS1 + q]; }
                 f += L.bf ? __ldg(L.bf + c) : 0.f;
                 g += L.bg ? __ldg(L.bg + c) : 0.f;
-                st_pair(zl + c, tanhf(f) * sigmoid_(g), tag);
+                st_pair(zl + c, tanh_(f) * sigmoid_(g), tag);
             }
+            TR();          // 4: z published
             stage_par ^= 1;
+            // ================= stage 2 inputs: z of all CTAs -> xz; old taps of the next stage 1 start flying now
+            float* xz = xin + stage_par * XN;
+            const bool active2 = (row2 < nR) ? (l + 1 < NL) : want_head;
+            if (l + 1 < NL) prefetch_old(l + 1, t, slot_s[l + 1]);
+            else if (ev + 1 < p.n_evals) prefetch_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
+            poll_vector(zl, D, tag, xz, false);
+            const float* w2 = stage_weights(2 * l + 1, row2, D);
+            TR();          // 5: own share of z polled
+            WORKER_SYNC();
             // ================= stage 2: residual rows (first nR) and skip rows (next nS), K = D
             {
-                const int row = warp / HS2, kp = warp - row * HS2, Kp = D / HS2;
-                const bool is_res = row < nR;
-                const bool active = is_res ? (l + 1 < NL) : want_head;
-                if (l + 1 < NL) prefetch_old(l + 1, t, slot_s[l + 1]);
-                else if (ev + 1 < p.n_evals) prefetch_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
-                const float* w = stage_weights(2 * l + 1, row, D);
                 float acc = 0.f;
-                if (active) {
-                    const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
-                    float z[FAST_MAXI][4];
-                    poll_quads(zl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
+                if (active2) {
 #pragma unroll
                     for (int it = 0; it < FAST_MAXI; ++it)
-                        if (it < n_iter) {
-                            const float4 w4 = ldw(w, g4_0 + it * 32);
-                            acc = fmaf(w4.x, z[it][0], acc); acc = fmaf(w4.y, z[it][1], acc);
-                            acc = fmaf(w4.z, z[it][2], acc); acc = fmaf(w4.w, z[it][3], acc);
+                        if (it < n2) {
+                            const float4 z4 = *reinterpret_cast<const float4*>(xz + 4 * (g2 + it * 32));
+                            const float4 w4 = ldw(w2, g2 + it * 32);
+                            acc = fmaf(w4.x, z4.x, acc); acc = fmaf(w4.y, z4.y, acc); acc = fmaf(w4.z, z4.z, acc); acc = fmaf(w4.w, z4.w, acc);
                         }
                     acc = warp_sum(acc);
                 }
                 if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
-                if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
-                ++cons_q;
+                release_slot();
                 asm volatile("cp.async.wait_group 0;" ::: "memory");      // the old taps for the next stage 1 have landed
             }
+            TR();          // 6: stage-2 dot done
             WORKER_SYNC();
+            TR();          // 7: barrier passed
             if (*abort_s) return;
             if (tid < nR + nS) {
                 const float* ps = part + stage_par * GEN_WARPS + tid * HS2;
@@ -1128,9 +1231,10 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
                     skacc[li] = v + skacc[li];
                 }
             }
+            TR();          // 8: h' published
             stage_par ^= 1;
-            // no barrier here: part and cur_own are double buffered, and their next writers sit behind the next
-            // stage's __syncthreads, which this epilogue's threads must reach first
+            // no barrier here: part, xin and cur_own are double buffered, and their next writers sit behind a barrier
+            // that this epilogue's threads must reach first
         }
         if (!want_head) continue;
 
@@ -1139,25 +1243,21 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
         if (tid >= nR && tid < nR + nS) st_pair(skl + oS + (tid - nR), skacc[tid - nR], tag);   // same thread that summed it
         uint2* yl = p.y1LL + (size_t)par * E;
         {
-            const int row = warp / HSA, kp = warp - row * HSA, Kp = S / HSA;
-            const float* w = stage_weights(2 * NL, row, S);
+            float* xs = xin + stage_par * XN;
+            poll_vector(skl, S, tag, xs, true);
+            const float* w = stage_weights(2 * NL, rowA, S);
+            WORKER_SYNC();
             float acc = 0.f;
-            {
-                const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
-                float z[FAST_MAXI][4];
-                poll_quads(skl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
 #pragma unroll
-                for (int it = 0; it < FAST_MAXI; ++it)
-                    if (it < n_iter) {
-                        const float4 w4 = ldw(w, g4_0 + it * 32);
-                        acc = fmaf(w4.x, fmaxf(z[it][0], 0.f), acc); acc = fmaf(w4.y, fmaxf(z[it][1], 0.f), acc);
-                        acc = fmaf(w4.z, fmaxf(z[it][2], 0.f), acc); acc = fmaf(w4.w, fmaxf(z[it][3], 0.f), acc);
-                    }
-            }
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nA) {
+                    const float4 z4 = *reinterpret_cast<const float4*>(xs + 4 * (gA + it * 32));
+                    const float4 w4 = ldw(w, gA + it * 32);
+                    acc = fmaf(w4.x, z4.x, acc); acc = fmaf(w4.y, z4.y, acc); acc = fmaf(w4.z, z4.z, acc); acc = fmaf(w4.w, z4.w, acc);
+                }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
-            if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
-            ++cons_q;
+            release_slot();
         }
         WORKER_SYNC();
         if (*abort_s) return;
@@ -1171,25 +1271,21 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
         stage_par ^= 1;
         uint2* lgl = p.logitLL + (size_t)par * C;
         {
-            const int row = warp / HSB, kp = warp - row * HSB, Kp = E / HSB;
-            const float* w = stage_weights(2 * NL + 1, row, E);
+            float* xs = xin + stage_par * XN;
+            poll_vector(yl, E, tag, xs, false);
+            const float* w = stage_weights(2 * NL + 1, rowB, E);
+            WORKER_SYNC();
             float acc = 0.f;
-            {
-                const int g4_0 = (kp * Kp >> 2) + lane, n_iter = ((Kp >> 2) - lane + 31) / 32;
-                float z[FAST_MAXI][4];
-                poll_quads(yl, 4 * g4_0, n_iter, tag, z, p.err, abort_s);
 #pragma unroll
-                for (int it = 0; it < FAST_MAXI; ++it)
-                    if (it < n_iter) {
-                        const float4 w4 = ldw(w, g4_0 + it * 32);
-                        acc = fmaf(w4.x, z[it][0], acc); acc = fmaf(w4.y, z[it][1], acc);
-                        acc = fmaf(w4.z, z[it][2], acc); acc = fmaf(w4.w, z[it][3], acc);
-                    }
-            }
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nB) {
+                    const float4 z4 = *reinterpret_cast<const float4*>(xs + 4 * (gB + it * 32));
+                    const float4 w4 = ldw(w, gB + it * 32);
+                    acc = fmaf(w4.x, z4.x, acc); acc = fmaf(w4.y, z4.y, acc); acc = fmaf(w4.z, z4.z, acc); acc = fmaf(w4.w, z4.w, acc);
+                }
             acc = warp_sum(acc);
             if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
-            if (PREFETCH) { __syncwarp(); if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask)); }
-            ++cons_q;
+            release_slot();
         }
         WORKER_SYNC();
         if (*abort_s) return;
@@ -1204,83 +1300,20 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
             if (p.out_logits) p.out_logits[(size_t)samp * C + row] = v;
         }
         stage_par ^= 1;
-        // ---- all logits -> shared memory, then warp 0 chooses
-        for (int c2 = tid; 2 * c2 < C; c2 += GEN_NT) {
-            float a, b;
-            poll2(lgl + 2 * c2, tag, a, b, p.err, abort_s);
-            logit_s[2 * c2] = a;
-            logit_s[2 * c2 + 1] = b;
-        }
+        // ---- all logits -> shared memory (cooperative poll), then warp 0 chooses
+        float* logit_s = xin + stage_par * XN;
+        poll_vector(lgl, C, tag, logit_s, false);
         WORKER_SYNC();
         if (*abort_s) return;
         if (warp == 0) {
-            int choice;
-            if (p.temperature > 0.f) {
-                float m = -INFINITY;
-                for (int c = lane; c < C; c += 32) {
-                    const float x = logit_s[c] / p.temperature;
-                    logit_s[c] = x;
-                    m = fmaxf(m, x);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                float sum = 0.f;
-                for (int c = lane; c < C; c += 32) {
-                    const float e = expf(logit_s[c] - m);
-                    logit_s[c] = e;
-                    sum += e;
-                }
-                sum = warp_sum(sum);
-                __syncwarp();
-                // numpy.random.choice: float64 cumulative sum of the float32 probabilities, normalised by its last element,
-                // searchsorted(side='right').  The running sum is taken per lane over a contiguous chunk plus a warp scan
-                // (equal to the sequential sum up to float64 rounding, i.e. ~1e-16 relative on the CDF).
-                const int per = (C + 31) / 32;
-                const int c_lo = lane * per, c_hi = min(C, c_lo + per);
-                double run = 0.0;
-                for (int c = c_lo; c < c_hi; ++c) { run += (double)(logit_s[c] / sum); cdf[c] = run; }
-                double incl = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 0.0;
-                const double total = __shfl_sync(0xffffffffu, incl, 31);
-                const double u = p.uniforms[samp];
-                const double ut = u * total;
-                int cnt = 0;
-                for (int c = c_lo; c < c_hi; ++c) {
-                    const double v = cdf[c] + excl;
-                    bool le = v <= ut;
-                    if (fabs(v - ut) <= 1e-9 * total) le = (v / total) <= u;       // exact rule only where it can matter
-                    cnt += le ? 1 : 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                choice = cnt < C ? cnt : C - 1;
-            } else {
-                float best = -INFINITY;
-                int bi = 0x7fffffff;
-                for (int c = lane; c < C; c += 32) {
-                    const float x = logit_s[c];
-                    if (x > best || (x == best && c < bi)) { best = x; bi = c; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                choice = bi == 0x7fffffff ? 0 : bi;
-            }
+            const int choice = choose_sample(logit_s, cdf, C, lane, p.temperature, p.uniforms ? p.uniforms + samp : nullptr);
             if (lane == 0) {
                 misc[0] = choice;
                 if (cta == 0) p.out_idx[samp] = choice;
             }
         }
-        // the top-of-evaluation __syncthreads publishes misc[0]
+        stage_par ^= 1;
+        // the top-of-evaluation barrier publishes misc[0]
     }
     WORKER_SYNC();
     if (cta == 0 && tid == 0) p.cur_idx[0] = misc[0];
@@ -1288,7 +1321,7 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
 
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
-    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, total;
+    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, total;
 };
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static ScratchLayout scratch_layout(const wn_gen_shape& s) {
@@ -1307,6 +1340,7 @@ static ScratchLayout scratch_layout(const wn_gen_shape& s) {
     o.y1LL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.E, 256);
     o.logitLL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.classes, 256);
     o.ll_end = off;
+    o.trace = off; off += 8 * 2048;
     o.total = off;
     return o;
 }
@@ -1340,6 +1374,7 @@ struct wn_gen_handle {
     bool fast_ok;           // single stream, k=2, power-of-two grid, rows per stage divide 8: gen_kernel_fast applies
     size_t smem_fast;
     int n_wslots_fast;
+    int xn_fast;
 };
 
 static int validate_shape(const wn_gen_shape* s) {
@@ -1451,6 +1486,7 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     p.y1LL = reinterpret_cast<uint2*>(h->scratch + h->lay.y1LL);
     p.logitLL = reinterpret_cast<uint2*>(h->scratch + h->lay.logitLL);
     p.err = reinterpret_cast<int*>(h->scratch + h->lay.err);
+    p.trace = getenv("WN_GEN_TRACE") ? reinterpret_cast<long long*>(h->scratch + h->lay.trace) : nullptr;
     {
         const int nDm = cdiv(s->D, G), nRm = cdiv(s->R, G), nSm = cdiv(s->S, G), nEm = cdiv(s->E, G), nCm = cdiv(s->classes, G);
         int mxA = mx1 > s->classes ? mx1 : s->classes;
@@ -1498,8 +1534,14 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
                  split_ok(s->classes / G, s->E);
         h->fast_ok = false;
         if (ok) {
-            const size_t fbase = sizeof(float) * (2 * GEN_WARPS + ((s->S / G + 3) & ~3) + 2 * ((s->R / G + 3) & ~3) +
-                                                  ((s->classes + 3) & ~3)) +
+            int xn = s->R;
+            if (s->D > xn) xn = s->D;
+            if (s->S > xn) xn = s->S;
+            if (s->E > xn) xn = s->E;
+            if (s->classes > xn) xn = s->classes;
+            xn = (xn + 3) & ~3;
+            h->xn_fast = xn;
+            const size_t fbase = sizeof(float) * (2 * GEN_WARPS + ((s->S / G + 3) & ~3) + 2 * ((s->R / G + 3) & ~3) + 2 * xn) +
                                  sizeof(double) * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
                                  sizeof(uint2) * 2 * (size_t)s->R + sizeof(int) * (size_t)(s->n_layers + 4);
             int fs = 0;
@@ -1615,6 +1657,7 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         int rc;
         if (h->mode == 0 && h->fast_ok) {
             p.n_wslots = h->n_wslots_fast;
+            p.regA = h->xn_fast;                    // the fast kernel reads its input-vector pitch from regA
             rc = p.n_wslots ? launch_gen_fast<true>(h, p, st) : launch_gen_fast<false>(h, p, st);
         } else if (h->mode == 0 || h->mode == 2) {
             if (h->shape.n_streams == 1)
@@ -1628,6 +1671,14 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         done += n;
     }
     h->cur_t = a->t0 + a->n_evals;
+    return 0;
+}
+
+extern "C" int wn_gen_read_trace(wn_gen_handle* h, long long* host_out, int n, void* stream) {
+    WN_REQUIRE(h && host_out && n > 0 && n <= 2048, WN_E_BADARG, "wn_gen_read_trace: bad arguments");
+    WN_REQUIRE(h->base.trace, WN_E_STATE, "wn_gen_read_trace: tracing is off (set WN_GEN_TRACE=1 before wn_gen_create)");
+    WN_CUDA(cudaMemcpyAsync(host_out, h->base.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    WN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 
