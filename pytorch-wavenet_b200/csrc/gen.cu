@@ -779,21 +779,25 @@ __device__ __forceinline__ Pair2 ld_pair2(const uint2* p) {
     return r;
 }
 // two consecutive pairs carrying `tag`; spins (bounded) until both are there
+// slow path of poll2, out of line: spinning code (with its timeout) must not bloat the per-layer instruction stream
+__device__ __noinline__ Pair2 poll2_spin(const uint2* p, unsigned tag, int* err, int* abort_s) {
+    Pair2 q;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    do {
+        q = ld_pair2(p);
+        if ((++spins & 255u) == 0 &&
+            (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0)) {
+            *reinterpret_cast<volatile int*>(err) = 1;
+            *reinterpret_cast<volatile int*>(abort_s) = 1;
+            break;
+        }
+    } while (q.a.y != tag || q.b.y != tag);
+    return q;
+}
 __device__ __forceinline__ void poll2(const uint2* p, unsigned tag, float& v0, float& v1, int* err, int* abort_s) {
     Pair2 q = ld_pair2(p);
-    if (q.a.y != tag || q.b.y != tag) {
-        const long long t0 = clock64();
-        unsigned spins = 0;
-        do {
-            q = ld_pair2(p);
-            if ((++spins & 255u) == 0 &&
-                (clock64() - t0 > GEN_TIMEOUT_CYCLES || *reinterpret_cast<volatile int*>(err) != 0)) {
-                *reinterpret_cast<volatile int*>(err) = 1;
-                *reinterpret_cast<volatile int*>(abort_s) = 1;
-                break;
-            }
-        } while (q.a.y != tag || q.b.y != tag);
-    }
+    if (q.a.y != tag || q.b.y != tag) q = poll2_spin(p, tag, err, abort_s);
     v0 = __uint_as_float(q.a.x);
     v1 = __uint_as_float(q.b.x);
 }
