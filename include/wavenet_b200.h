@@ -210,10 +210,13 @@ typedef struct wn_gen_run_args {
 } wn_gen_run_args;
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
-/* Exchange mechanism between the stages of one evaluation: 0 = flag-in-data pairs, no grid barrier (default, needs
- * n_layers >= 2; picks the register-polling single-stream kernel when the shape allows); 1 = atomic grid barrier
- * between stages (the simple reference kernel); 2 = the generic flag-in-data kernel.  All implement the same schedule;
- * 0 and 2 sum in the same order.  Call right after wn_gen_reset. */
+/* Which sampler kernel runs (all implement the same schedule; call right after wn_gen_reset):
+ *   0  auto: the cluster kernel when the shape allows, else the single-stream L2 kernel, else the generic one
+ *   1  atomic grid barrier between stages (the simple reference kernel)
+ *   2  generic flag-in-data exchange through L2 (any shape, any number of streams)
+ *   3  single-stream L2 kernel with register-free cooperative polling (k = 2, power-of-two row split)
+ *   4  cluster kernel: one 16-CTA thread-block cluster per stream, exchange through distributed shared memory
+ * Kernels 2 and 3 sum in the same order; kernel 4 splits rows differently (rounding-level differences). */
 int wn_gen_set_mode(wn_gen_handle* h, int mode);
 /* Synchronise the stream and report whether a launch aborted (a CTA waited > ~3 s for a tag): 0 = fine. */
 int wn_gen_check(wn_gen_handle* h, void* stream);

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -1323,6 +1324,375 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
     if (cta == 0 && tid == 0) p.cur_idx[0] = misc[0];
 }
 
+// ================================================================================================ cluster kernel
+// One thread-block cluster (16 CTAs) per stream.  The stage-to-stage exchange no longer goes through the L2: a CTA
+// that has computed a value stores the {value, tag} pair straight into the shared memory of all 16 CTAs of its
+// cluster (distributed shared memory), and consumers spin on their OWN shared memory.  Measured on this part an L2
+// all-to-all costs ~1300-1650 cycles per stage (tools/lat_probe.cu); a DSMEM store lands in ~200-250.
+//   stage 1 (conv rows)   warp-local: local poll of the layer input -> 4 rows per warp over the full K -> warp reduce ->
+//                         every lane recomputes z of the warp's 2 channels and stores it to one of the 16 CTAs
+//   stage 2 (1x1 rows)    warps 0-3 residual rows, warps 4-7 skip rows; one CTA barrier per layer before h' is
+//                         published keeps slow warps from being overtaken (buffers are double buffered by layer parity)
+//   head                  skip -> end_conv_1 -> end_conv_2 -> every CTA holds all logits; rank 0 records the choice
+// Clusters do not talk to each other, so a launch may hold any number of streams (they run in waves of co-resident
+// clusters) and needs no cooperative launch.  History (ring slots of time t-d) still lives in global memory and is
+// fetched one stage ahead with cp.async, as in gen_kernel_fast; weights stream through a TMA ring fed by warp 8.
+constexpr int CL = 16;                      // CTAs per cluster
+constexpr int CL_ROWS = 4;                  // max rows per warp per stage
+
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// {value, tag} into the same shared-memory offset of CTA `dst` of this cluster
+__device__ __forceinline__ void st_remote_pair(const void* local_ptr, unsigned dst, float v, unsigned tag) {
+    unsigned laddr = smem_u32(local_ptr), raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(dst));
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(raddr), "l"(w) : "memory");
+}
+// local spin on a shared-memory {value, tag} pair (volatile: the writer is another SM)
+__device__ __forceinline__ float wait_local(const uint2* p, unsigned tag, int* abort_s) {
+    const volatile unsigned long long* vp = reinterpret_cast<const volatile unsigned long long*>(p);
+    unsigned long long w = *vp;
+    if ((unsigned)(w >> 32) != tag) {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        do {
+            w = *vp;
+            if ((++spins & 1023u) == 0 && clock64() - t0 > GEN_TIMEOUT_CYCLES) asm volatile("trap;");   // never hang the GPU
+        } while ((unsigned)(w >> 32) != tag);
+    }
+    return __uint_as_float((unsigned)w);
+}
+
+__global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cluster(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    // exchange buffers first: they must sit at the same offset in every CTA (mapa keeps the offset)
+    uint2* xcur = reinterpret_cast<uint2*>(sm);                  // [2][R]  layer input (h), by layer parity
+    uint2* xz = xcur + 2 * p.R;                                  // [2][D]  gated activation z, by layer parity
+    uint2* xhead = xz + 2 * p.D;                                 // [S + E + C] skip, y1, logits of the current evaluation
+    uint2* old_s = xhead + (p.S + p.E + p.C);                    // [2][R] prefetched old taps
+    float* skacc = reinterpret_cast<float*>(old_s + 2 * p.R);    // [S/CL]
+    float* cur_own = skacc + ((p.S / CL + 3) & ~3);              // [2][R/CL]
+    float* part = cur_own + 2 * ((p.R / CL + 3) & ~3);           // [E/CL + C/CL + 32] row sums of the head stages
+    float* logit_s = part + (((p.E + p.C) / CL + 32 + 3) & ~3);  // [C]
+    double* cdf = reinterpret_cast<double*>(logit_s + ((p.C + 3) & ~3));      // [C]
+    float* wbuf = reinterpret_cast<float*>(cdf + p.C);                        // [n_wslots][wslot_floats]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    unsigned long long* emptyb = fullb + 4;
+    GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);
+    int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
+    int* misc = slot_s + p.n_layers;                             // [0] current index, [1] abort
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster_rank();
+    const int stream = blockIdx.x / CL, NS = p.NS;
+    const int R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, NL = p.n_layers;
+    const int K1 = 2 * R;
+    const int nD = D / CL, nR = R / CL, nS = S / CL, nE = E / CL, nC = C / CL;
+    const int oD = rank * nD, oR = rank * nR, oS = rank * nS, oE = rank * nE, oC = rank * nC;
+    const int NSLOT = p.n_wslots;
+    const int rw1 = 2 * nD / GEN_WARPS, rw2 = (nR + nS) / GEN_WARPS;       // rows per warp in stage 1 / stage 2 (<= CL_ROWS)
+
+    {   // zero the exchange buffers (tag 0 = nothing yet), copy the layer table
+        unsigned long long* z0 = reinterpret_cast<unsigned long long*>(xcur);
+        const int n0 = 2 * R + 2 * D + S + E + C + 2 * R;
+        for (int i = tid; i < n0; i += GEN_NT + 32) z0[i] = 0ull;
+        const int* src = reinterpret_cast<const int*>(p.layers);
+        int* dst = reinterpret_cast<int*>(lay_s);
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        misc[0] = p.cur_idx[stream];
+        misc[1] = 0;
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    for (int l = tid; l < NL; l += GEN_NT) {
+        const int len = lay_s[l].ring_len;
+        slot_s[l] = (p.t0 + len - 1) % len;
+    }
+    cluster_sync_all();                                          // nobody may store into a peer before it is zeroed
+    int* abort_s = misc + 1;
+    const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
+
+    // ---- producer warp: weight rows of this CTA for every stage, in order, through the TMA ring
+    if (warp == GEN_WARPS) {
+        if (lane == 0) {
+            unsigned q = 0;
+            for (int ev = 0; ev < p.n_evals; ++ev) {
+                const bool wh = (p.t0 + ev >= p.n_given - 1);
+                const int n_st = wh ? 2 * NL + 2 : 2 * NL;
+                for (int st = 0; st < n_st; ++st, ++q) {
+                    StageDesc d = stage_desc(p, st, true, nD, nR, nS, nE, nC);
+                    if (st < 2 * NL && (st & 1)) { d.n_first = nR; d.n = nR + nS; }
+                    const int slot = (int)(q & smask);
+                    if (q >= (unsigned)NSLOT) {
+                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                            if (!done && ++spins > (1u << 30)) asm volatile("trap;");
+                        }
+                    }
+                    mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+                    float* dst = wbuf + (size_t)slot * p.wslot_floats;
+                    for (int i = 0; i < d.n; ++i)
+                        bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, st, d, i, rank, CL), d.K * 4, fullb + slot);
+                }
+            }
+        }
+        cluster_sync_all();                                      // matches the workers' final cluster barrier
+        return;
+    }
+    unsigned cons_q = 0;
+    auto stage_weights = [&](int row, int K) -> const float* {
+        const int slot = (int)(cons_q & smask);
+        mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
+        return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * K;
+    };
+    auto release_slot = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask));
+        ++cons_q;
+    };
+    const size_t ring_stream = (size_t)stream * R;               // ring element (slot, stream, r): (slot*NS + stream)*R + r
+    auto prefetch_old = [&](int ln, int te, int slot_te) {
+        const GenLayer& Lp = lay_s[ln];
+        if (te >= Lp.dil && tid < R / 2) {
+            const int so = (slot_te + 1 == Lp.ring_len) ? 0 : slot_te + 1;
+            const uint2* src = p.ringLL + Lp.ring_off + (size_t)so * NS * R + ring_stream + 2 * tid;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(old_s + (ln & 1) * R + 2 * tid);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch_old(0, p.t0, p.t0 % lay_s[0].ring_len);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    WORKER_SYNC();
+    unsigned seq = (unsigned)p.t0 * (unsigned)(2 * NL + 4);      // exchange tag counter, unique per (evaluation, stage)
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;
+        const unsigned rtag = (unsigned)t + 1u;                  // ring tag of time t
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);
+        if (tid == 0) {
+            if (t < p.n_given) misc[0] = p.first[(size_t)stream * p.n_given + t];
+            else if (p.forced != nullptr) misc[0] = p.forced[(size_t)stream * p.n_samples + (t - p.n_given)];
+        }
+        for (int l = tid; l < NL; l += GEN_NT) {
+            const int s1 = slot_s[l] + 1;
+            slot_s[l] = (s1 == lay_s[l].ring_len) ? 0 : s1;
+        }
+        for (int i = tid; i < nS; i += GEN_NT) skacc[i] = 0.f;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");    // layer 0's history, requested at the end of the last evaluation
+        WORKER_SYNC();
+        int idx = misc[0];
+        idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
+        const unsigned etag = seq + 1u;                          // tags of this evaluation: etag + 2l (cur), etag + 2l + 1 (z)
+        seq += (unsigned)(2 * NL + 4);
+
+        // layer 0's input: the start-conv column, computed locally by every CTA; owners also enqueue it
+        {
+            const GenLayer& L0 = lay_s[0];
+            for (int r = tid; r < R; r += GEN_NT) {
+                const float v = __ldg(p.start_w + (size_t)r * C + idx) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
+                reinterpret_cast<unsigned long long*>(xcur)[r] =
+                    ((unsigned long long)etag << 32) | (unsigned long long)__float_as_uint(v);
+                if (r >= oR && r < oR + nR)
+                    st_pair(p.ringLL + L0.ring_off + ((size_t)slot_s[0] * NS) * R + ring_stream + r, v, rtag);
+            }
+        }
+        WORKER_SYNC();
+
+        for (int l = 0; l < NL; ++l) {
+            const GenLayer& L = lay_s[l];
+            const bool have_old = (t >= L.dil);
+            const unsigned tag_old = (unsigned)(t - L.dil) + 1u, tag_cur = etag + 2u * (unsigned)l, tag_z = tag_cur + 1u;
+            const uint2* xc = xcur + (l & 1) * R;
+            const uint2* os = old_s + (l & 1) * R;
+            uint2* zbuf = xz + (l & 1) * D;
+            float* cur_l = cur_own + (l & 1) * ((nR + 3) & ~3);
+            // ================= stage 1: rows [warp*rw1, +rw1) of this CTA's 2*nD conv rows, full K, warp-local
+            {
+                const float* w = stage_weights(warp * rw1, K1);
+                float acc[CL_ROWS];
+#pragma unroll
+                for (int j = 0; j < CL_ROWS; ++j) acc[j] = 0.f;
+                for (int g4 = lane; g4 < (K1 >> 2); g4 += 32) {
+                    const int r0 = 2 * g4;
+                    float o0 = 0.f, o1 = 0.f;
+                    if (have_old) {
+                        uint4 q = *reinterpret_cast<const uint4*>(os + r0);
+                        if (q.y != tag_old || q.w != tag_old) {          // prefetched copy not there yet (rare): go to the ring
+                            const int so = (slot_s[l] + 1 == L.ring_len) ? 0 : slot_s[l] + 1;
+                            poll2(p.ringLL + L.ring_off + (size_t)so * NS * R + ring_stream + r0, tag_old, o0, o1, p.err, abort_s);
+                        } else {
+                            o0 = __uint_as_float(q.x);
+                            o1 = __uint_as_float(q.z);
+                        }
+                    }
+                    const float c0 = wait_local(xc + r0, tag_cur, abort_s), c1 = wait_local(xc + r0 + 1, tag_cur, abort_s);
+                    if (r0 >= oR && r0 < oR + nR) cur_l[r0 - oR] = c0;           // every warp writes the same values
+                    if (r0 + 1 >= oR && r0 + 1 < oR + nR) cur_l[r0 + 1 - oR] = c1;
+#pragma unroll
+                    for (int j = 0; j < CL_ROWS; ++j)
+                        if (j < rw1) {
+                            const float4 w4 = reinterpret_cast<const float4*>(w + (size_t)j * K1)[g4];
+                            float a = acc[j];
+                            a = fmaf(w4.x, o0, a); a = fmaf(w4.y, c0, a); a = fmaf(w4.z, o1, a); a = fmaf(w4.w, c1, a);
+                            acc[j] = a;
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < CL_ROWS; ++j)
+                    if (j < rw1) acc[j] = warp_sum(acc[j]);
+                release_slot();
+                // rows come in (filter, gate) pairs: channel ci = (warp*rw1 + 2*jj)/2; every lane recomputes z and
+                // lane -> (channel jj = lane / 16, destination CTA = lane % 16)
+                const int dst = lane & 15;
+#pragma unroll
+                for (int jj = 0; jj < CL_ROWS / 2; ++jj)
+                    if (2 * jj < rw1 && ((lane >> 4) == (jj & 1))) {
+                        const int ci = (warp * rw1 >> 1) + jj, c = oD + ci;
+                        const float f = acc[2 * jj] + (L.bf ? __ldg(L.bf + c) : 0.f);
+                        const float g = acc[2 * jj + 1] + (L.bg ? __ldg(L.bg + c) : 0.f);
+                        st_remote_pair(zbuf + c, (unsigned)dst, tanh_(f) * sigmoid_(g), tag_z);
+                    }
+            }
+            // ================= stage 2: warps [0, nR/rw2) residual rows, the rest skip rows; K = D
+            {
+                if (l + 1 < NL) prefetch_old(l + 1, t, slot_s[l + 1]);
+                const int row0 = warp * rw2;
+                const bool is_res = row0 < nR;
+                const bool active = is_res ? (l + 1 < NL) : want_head;
+                const float* w = stage_weights(row0, D);
+                float acc[CL_ROWS];
+#pragma unroll
+                for (int j = 0; j < CL_ROWS; ++j) acc[j] = 0.f;
+                if (active) {
+                    for (int g4 = lane; g4 < (D >> 2); g4 += 32) {
+                        const float z0 = wait_local(zbuf + 4 * g4, tag_z, abort_s), z1 = wait_local(zbuf + 4 * g4 + 1, tag_z, abort_s);
+                        const float z2 = wait_local(zbuf + 4 * g4 + 2, tag_z, abort_s), z3 = wait_local(zbuf + 4 * g4 + 3, tag_z, abort_s);
+#pragma unroll
+                        for (int j = 0; j < CL_ROWS; ++j)
+                            if (j < rw2) {
+                                const float4 w4 = reinterpret_cast<const float4*>(w + (size_t)j * D)[g4];
+                                float a = acc[j];
+                                a = fmaf(w4.x, z0, a); a = fmaf(w4.y, z1, a); a = fmaf(w4.z, z2, a); a = fmaf(w4.w, z3, a);
+                                acc[j] = a;
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CL_ROWS; ++j)
+                        if (j < rw2) acc[j] = warp_sum(acc[j]);
+                }
+                release_slot();
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                // all warps of this CTA are past their reads of z(l) and h(l) before h'(l) leaves (see header comment)
+                WORKER_SYNC();
+                if (l + 1 == NL && ev + 1 < p.n_evals)       // history of the next evaluation's layer 0 (buffer 0 is free now)
+                    prefetch_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
+                        if (is_res) {
+                    if (l + 1 < NL) {
+                        const GenLayer& Ln = lay_s[l + 1];
+                        uint2* xn = xcur + ((l + 1) & 1) * R;
+                        const unsigned tag_n = tag_cur + 2u;
+                        // lane -> (row j = lane / 16 + 2*pass, destination CTA = lane % 16)
+#pragma unroll
+                        for (int ps = 0; ps < CL_ROWS / 2; ++ps) {
+                            const int j = (lane >> 4) + 2 * ps;
+                            if (j < rw2) {
+                                const int li = row0 + j, row = oR + li;
+                                float v = (j == 0) ? acc[0] : (j == 1) ? acc[1] : (j == 2) ? acc[2] : acc[3];
+                                v += L.br ? __ldg(L.br + row) : 0.f;
+                                v += cur_l[li];
+                                st_remote_pair(xn + row, (unsigned)(lane & 15), v, tag_n);
+                                if ((lane & 15) == 0)                      // history for the taps d steps from now
+                                    st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS) * R + ring_stream + row, v, rtag);
+                            }
+                        }
+                    }
+                } else if (want_head && lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < CL_ROWS; ++j)
+                        if (j < rw2) {
+                            const int li = row0 + j - nR, row = oS + li;
+                            const float v = acc[j] + (L.bs ? __ldg(L.bs + row) : 0.f);
+                            skacc[li] = v + skacc[li];
+                        }
+                }
+            }
+        }
+        if (!want_head) continue;
+
+        // ================= head (3 exchanges per evaluation; rows spread one per warp-iteration)
+        const unsigned tag_s = etag + 2u * (unsigned)NL + 1u, tag_y = tag_s + 1u, tag_l = tag_s + 2u;
+        uint2* xs = xhead, *xy = xhead + S, *xl = xhead + S + E;
+        WORKER_SYNC();                                           // skacc complete (written by the skip warps' lane 0)
+        for (int i = tid; i < nS * CL; i += GEN_NT) st_remote_pair(xs + oS + (i >> 4), (unsigned)(i & 15), skacc[i >> 4], tag_s);
+        {
+            const float* w = stage_weights(0, S);
+            for (int it = warp; it < nE; it += GEN_WARPS) {
+                float acc = 0.f;
+                for (int g4 = lane; g4 < (S >> 2); g4 += 32) {
+                    const float4 w4 = reinterpret_cast<const float4*>(w + (size_t)it * S)[g4];
+                    acc = fmaf(w4.x, fmaxf(wait_local(xs + 4 * g4, tag_s, abort_s), 0.f), acc);
+                    acc = fmaf(w4.y, fmaxf(wait_local(xs + 4 * g4 + 1, tag_s, abort_s), 0.f), acc);
+                    acc = fmaf(w4.z, fmaxf(wait_local(xs + 4 * g4 + 2, tag_s, abort_s), 0.f), acc);
+                    acc = fmaf(w4.w, fmaxf(wait_local(xs + 4 * g4 + 3, tag_s, abort_s), 0.f), acc);
+                }
+                acc = warp_sum(acc);
+                const int row = oE + it;
+                if (lane < CL) st_remote_pair(xy + row, (unsigned)lane, fmaxf(acc + __ldg(p.e1b + row), 0.f), tag_y);
+            }
+            release_slot();
+        }
+        {
+            const float* w = stage_weights(0, E);
+            for (int it = warp; it < nC; it += GEN_WARPS) {
+                float acc = 0.f;
+                for (int g4 = lane; g4 < (E >> 2); g4 += 32) {
+                    const float4 w4 = reinterpret_cast<const float4*>(w + (size_t)it * E)[g4];
+                    acc = fmaf(w4.x, wait_local(xy + 4 * g4, tag_y, abort_s), acc);
+                    acc = fmaf(w4.y, wait_local(xy + 4 * g4 + 1, tag_y, abort_s), acc);
+                    acc = fmaf(w4.z, wait_local(xy + 4 * g4 + 2, tag_y, abort_s), acc);
+                    acc = fmaf(w4.w, wait_local(xy + 4 * g4 + 3, tag_y, abort_s), acc);
+                }
+                acc = warp_sum(acc);
+                const int row = oC + it;
+                const float dc = (float)row - (float)C / 2.f;
+                const float v = (acc + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+                if (lane < CL) st_remote_pair(xl + row, (unsigned)lane, v, tag_l);
+                if (lane == 0 && p.out_logits) p.out_logits[((size_t)stream * p.n_samples + samp) * C + row] = v;
+            }
+            release_slot();
+        }
+        for (int c = tid; c < C; c += GEN_NT) logit_s[c] = wait_local(xl + c, tag_l, abort_s);
+        WORKER_SYNC();
+        if (warp == 0) {
+            const int choice = choose_sample(logit_s, cdf, C, lane, p.temperature,
+                                             p.uniforms ? p.uniforms + (size_t)stream * p.n_samples + samp : nullptr);
+            if (lane == 0) {
+                misc[0] = choice;
+                if (rank == 0) p.out_idx[(size_t)stream * p.n_samples + samp] = choice;
+            }
+        }
+    }
+    WORKER_SYNC();
+    if (rank == 0 && tid == 0) p.cur_idx[stream] = misc[0];
+    cluster_sync_all();                                          // peers may still be storing into this CTA's shared memory
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
     size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, total;
@@ -1379,6 +1749,9 @@ struct wn_gen_handle {
     size_t smem_fast;
     int n_wslots_fast;
     int xn_fast;
+    bool cluster_ok;        // k=2, 256-class nets whose rows split over 16 CTAs x 8 warps: gen_kernel_cluster applies
+    size_t smem_cluster;
+    int n_wslots_cluster, wslot_cluster;
 };
 
 static int validate_shape(const wn_gen_shape* s) {
@@ -1559,6 +1932,40 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
             h->fast_ok = h->smem_fast <= (size_t)smem_optin;
         }
     }
+    // ---- cluster kernel eligibility: rows of every stage split evenly over 16 CTAs x 8 warps, <= 4 rows per warp
+    {
+        auto div_ok = [&](int N) { return N % CL == 0; };
+        bool ok = s->k == 2 && s->n_layers >= 2 && div_ok(s->D) && div_ok(s->R) && div_ok(s->S) && div_ok(s->E) &&
+                  div_ok(s->classes) && (s->R % 4 == 0) && (s->D % 4 == 0) && (s->S % 4 == 0) && (s->E % 4 == 0);
+        if (ok) {
+            const int nD = s->D / CL, nR = s->R / CL, nS = s->S / CL;
+            const int rw1 = 2 * nD / GEN_WARPS, rw2 = (nR + nS) / GEN_WARPS;
+            ok = (2 * nD) % GEN_WARPS == 0 && (nR + nS) % GEN_WARPS == 0 && (rw1 == 2 || rw1 == 4) && rw2 >= 1 && rw2 <= CL_ROWS &&
+                 nR % rw2 == 0 && (rw2 == 2 || rw2 == 4 || rw2 == 1);
+        }
+        h->cluster_ok = false;
+        if (ok && !getenv("WN_GEN_NOCLUSTER")) {
+            long long slot = (long long)2 * (s->D / CL) * 2 * s->R;
+            if ((long long)(s->R / CL + s->S / CL) * s->D > slot) slot = (long long)(s->R / CL + s->S / CL) * s->D;
+            if ((long long)(s->E / CL) * s->S > slot) slot = (long long)(s->E / CL) * s->S;
+            if ((long long)(s->classes / CL) * s->E > slot) slot = (long long)(s->classes / CL) * s->E;
+            slot = (slot + 3) / 4 * 4;
+            const size_t cbase = sizeof(uint2) * (size_t)(2 * s->R + 2 * s->D + s->S + s->E + s->classes + 2 * s->R) +
+                                 sizeof(float) * (size_t)(((s->S / CL + 3) & ~3) + 2 * ((s->R / CL + 3) & ~3) +
+                                                          (((s->E + s->classes) / CL + 32 + 3) & ~3) + ((s->classes + 3) & ~3)) +
+                                 sizeof(double) * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
+                                 sizeof(int) * (size_t)(s->n_layers + 4);
+            int cs = 0;
+            if (cbase < (size_t)smem_optin) {
+                long long fit = ((long long)smem_optin - (long long)cbase) / (slot * 4);
+                cs = fit >= 4 ? 4 : (fit >= 2 ? 2 : 0);
+            }
+            h->n_wslots_cluster = cs;
+            h->wslot_cluster = (int)slot;
+            h->smem_cluster = cbase + (size_t)cs * slot * 4;
+            h->cluster_ok = cs >= 2 && h->smem_cluster <= (size_t)smem_optin;
+        }
+    }
     h->tables_uploaded = false;
     h->cur_t = 0;
     *out = h;
@@ -1603,6 +2010,28 @@ static int launch_gen_ll(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     return 0;
 }
 
+static int launch_gen_cluster(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cluster));
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(h->shape.n_streams * CL));
+    cfg.blockDim = dim3(GEN_NT + 32);
+    cfg.dynamicSmemBytes = h->smem_cluster;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_cluster, &cfg));
+    WN_REQUIRE(max_clusters >= 1, WN_E_UNSUPP, "wn_gen_run: a %d-CTA cluster cannot be scheduled on this device", CL);
+    WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_cluster, p));
+    return 0;
+}
+
 template <bool PF>
 static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
@@ -1616,8 +2045,11 @@ static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
 
 extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_set_mode: null handle");
-    WN_REQUIRE(mode >= 0 && mode <= 2, WN_E_BADARG,
-               "wn_gen_set_mode: mode must be 0 (best flag-exchange kernel), 1 (grid barrier) or 2 (generic flag exchange)");
+    WN_REQUIRE(mode >= 0 && mode <= 4, WN_E_BADARG,
+               "wn_gen_set_mode: mode must be 0 (auto), 1 (grid barrier), 2 (generic flag exchange), 3 (single-stream L2 kernel) "
+               "or 4 (cluster / DSMEM kernel)");
+    if (mode == 3) WN_REQUIRE(h->fast_ok, WN_E_UNSUPP, "wn_gen_set_mode: the single-stream L2 kernel does not apply to this shape");
+    if (mode == 4) WN_REQUIRE(h->cluster_ok, WN_E_UNSUPP, "wn_gen_set_mode: the cluster kernel does not apply to this shape");
     WN_REQUIRE(h->cur_t == 0, WN_E_STATE, "wn_gen_set_mode: switch kernels only right after wn_gen_reset");
     if (mode != 1) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
     h->mode = mode;
@@ -1659,7 +2091,11 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         p.t0 = a->t0 + done; p.n_evals = n; p.temperature = a->temperature; p.regularize = a->regularize;
         WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
         int rc;
-        if (h->mode == 0 && h->fast_ok) {
+        if ((h->mode == 0 || h->mode == 4) && h->cluster_ok) {
+            p.n_wslots = h->n_wslots_cluster;
+            p.wslot_floats = h->wslot_cluster;
+            rc = launch_gen_cluster(h, p, st);
+        } else if ((h->mode == 0 || h->mode == 3) && h->fast_ok) {
             p.n_wslots = h->n_wslots_fast;
             p.regA = h->xn_fast;                    // the fast kernel reads its input-vector pitch from regA
             rc = p.n_wslots ? launch_gen_fast<true>(h, p, st) : launch_gen_fast<false>(h, p, st);

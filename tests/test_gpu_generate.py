@@ -162,19 +162,56 @@ def test_fast_kernel_equals_generic_kernel_bitwise(golden):
     first = rng.randint(0, 256, size=(3, 7))
     uni = rng.random_sample((3, 40))
     out = {}
-    for mode in (0, 2):
+    for mode in (3, 2):
         rt.gen_mode = mode
         out[mode] = [m.generate_fast_batch(40, first[s:s + 1], temperature=1.0, uniforms=uni[s:s + 1], return_logits=True)
                      for s in range(3)]
+    for s in range(3):
+        assert np.array_equal(out[3][s][0], out[2][s][0]) and np.array_equal(out[3][s][1], out[2][s][1])
+    rt.gen_mode = 2
+    multi_idx, multi_lg = m.generate_fast_batch(40, first, temperature=1.0, uniforms=uni, return_logits=True)
     rt.gen_mode = None
     for s in range(3):
-        assert np.array_equal(out[0][s][0], out[2][s][0]) and np.array_equal(out[0][s][1], out[2][s][1])
-    multi_idx, multi_lg = m.generate_fast_batch(40, first, temperature=1.0, uniforms=uni, return_logits=True)
-    for s in range(3):
-        assert np.array_equal(multi_idx[s], out[0][s][0][0]) and np.array_equal(multi_lg[s], out[0][s][1][0])
+        assert np.array_equal(multi_idx[s], out[3][s][0][0]) and np.array_equal(multi_lg[s], out[3][s][1][0])
     # argmax + warm-up + chunked launches (progress callback) through the fast kernel
     calls = []
     a = m.generate_fast(30, first_samples=first[0], temperature=0.0, progress_callback=lambda i, n: calls.append(i),
                         progress_interval=7)
     b = m.generate_fast(30, first_samples=first[0], temperature=0.0)
+    assert np.array_equal(a, b) and len(calls) > 3
+
+
+def test_cluster_kernel_cfg2(golden):
+    """The cluster (distributed shared memory) kernel is what a 256-channel net runs by default: golden parity,
+    agreement with the L2 kernels, and multi-stream == single-stream bit for bit (one cluster per stream)."""
+    g = golden("net_cfg2.npz")
+    m = build_model(g)
+    rt = m._runtime()
+    rng = np.random.RandomState(8)
+    first = rng.randint(0, 256, size=(5, 9))
+    uni = rng.random_sample((5, 60))
+    rt.gen_mode = 4
+    idx4, lg4 = m.generate_fast_batch(60, first, temperature=1.0, uniforms=uni, return_logits=True)
+    singles = [m.generate_fast_batch(60, first[s:s + 1], temperature=1.0, uniforms=uni[s:s + 1], return_logits=True)
+               for s in range(5)]
+    for s in range(5):
+        assert np.array_equal(singles[s][0][0], idx4[s]) and np.array_equal(singles[s][1][0], lg4[s])
+    # teacher-forced logits against the reference's golden stream
+    _, lg = m.generate_fast_batch(48, np.array([[128]]), temperature=0.0, forced=g["gen_argmax_idx"][None, :],
+                                  return_logits=True)
+    assert rel_err(lg[0], g["gen_argmax_logits"]) < TOL
+    idx, _ = m.generate_fast_batch(48, np.array([[128]]), temperature=0.0, return_logits=True)
+    assert_stream_parity(idx[0], g["gen_argmax_idx"], g["gen_argmax_logits"])
+    # against the generic L2 kernel on the same inputs (teacher forced so rounding cannot fork the streams)
+    rt.gen_mode = 2
+    _, lg2 = m.generate_fast_batch(60, first[:2], temperature=1.0, uniforms=uni[:2], forced=idx4[:2], return_logits=True)
+    rt.gen_mode = 4
+    _, lg4f = m.generate_fast_batch(60, first[:2], temperature=1.0, uniforms=uni[:2], forced=idx4[:2], return_logits=True)
+    rt.gen_mode = None
+    assert rel_err(lg4f, lg2) < 1e-5
+    # chunked launches (progress callback) continue the cluster kernel's state correctly
+    calls = []
+    a = m.generate_fast(40, first_samples=first[0], temperature=0.0, progress_callback=lambda i, n: calls.append(i),
+                        progress_interval=9)
+    b = m.generate_fast(40, first_samples=first[0], temperature=0.0)
     assert np.array_equal(a, b) and len(calls) > 3
