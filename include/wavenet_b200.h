@@ -166,8 +166,9 @@ int wn_head_bwd_data(const wn_head_bwd_args* a, void* stream);
  * `n_evals` network evaluations without returning to the host; the per-layer ring buffers live in d_rings.
  *
  * Weights are the reference's own parameter tensors, UNPACKED (state_dict layout); bias pointers may be NULL.
- * n_streams independent streams share the weights (the reference has a single stream, wavenet_model.py:179;
- * stream s of a multi-stream run equals a single-stream run with the same inputs bit for bit).            */
+ * n_streams independent streams share the weights (the reference has a single stream, wavenet_model.py:179).
+ * Run through the SAME kernel (wn_gen_set_mode), stream s of a multi-stream run equals a single-stream run with the
+ * same inputs bit for bit; different kernels split the dot products differently (rounding-level differences). */
 typedef struct wn_gen_weights {
     const float* d_start_w; const float* d_start_b;            /* (R,classes,1), (R) */
     const float* const* d_wf; const float* const* d_bf;        /* HOST arrays [n_layers] of device pointers */
@@ -211,7 +212,8 @@ typedef struct wn_gen_run_args {
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
 /* Which sampler kernel runs (all implement the same schedule; call right after wn_gen_reset):
- *   0  auto: the cluster kernel when the shape allows, else the single-stream L2 kernel, else the generic one
+ *   0  auto: one stream -> the single-stream L2 kernel (lowest latency: the whole GPU works on one sample);
+ *            several streams -> one cluster per stream (kernel 4); otherwise the generic kernel
  *   1  atomic grid barrier between stages (the simple reference kernel)
  *   2  generic flag-in-data exchange through L2 (any shape, any number of streams)
  *   3  single-stream L2 kernel with register-free cooperative polling (k = 2, power-of-two row split)

@@ -2091,7 +2091,8 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         p.t0 = a->t0 + done; p.n_evals = n; p.temperature = a->temperature; p.regularize = a->regularize;
         WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
         int rc;
-        if ((h->mode == 0 || h->mode == 4) && h->cluster_ok) {
+        const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
+        if ((auto_cluster || h->mode == 4) && h->cluster_ok) {
             p.n_wslots = h->n_wslots_cluster;
             p.wslot_floats = h->wslot_cluster;
             rc = launch_gen_cluster(h, p, st);

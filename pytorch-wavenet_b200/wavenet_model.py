@@ -633,7 +633,9 @@ class WaveNetModel(nn.Module):
                             forced=None, return_logits=False):
         """``n_streams`` independent generate_fast runs batched in one kernel (the reference has a single stream,
         wavenet_model.py:179).  first_samples: (n_streams, n_given) ints.  Returns int64 indices
-        (n_streams, num_samples) [and the per-step logits].  Stream s equals a single-stream run bit for bit."""
+        (n_streams, num_samples) [and the per-step logits].  Run through the same sampler kernel, stream s equals a
+        single-stream run bit for bit (the default picks a latency kernel for one stream and one thread-block cluster per
+        stream otherwise; those differ at rounding level)."""
         self.eval()
         first = np.asarray(first_samples.detach().cpu().numpy() if torch.is_tensor(first_samples) else first_samples)
         first = first.astype(np.int64).reshape(first.shape[0], -1) if first.ndim > 1 else first.astype(np.int64)[None, :]
