@@ -29,6 +29,7 @@ constexpr int W_BYTES = BN * BK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
 constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
 constexpr int SPLIT_THREADS = 128;
+constexpr int CS = 2;                       // CTAs per cluster sharing every weight slab through TMA multicast
 constexpr int TP = 36;                      // pitch of the 32x32 epilogue transpose tile (conflict-free 128-bit access)
 constexpr unsigned SPIN_LIMIT = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
 
@@ -59,6 +60,24 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar,
+                                               unsigned short mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(s32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(unsigned long long* bar, unsigned short mask) {   // arrive on `bar` of every CTA in mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(s32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank_() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(unsigned* slot_in_smem, unsigned cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot_in_smem)), "r"(cols) : "memory");
@@ -136,6 +155,7 @@ __device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(
 template <int EPI, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+    // mapW's box is BN/CS rows: every CTA of the cluster fetches its share of a weight slab and multicasts it to all
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* stage_mem = base;                                           // STAGES * STAGE_BYTES
@@ -152,11 +172,17 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_tiles = (p.L - p.t_begin + BM - 1) / BM;
     const int items = p.B * m_tiles;
+    // Work: item (sequence b, 128-frame tile) number (cluster + round * n_clusters) * CS + rank.  The CTAs of a cluster walk
+    // the same (output tile, K slab) sequence in lockstep because they share the weight slabs; a CTA whose item does not
+    // exist runs a ghost tile (frames beyond L: TMA zero fill, no stores) so that it keeps feeding its peers.
+    const int crank = (int)cluster_rank_(), n_clusters = gridDim.x / CS, cluster_id = blockIdx.x / CS;
+    const int rounds = (items + n_clusters * CS - 1) / (n_clusters * CS);
+    const unsigned short mc_mask = (unsigned short)((1u << CS) - 1u);
     const int slabs_per_tap = p.C / BK;
     const int slabs = p.taps * slabs_per_tap;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, CS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -166,6 +192,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int i = tid; i < p.n_total; i += NTHREADS) bias_s[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
+    cluster_sync_();                              // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
@@ -173,19 +200,24 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================================================================= TMA producer
         if (elect_one()) {
             unsigned it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int b = item / m_tiles, t0 = p.t_begin + (item % m_tiles) * BM;
+            for (int rd = 0; rd < rounds; ++rd) {
+                const int item = (cluster_id + rd * n_clusters) * CS + crank;
+                const bool ghost = item >= items;
+                const int b = ghost ? 0 : item / m_tiles, t0 = ghost ? p.L : p.t_begin + (item % m_tiles) * BM;
                 for (int nt = 0; nt < p.n_tiles; ++nt)
                     for (int sl = 0; sl < slabs; ++sl, ++it) {
                         const int st = it % STAGES;
                         const unsigned ph = (it / STAGES) & 1;
-                        mbar_wait(empty + st, ph ^ 1);
+                        mbar_wait(empty + st, ph ^ 1);           // every CTA of the cluster is done with this stage
                         unsigned char* sm = stage_mem + st * STAGE_BYTES;
                         const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
                         mbar_expect_tx(full + st, A_BYTES + (EXACT ? 2 : 1) * W_BYTES);
                         tma_load_3d(sm, &mapA, c0, t0 - (p.taps - 1 - j) * p.dil - p.a_origin, b, full + st);
-                        tma_load_2d(sm + 2 * A_BYTES, &mapW, sl * BK, nt * BN, full + st);
-                        if (EXACT) tma_load_2d(sm + 2 * A_BYTES + W_BYTES, &mapW, sl * BK, p.n_total + nt * BN, full + st);
+                        constexpr int WR = BN / CS, WB = W_BYTES / CS;      // this CTA's rows / bytes of the slab
+                        tma_load_2d_mc(sm + 2 * A_BYTES + crank * WB, &mapW, sl * BK, nt * BN + crank * WR, full + st, mc_mask);
+                        if (EXACT)
+                            tma_load_2d_mc(sm + 2 * A_BYTES + W_BYTES + crank * WB, &mapW, sl * BK, p.n_total + nt * BN + crank * WR,
+                                           full + st, mc_mask);
                     }
             }
         }
@@ -193,7 +225,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================================================================= MMA issuer
         constexpr unsigned idesc = make_idesc();
         unsigned it = 0, tile = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x)
+        for (int rd = 0; rd < rounds; ++rd)
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                 const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
                 mbar_wait(acc_empty + ab, aph ^ 1);
@@ -217,7 +249,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 umma_tf32(d_tmem, a_hi + o, w_lo + o, idesc, 1);
                             }
                         }
-                        umma_commit(empty + st);                 // stage reusable once these MMAs retire
+                        umma_commit_mc(empty + st, mc_mask);     // stage reusable (in every CTA) once these MMAs retire
                         if (sl == slabs - 1) umma_commit(acc_full + ab);
                     }
                     __syncwarp();
@@ -227,7 +259,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================================================================= splitter (warps 2,3,8,9 = 128 threads)
         const int st_tid = warp < 4 ? tid - 64 : tid - 192;
         unsigned it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x)
+        for (int rd = 0; rd < rounds; ++rd)
             for (int nt = 0; nt < p.n_tiles; ++nt)
                 for (int sl = 0; sl < slabs; ++sl, ++it) {
                     const int st = it % STAGES;
@@ -254,8 +286,10 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================================================================= epilogue (warps 4..7 = TMEM lane quadrants 0..3)
         const int q = warp - 4;
         unsigned tile = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int b = item / m_tiles, t0 = p.t_begin + (item % m_tiles) * BM;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int item = (cluster_id + rd * n_clusters) * CS + crank;
+            const bool ghost = item >= items;
+            const int b = ghost ? 0 : item / m_tiles, t0 = ghost ? p.L : p.t_begin + (item % m_tiles) * BM;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                 const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
                 mbar_wait(acc_full + ab, aph);
@@ -361,6 +395,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_();                              // no peer may still signal this CTA's barriers after it is gone
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -438,7 +473,7 @@ static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
     WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t box[2] = {BK, BN / CS};          // one CTA's share of a slab; the multicast assembles the rest
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -459,8 +494,22 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParam
     const size_t smem = tc_smem_bytes(p.n_total);
     WN_CUDA(cudaFuncSetAttribute(frames_gemm_tc<EPI, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int items = p.B * ((p.L - p.t_begin + BM - 1) / BM);
-    const int grid = items < sms ? items : sms;
-    frames_gemm_tc<EPI, EXACT><<<grid, NTHREADS, smem, st>>>(mA, mW, p);
+    int grid = ((items + CS - 1) / CS) * CS;
+    const int max_grid = (sms / CS) * CS;
+    if (grid > max_grid) grid = max_grid;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WN_CUDA(cudaLaunchKernelEx(&cfg, frames_gemm_tc<EPI, EXACT>, mA, mW, p));
     WN_CUDA(cudaGetLastError());
     return 0;
 }
