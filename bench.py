@@ -506,6 +506,8 @@ def main():
             line["argmax_samples_per_s"] = gen["argmax_samples_per_s"]
             if train is not None:
                 line["train"] = train
+        else:
+            line.update({k: train[k] for k in ("train_step", "fast_tf32", "e2e_index_api", "cpu_baseline") if k in train})
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

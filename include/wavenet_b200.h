@@ -113,6 +113,9 @@ typedef struct wn_tc_block_args {
                          * after 50 layers -- OUTSIDE the 1e-4 parity bar; opt-in, reported separately by bench.py */
 } wn_tc_block_args;
 int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream);
+/* Debug aid (WN_TC_TRACE=1): per-stage clock64 stamps of CTA 0 of the most recent tensor-core launch, 8 per stage:
+ * producer before/after the empty wait, MMA warp before/after the operand wait and after issue, splitter start/end. */
+int wn_tc_read_trace(long long* host_out, int n);
 
 /* ---------------------------------------------------------------- (T) head
  * replaces relu -> end_conv_1 -> relu -> end_conv_2 (wavenet_model.py:167-169) and forward()'s

@@ -15,6 +15,7 @@
 // mbarriers: full (TMA landed), split (lo ready), empty (MMAs of the stage retired), acc_full / acc_empty.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 
 namespace wn {
@@ -22,11 +23,13 @@ namespace tc {
 
 constexpr int BM = 128;            // frames per tile (UMMA M)
 constexpr int BN = 256;            // output columns per tile (UMMA N)
-constexpr int BK = 16;             // fp32 per K slab = 64 bytes = one 64B-swizzle row (two k-steps of 8)
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 4;          // 8 KB
-constexpr int W_BYTES = BN * BK * 4;          // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
+constexpr int BK = 8;              // fp32 per K slab = 32 bytes = one 32B-swizzle row = one k-step (measured: a stage slot takes
+                                   // ~3500 cycles to come round (TMA ~1900 + split ~700 + MMA + hand-offs), so the ring must
+                                   // hold >= 8 stages of <= 384 MMA cycles each to keep the tensor pipe busy)
+constexpr int STAGES = 8;
+constexpr int A_BYTES = BM * BK * 4;          // 4 KB
+constexpr int W_BYTES = BN * BK * 4;          // 8 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 24 KB
 constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
 constexpr int SPLIT_THREADS = 128;
 constexpr int CS = 2;                       // CTAs per cluster sharing every weight slab through TMA multicast
@@ -116,7 +119,7 @@ __device__ __forceinline__ bool elect_one() {
 // (64B rows -> SWIZZLE_64B, 128B rows -> SWIZZLE_128B); 8-row atoms are 8*row_bytes apart
 __device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
     constexpr unsigned row_bytes = BK * 4;
-    constexpr unsigned long long layout = (row_bytes == 128) ? 2ull : 4ull;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    constexpr unsigned long long layout = (row_bytes == 128) ? 2ull : (row_bytes == 64 ? 4ull : 6ull);   // SWIZZLE_128B/64B/32B
     unsigned long long d = 0;
     d |= (unsigned long long)((saddr >> 4) & 0x3fff);            // start address, 16-byte units
     d |= (unsigned long long)1 << 16;                            // leading byte offset (unused for swizzled K-major)
@@ -144,6 +147,7 @@ struct TcParams {
     float* out1;                  // GATE: fg_save (B,L,2D)|0   RES_SKIP: skip (B,L-skip_start,S)
     const float* res;             // RES_SKIP: h_in (B,L,R)
     int D, R, S, in_start, skip_start, skip_init;
+    long long* dbg;               // optional trace buffer (WN_TC_TRACE): CTA 0 stamps clock64 per stage, see tools/tc_trace.py
 };
 
 __device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
@@ -166,7 +170,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned long long* acc_full = bars + 3 * STAGES;      // [2]
     unsigned long long* acc_empty = bars + 3 * STAGES + 2; // [2]
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * STAGES + 4);
-    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                   // [n_total]
+    float* bias_s = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES + 512);                   // [n_total]
     float* stage_t = bias_s + ((p.n_total + 3) & ~3);                          // [4 warps][32][TP] epilogue transpose tiles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -208,7 +212,9 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int sl = 0; sl < slabs; ++sl, ++it) {
                         const int st = it % STAGES;
                         const unsigned ph = (it / STAGES) & 1;
+                        if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it * 8 + 0] = clock64();
                         mbar_wait(empty + st, ph ^ 1);           // every CTA of the cluster is done with this stage
+                        if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it * 8 + 1] = clock64();
                         unsigned char* sm = stage_mem + st * STAGE_BYTES;
                         const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
                         mbar_expect_tx(full + st, A_BYTES + (EXACT ? 2 : 1) * W_BYTES);
@@ -234,7 +240,9 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int sl = 0; sl < slabs; ++sl, ++it) {
                     const int st = it % STAGES;
                     const unsigned ph = (it / STAGES) & 1;
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 2] = clock64();
                     mbar_wait(split + st, ph);                   // TMA landed and the splitter produced hi/lo
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 3] = clock64();
                     tc_fence_after();
                     if (elect_one()) {
                         const unsigned sa = s32(stage_mem + st * STAGE_BYTES);
@@ -253,6 +261,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (sl == slabs - 1) umma_commit(acc_full + ab);
                     }
                     __syncwarp();
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 4] = clock64();
                 }
             }
     } else if (warp < 4 || warp >= 8) {
@@ -265,6 +274,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int st = it % STAGES;
                     const unsigned ph = (it / STAGES) & 1;
                     mbar_wait(full + st, ph);
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && st_tid == 0) p.dbg[it * 8 + 5] = clock64();
                     float4* hi = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES);
                     float4* lo = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES + A_BYTES);
 #pragma unroll
@@ -280,6 +290,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         lo[i] = l;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && st_tid == 0) p.dbg[it * 8 + 6] = clock64();
                     mbar_arrive(split + st);
                 }
     } else {
@@ -462,7 +473,7 @@ static int make_act_map(CUtensorMap* m, const float* base, int B, int L, int C, 
     cuuint32_t box[3] = {BK, BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(base + (size_t)origin * C), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : (BK * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
     return 0;
@@ -476,14 +487,15 @@ static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
     cuuint32_t box[2] = {BK, BN / CS};          // one CTA's share of a slab; the multicast assembles the rest
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : (BK * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
     return 0;
 }
 
 static size_t tc_smem_bytes(int n_total) {
-    return 1024 + (size_t)STAGES * STAGE_BYTES + 256 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 4 * 32 * TP;
+    return 1024 + (size_t)STAGES * STAGE_BYTES + 512 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 4 * 32 * TP;
 }
 
 template <int EPI, bool EXACT>
@@ -519,6 +531,14 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParam
 
 using namespace wn;
 
+static long long* g_tc_dbg = nullptr;
+extern "C" int wn_tc_read_trace(long long* host_out, int n) {
+    WN_REQUIRE(g_tc_dbg && host_out && n > 0 && n <= 512 * 8, WN_E_STATE, "wn_tc_read_trace: tracing is off (WN_TC_TRACE=1) or bad n");
+    WN_CUDA(cudaDeviceSynchronize());
+    WN_CUDA(cudaMemcpy(host_out, g_tc_dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int wn_tc_supported(int R, int D, int S, int k) {
     return (R % 256 == 0) && (S % 256 == 0) && (D % 128 == 0) && k >= 1 && (R + S) <= 2048 && 2 * D <= 2048;
 }
@@ -551,6 +571,10 @@ extern "C" int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream) {
     if (int rc = tc::make_w_map(&mWb, a->d_wb, 2 * (a->R + a->S), a->D)) return rc;
     tc::TcParams p;
     memset(&p, 0, sizeof(p));
+    if (getenv("WN_TC_TRACE")) {
+        if (!g_tc_dbg) WN_CUDA(cudaMalloc(&g_tc_dbg, sizeof(long long) * 512 * 8));
+        p.dbg = g_tc_dbg;
+    }
     p.B = a->B; p.L = a->L; p.t_begin = a->out_start;
     p.D = a->D; p.R = a->R; p.S = a->S; p.in_start = a->in_start; p.skip_start = a->skip_start; p.skip_init = a->skip_init;
     // pass A: conv taps + gate
