@@ -23,13 +23,14 @@ namespace tc {
 
 constexpr int BM = 128;            // frames per tile (UMMA M)
 constexpr int BN = 256;            // output columns per tile (UMMA N)
-constexpr int BK = 8;              // fp32 per K slab = 32 bytes = one 32B-swizzle row = one k-step (measured: a stage slot takes
-                                   // ~3500 cycles to come round (TMA ~1900 + split ~700 + MMA + hand-offs), so the ring must
-                                   // hold >= 8 stages of <= 384 MMA cycles each to keep the tensor pipe busy)
-constexpr int STAGES = 8;
-constexpr int A_BYTES = BM * BK * 4;          // 4 KB
-constexpr int W_BYTES = BN * BK * 4;          // 8 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 24 KB
+constexpr int BK = 16;             // fp32 per K slab = 64 bytes = one 64B-swizzle row (two k-steps of 8).  Measured on B200:
+                                   // 128B rows x 2 stages 36.4 ms, 64B x 4 stages 27.7 ms, 32B x 8 stages 33.5 ms per cfg-3
+                                   // forward -- a stage slot needs ~3500 cycles to come round (TMA ~1900, split ~700), so
+                                   // depth matters, but TMA latency grows again when the boxes get too small
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;          // 8 KB
+constexpr int W_BYTES = BN * BK * 4;          // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
 constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
 constexpr int SPLIT_THREADS = 128;
 constexpr int CS = 2;                       // CTAs per cluster sharing every weight slab through TMA multicast
