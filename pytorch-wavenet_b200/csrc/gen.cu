@@ -948,7 +948,7 @@ __device__ __noinline__ int choose_sample(float* logit_s, double* cdf, int C, in
     return choice;
 }
 
-template <bool PREFETCH>
+template <bool PREFETCH, bool TRACE>
 __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParams p) {
     extern __shared__ __align__(16) float sm[];
     float* part = sm;                                   // [2][GEN_WARPS] partial sums, double buffered by stage parity
@@ -1103,9 +1103,9 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_fast(const GenParam
         if (*abort_s) return;
         int idx = misc[0];
         idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
-        const bool tr_on = p.trace != nullptr && cta == 0 && tid == 0 && ev == p.n_evals - 1;
+        const bool tr_on = TRACE && p.trace != nullptr && cta == 0 && tid == 0 && ev == p.n_evals - 1;
         int tr_n = 0;
-#define TR() do { if (tr_on && tr_n < 2040) p.trace[tr_n++] = clock64(); } while (0)
+#define TR() do { if (TRACE) { if (tr_on && tr_n < 2040) p.trace[tr_n++] = clock64(); } } while (0)
         TR();
 
         for (int l = 0; l < NL; ++l) {
@@ -2032,15 +2032,21 @@ static int launch_gen_cluster(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <bool PF>
-static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
-    WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
+template <bool PF, bool TRACE>
+static int launch_gen_fast_t(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
     int per_sm = 0;
-    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_fast<PF>, GEN_NT + 32, h->smem_fast));
+    WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_kernel_fast<PF, TRACE>, GEN_NT + 32, h->smem_fast));
     WN_REQUIRE(per_sm * h->sm_count >= h->grid, WN_E_UNSUPP, "wn_gen_run: %d CTAs cannot be co-resident", h->grid);
     void* args[] = {(void*)&p};
-    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_fast<PF>, dim3(h->grid), dim3(GEN_NT + 32), args, h->smem_fast, st));
+    WN_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel_fast<PF, TRACE>, dim3(h->grid), dim3(GEN_NT + 32), args,
+                                        h->smem_fast, st));
     return 0;
+}
+template <bool PF>
+static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    // the stamping variant is a separate instantiation so that the production kernel's hot loop carries no trace code
+    return p.trace ? launch_gen_fast_t<PF, true>(h, p, st) : launch_gen_fast_t<PF, false>(h, p, st);
 }
 
 extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
