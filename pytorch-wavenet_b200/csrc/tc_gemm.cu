@@ -360,9 +360,13 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const bool is_res = n0 < p.R;
                     const float* bt = bias_s + n0;
                     const int Tsk = p.L - p.skip_start;
-                    // the values this lane adds in the coalesced domain (residual h_in(t) or the running skip) are fetched one
-                    // 32-column chunk ahead, so their latency hides behind the TMEM read / transpose / stores of the chunk before
-                    auto fetch_x = [&](int c, float4 (&x)[8]) {
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32) {
+                        float v[32];
+                        tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+                        tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                        // the values this lane will add in the coalesced domain (residual h_in(t) or the running skip)
+                        float4 x[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int fr = tbase + 4 * i + sub_r;
@@ -376,38 +380,23 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 }
                             }
                         }
-                    };
-                    float4 xa[8], xb[8];
-                    fetch_x(0, xa);
-#pragma unroll 1
-                    for (int c = 0; c < BN; c += 64) {
+                        tmem_ld_wait();
+                        __syncwarp();
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int cc = c + 32 * half;
-                            float v[32];
-                            tmem_ld16(taddr + cc, *reinterpret_cast<float(*)[16]>(&v[0]));
-                            tmem_ld16(taddr + cc + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-                            if (half == 0) fetch_x(cc + 32, xb);
-                            else if (cc + 32 < BN) fetch_x(cc + 32, xa);
-                            tmem_ld_wait();
-                            __syncwarp();
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(tt + lane * TP + i) =
+                                make_float4(v[i] + bt[c + i], v[i + 1] + bt[c + i + 1], v[i + 2] + bt[c + i + 2], v[i + 3] + bt[c + i + 3]);
+                        __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                *reinterpret_cast<float4*>(tt + lane * TP + i) =
-                                    make_float4(v[i] + bt[cc + i], v[i + 1] + bt[cc + i + 1], v[i + 2] + bt[cc + i + 2], v[i + 3] + bt[cc + i + 3]);
-                            __syncwarp();
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int fr = tbase + 4 * i + sub_r;
-                                if (fr >= p.L) continue;
-                                float4 o = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
-                                const float4 xv = half == 0 ? xa[i] : xb[i];
-                                o.x += xv.x; o.y += xv.y; o.z += xv.z; o.w += xv.w;
-                                if (is_res)
-                                    *reinterpret_cast<float4*>(p.out0 + ((size_t)b * p.L + fr) * p.R + n0 + cc + sub_c) = o;
-                                else if (fr >= p.skip_start)
-                                    *reinterpret_cast<float4*>(p.out1 + ((size_t)b * Tsk + (fr - p.skip_start)) * p.S + (n0 - p.R) + cc + sub_c) = o;
-                            }
+                        for (int i = 0; i < 8; ++i) {
+                            const int fr = tbase + 4 * i + sub_r;
+                            if (fr >= p.L) continue;
+                            float4 o = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
+                            o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w;
+                            if (is_res)
+                                *reinterpret_cast<float4*>(p.out0 + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c) = o;
+                            else if (fr >= p.skip_start)
+                                *reinterpret_cast<float4*>(p.out1 + ((size_t)b * Tsk + (fr - p.skip_start)) * p.S + (n0 - p.R) + c + sub_c) = o;
                         }
                     }
                 }
