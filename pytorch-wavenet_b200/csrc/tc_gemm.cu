@@ -7,11 +7,12 @@
 //            the dilation; frames left of in_start come back as zeros from the TMA out-of-bounds fill)
 //            epilogue: z = tanh(F+bf) * sigmoid(G+bg)  -> z (B,L,D)  [+ optional f,g for the backward]
 //   pass B   [O|S][128 x 256] per tile = z[128 x D] * Wb^T ;  h_out = O + br + h_in,  skip (+)= S + bs
-// Kernel anatomy (one CTA per SM, persistent over (sequence, 128-frame tile) items, 320 threads):
+// Kernel anatomy (one CTA per SM, persistent over (sequence, 128-frame tile) items, 448 threads):
 //   warp 0        TMA producer: per K slab (16 fp32 = one 64-byte swizzle row) loads A raw, W_hi, W_lo (4-stage ring)
 //   warp 1        allocates TMEM, issues tcgen05.mma kind::tf32 (M128 N256 K8): hi*hi + lo*hi + hi*lo per k-step
 //   warps 2,3,8,9 splitter: rewrite the landed A slab as hi = rna_tf32(x) in place and lo = x - hi in a second buffer
-//   warps 4-7     epilogue: tcgen05.ld the finished accumulator (2 x 256 TMEM columns, double buffered) and store
+//   warps 4-7,10-13 epilogue (2 groups x 4 TMEM lane quadrants): tcgen05.ld the finished accumulator (2 x 256 TMEM
+//                 columns, double buffered), apply gate / residual / skip, store whole sectors
 // mbarriers: full (TMA landed), split (lo ready), empty (MMAs of the stage retired), acc_full / acc_empty.
 #include "common.cuh"
 #include <cuda.h>
@@ -31,10 +32,11 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB
 constexpr int W_BYTES = BN * BK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
-constexpr int NTHREADS = 320;             // 10 warps: TMA, MMA, 2 split, 4 epilogue, 2 more split
+constexpr int NTHREADS = 448;             // 14 warps: TMA, MMA, 4 split (2,3,8,9), 2 x 4 epilogue (4-7 and 10-13)
+constexpr int EPI_THREADS = 256;
 constexpr int SPLIT_THREADS = 128;
 constexpr int CS = 2;                       // CTAs per cluster sharing every weight slab through TMA multicast
-constexpr int TP = 36;                      // pitch of the 32x32 epilogue transpose tile (conflict-free 128-bit access)
+constexpr int TP = 20;                      // pitch of the 32x16 epilogue transpose tile (16-byte aligned rows)
 constexpr unsigned SPIN_LIMIT = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -188,7 +190,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, CS); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -265,7 +267,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 4] = clock64();
                 }
             }
-    } else if (warp < 4 || warp >= 8) {
+    } else if (warp == 2 || warp == 3 || warp == 8 || warp == 9) {
         // ================================================================= splitter (warps 2,3,8,9 = 128 threads)
         const int st_tid = warp < 4 ? tid - 64 : tid - 192;
         unsigned it = 0;
@@ -294,47 +296,44 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (p.dbg && blockIdx.x == 0 && it < 512 && st_tid == 0) p.dbg[it * 8 + 6] = clock64();
                     mbar_arrive(split + st);
                 }
-    } else {
-        // ================================================================= epilogue (warps 4..7 = TMEM lane quadrants 0..3)
-        const int q = warp - 4;
+    } else if ((warp >= 4 && warp < 8) || warp >= 10) {
+        // ================================================================= epilogue: two groups of 4 warps (4-7 and 10-13); warp w may
+        // touch TMEM lanes 32*(w%4)..+31, so each group covers all 128 accumulator rows and takes half of the tile's columns.
+        // A 16-column chunk is read row-per-thread, turned through a 32x16 shared-memory tile and leaves as 64-byte row pieces
+        // (instruction i: lane -> frame 8i + lane/4, 16-byte piece lane%4): whole sectors, 8 rows per warp instruction.
+        const int grp = warp >= 10 ? 1 : 0, q = warp & 3;
+        float* tt = stage_t + (grp * 4 + q) * 32 * TP;
+        const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
         unsigned tile = 0;
         for (int rd = 0; rd < rounds; ++rd) {
             const int item = (cluster_id + rd * n_clusters) * CS + crank;
             const bool ghost = item >= items;
             const int b = ghost ? 0 : item / m_tiles, t0 = ghost ? p.L : p.t_begin + (item % m_tiles) * BM;
+            const int tbase = t0 + q * 32;                                   // first frame of this warp's rows
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                 const unsigned ab = tile & 1, aph = (tile >> 1) & 1;
                 mbar_wait(acc_full + ab, aph);
                 tc_fence_after();
                 const unsigned taddr = tmem_base + ab * BN + ((unsigned)(q * 32) << 16);
-                // Each epilogue warp owns 32 accumulator rows (frames).  A 32-column chunk is read from TMEM row-per-thread,
-                // turned through a 32x32 shared-memory tile, and leaves for global memory as whole 128-byte lines
-                // (instruction i: lane -> frame 4i + lane/8, 16-byte piece lane%8): 4 full lines per warp instruction.
-                float* tt = stage_t + q * 32 * TP;
-                const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-                const int tbase = t0 + q * 32;                                   // first frame of this warp's rows
                 if (EPI == EPI_GATE) {
-                    // tile columns: [0,128) = F of channels 128*nt.., [128,256) = G of the same channels
+                    // tile columns: [0,128) = F of channels 128*nt.., [128,256) = G of the same channels; group g takes 64 channels
                     const float* bt = bias_s + nt * BN;
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 32) {
-                        float f[32], g[32];
-                        tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&f[0]));
-                        tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&f[16]));
-                        tmem_ld16(taddr + 128 + c, *reinterpret_cast<float(*)[16]>(&g[0]));
-                        tmem_ld16(taddr + 128 + c + 16, *reinterpret_cast<float(*)[16]>(&g[16]));
+                    for (int c = grp * 64; c < grp * 64 + 64; c += 16) {
+                        float f[16], g[16];
+                        tmem_ld16(taddr + c, f);
+                        tmem_ld16(taddr + 128 + c, g);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
+                        for (int i = 0; i < 16; ++i) {
                             f[i] = tanhf(f[i] + bt[c + i]);
                             g[i] = sigmoid_tc(g[i] + bt[128 + c + i]);
                         }
-                        // three passes through the tile: z, then (optionally) f and g for the backward
-                        const int n_pass = p.out1 ? 3 : 1;
+                        const int n_pass = p.out1 ? 3 : 1;                   // z, then (optionally) f and g for the backward
                         for (int ps = 0; ps < n_pass; ++ps) {
                             __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
+                            for (int i = 0; i < 16; i += 4) {
                                 float4 v;
                                 if (ps == 0) v = make_float4(f[i] * g[i], f[i + 1] * g[i + 1], f[i + 2] * g[i + 2], f[i + 3] * g[i + 3]);
                                 else if (ps == 1) v = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -343,10 +342,10 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int fr = tbase + 4 * i + sub_r;
+                            for (int i = 0; i < 4; ++i) {
+                                const int fr = tbase + 8 * i + sub_r;
                                 if (fr < p.L) {
-                                    const float4 v = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
+                                    const float4 v = *reinterpret_cast<const float4*>(tt + (8 * i + sub_r) * TP + sub_c);
                                     float* dst = (ps == 0) ? p.out0 + ((size_t)b * p.L + fr) * p.D + nt * 128 + c + sub_c
                                                            : p.out1 + ((size_t)b * p.L + fr) * (2 * p.D) + (ps == 2 ? p.D : 0) + nt * 128 + c + sub_c;
                                     *reinterpret_cast<float4*>(dst) = v;
@@ -355,21 +354,20 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     }
                 } else {
-                    // tile columns: global output column n = nt*256 + c; n < R residual, else skip channel n - R
+                    // tile columns: global output column n = nt*256 + c; n < R residual, else skip channel n - R; group g takes 128
                     const int n0 = nt * BN;
                     const bool is_res = n0 < p.R;
                     const float* bt = bias_s + n0;
                     const int Tsk = p.L - p.skip_start;
 #pragma unroll 1
-                    for (int c = 0; c < BN; c += 32) {
-                        float v[32];
-                        tmem_ld16(taddr + c, *reinterpret_cast<float(*)[16]>(&v[0]));
-                        tmem_ld16(taddr + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                    for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c, v);
                         // the values this lane will add in the coalesced domain (residual h_in(t) or the running skip)
-                        float4 x[8];
+                        float4 x[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int fr = tbase + 4 * i + sub_r;
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
                             x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (fr < p.L) {
                                 if (is_res) {
@@ -383,15 +381,15 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tmem_ld_wait();
                         __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
+                        for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4*>(tt + lane * TP + i) =
                                 make_float4(v[i] + bt[c + i], v[i + 1] + bt[c + i + 1], v[i + 2] + bt[c + i + 2], v[i + 3] + bt[c + i + 3]);
                         __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int fr = tbase + 4 * i + sub_r;
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
                             if (fr >= p.L) continue;
-                            float4 o = *reinterpret_cast<const float4*>(tt + (4 * i + sub_r) * TP + sub_c);
+                            float4 o = *reinterpret_cast<const float4*>(tt + (8 * i + sub_r) * TP + sub_c);
                             o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w;
                             if (is_res)
                                 *reinterpret_cast<float4*>(p.out0 + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c) = o;
@@ -496,7 +494,7 @@ static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
 }
 
 static size_t tc_smem_bytes(int n_total) {
-    return 1024 + (size_t)STAGES * STAGE_BYTES + 512 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 4 * 32 * TP;
+    return 1024 + (size_t)STAGES * STAGE_BYTES + 512 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 8 * 32 * TP;
 }
 
 template <int EPI, bool EXACT>
