@@ -151,6 +151,15 @@ typedef struct wn_block_bwd_args {
 } wn_block_bwd_args;
 int wn_block_bwd_data(const wn_block_bwd_args* a, void* stream);
 
+/* The same two data-gradient GEMMs on the tensor cores (tcgen05, 3xTF32), for R % 256 == 0, S % 256 == 0, D % 256 == 0:
+ * weights packed K-major and pre-split by wn_tc_pack_block_bwd_weights into d_wdz [2][D][R+S] (row c: residual_conv
+ * column c then skip_conv column c) and d_wdh [2][R][k*2D] (row r, column j*2D+n: [filter;gate].weight[n][r][j]).
+ * d_wrs_rows / d_wfg_bwd of the args are ignored. */
+int wn_tc_bwd_supported(int R, int D, int S, int k);
+int wn_tc_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws,
+                                 int R, int D, int S, int k, float* d_wdz, float* d_wdh, void* stream);
+int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_wdz, const float* d_wdh, void* stream);
+
 /* head: given d_dlogits (B*out_len, classes) and the saved skip sum (B, L-skip_start, S) produce
  * d_y1 (B*out_len, E) = relu(W1 relu(skip)+b1) (recomputed), d_dy1 (B*out_len, E) and d_dskip (B, out_len, S).
  * d_w1_t/d_b1: end_conv_1 packed by wn_pack_1x1_weights; d_w2_rows [classes][wn_n2p(E)] = end_conv_2.weight rows;

@@ -137,18 +137,23 @@ __host__ __device__ constexpr unsigned make_idesc() {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-enum { EPI_GATE = 0, EPI_RES_SKIP = 1 };
+enum { EPI_GATE = 0, EPI_RES_SKIP = 1, EPI_GATE_BWD = 2, EPI_ADD = 3 };
 
 struct TcParams {
     int B, L, t_begin;            // frames [t_begin, L) of every sequence are produced
-    int taps, dil, C;             // A row = taps x C channels; tap j reads frame t - (taps-1-j)*dil
+    int taps, dil, C;             // A row = taps x C channels; tap j reads frame t - (taps-1-j)*dil  (dil < 0: future frames)
     int a_origin;                 // frame that coordinate 0 of the A tensor map corresponds to
+    // optional second A source appended along K (backward dz: A row = [dh_out(t) | dskip(t)]): C2 channels read through
+    // mapA2 at frame t - a2_origin; when C2 > 0 and C == 0 the first source is absent (last layer: no dh_out)
+    int C2, a2_origin;
     int n_tiles, n_total;         // output columns = n_tiles * BN; the W map holds hi rows [0,n_total) then lo rows
     // epilogue
     const float* bias;            // [n_total] in tile column order
     float* out0;                  // GATE: z (B,L,D)            RES_SKIP: h_out (B,L,R)
     float* out1;                  // GATE: fg_save (B,L,2D)|0   RES_SKIP: skip (B,L-skip_start,S)
-    const float* res;             // RES_SKIP: h_in (B,L,R)
+    const float* res;             // RES_SKIP: h_in (B,L,R)     GATE_BWD: fg (B,L,2D)      ADD: dh_out (B,L,R) or null
+    float* out2;                  // GATE_BWD: z (B,L,D)
+    int id_start;                 // ADD: frames >= id_start carry `res` straight through
     int D, R, S, in_start, skip_start, skip_init;
     long long* dbg;               // optional trace buffer (WN_TC_TRACE): CTA 0 stamps clock64 per stage, see tools/tc_trace.py
 };
@@ -161,7 +166,8 @@ __device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(
 //                "fast" mode and reported separately.
 template <int EPI, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapW, const TcParams p) {
     // mapW's box is BN/CS rows: every CTA of the cluster fetches its share of a weight slab and multicasts it to all
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -186,7 +192,8 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int rounds = (items + n_clusters * CS - 1) / (n_clusters * CS);
     const unsigned short mc_mask = (unsigned short)((1u << CS) - 1u);
     const int slabs_per_tap = p.C / BK;
-    const int slabs = p.taps * slabs_per_tap;
+    const int slabs1 = p.taps * slabs_per_tap;                  // K slabs of the first A source
+    const int slabs = slabs1 + p.C2 / BK;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, CS); }
@@ -196,7 +203,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
-    for (int i = tid; i < p.n_total; i += NTHREADS) bias_s[i] = p.bias[i];
+    for (int i = tid; i < p.n_total; i += NTHREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     cluster_sync_();                              // peers' barriers are initialised before anything is multicast at them
@@ -219,9 +226,13 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         mbar_wait(empty + st, ph ^ 1);           // every CTA of the cluster is done with this stage
                         if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it * 8 + 1] = clock64();
                         unsigned char* sm = stage_mem + st * STAGE_BYTES;
-                        const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
                         mbar_expect_tx(full + st, A_BYTES + (EXACT ? 2 : 1) * W_BYTES);
-                        tma_load_3d(sm, &mapA, c0, t0 - (p.taps - 1 - j) * p.dil - p.a_origin, b, full + st);
+                        if (sl < slabs1) {
+                            const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
+                            tma_load_3d(sm, &mapA, c0, t0 - (p.taps - 1 - j) * p.dil - p.a_origin, b, full + st);
+                        } else {
+                            tma_load_3d(sm, &mapA2, (sl - slabs1) * BK, t0 - p.a2_origin, b, full + st);
+                        }
                         constexpr int WR = BN / CS, WB = W_BYTES / CS;      // this CTA's rows / bytes of the slab
                         tma_load_2d_mc(sm + 2 * A_BYTES + crank * WB, &mapW, sl * BK, nt * BN + crank * WR, full + st, mc_mask);
                         if (EXACT)
@@ -353,6 +364,75 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                         }
                     }
+                } else if (EPI == EPI_GATE_BWD) {
+                    // dz tile (columns = dilation channels nt*256 + c): dF = dz*g*(1-f^2), dG = dz*f*g*(1-g), z = f*g
+                    const int n0 = nt * BN;
+#pragma unroll 1
+                    for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c, v);
+                        float4 fq[4], gq[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
+                            fq[i] = gq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (fr < p.L) {
+                                const float* fg = p.res + ((size_t)b * p.L + fr) * (2 * p.D) + n0 + c + sub_c;
+                                fq[i] = __ldg(reinterpret_cast<const float4*>(fg));
+                                gq[i] = __ldg(reinterpret_cast<const float4*>(fg + p.D));
+                            }
+                        }
+                        tmem_ld_wait();
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(tt + lane * TP + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
+                            if (fr >= p.L) continue;
+                            const float4 dz = *reinterpret_cast<const float4*>(tt + (8 * i + sub_r) * TP + sub_c);
+                            const float4 f = fq[i], g = gq[i];
+                            float* dfg = p.out0 + ((size_t)b * p.L + fr) * (2 * p.D) + n0 + c + sub_c;
+                            *reinterpret_cast<float4*>(dfg) = make_float4(dz.x * g.x * (1.f - f.x * f.x), dz.y * g.y * (1.f - f.y * f.y),
+                                                                          dz.z * g.z * (1.f - f.z * f.z), dz.w * g.w * (1.f - f.w * f.w));
+                            *reinterpret_cast<float4*>(dfg + p.D) = make_float4(dz.x * f.x * g.x * (1.f - g.x), dz.y * f.y * g.y * (1.f - g.y),
+                                                                                dz.z * f.z * g.z * (1.f - g.z), dz.w * f.w * g.w * (1.f - g.w));
+                            *reinterpret_cast<float4*>(p.out2 + ((size_t)b * p.L + fr) * p.D + n0 + c + sub_c) =
+                                make_float4(f.x * g.x, f.y * g.y, f.z * g.z, f.w * g.w);
+                        }
+                    }
+                } else if (EPI == EPI_ADD) {
+                    // dh_in tile (columns = residual channels nt*256 + c) = acc + dh_out(t) for t >= id_start
+                    const int n0 = nt * BN;
+#pragma unroll 1
+                    for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c, v);
+                        float4 x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
+                            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (fr < p.L && p.res != nullptr && fr >= p.id_start)
+                                x[i] = __ldg(reinterpret_cast<const float4*>(p.res + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c));
+                        }
+                        tmem_ld_wait();
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(tt + lane * TP + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int fr = tbase + 8 * i + sub_r;
+                            if (fr >= p.L) continue;
+                            float4 o = *reinterpret_cast<const float4*>(tt + (8 * i + sub_r) * TP + sub_c);
+                            o.x += x[i].x; o.y += x[i].y; o.z += x[i].z; o.w += x[i].w;
+                            *reinterpret_cast<float4*>(p.out0 + ((size_t)b * p.L + fr) * p.R + n0 + c + sub_c) = o;
+                        }
+                    }
                 } else {
                     // tile columns: global output column n = nt*256 + c; n < R residual, else skip channel n - R; group g takes 128
                     const int n0 = nt * BN;
@@ -449,6 +529,38 @@ __global__ void pack_b_kernel(const float* __restrict__ wr, const float* __restr
     }
 }
 
+// backward dz: rows = dilation channels c, columns k: [0,R) = residual_conv.weight[k][c], [R,R+S) = skip_conv.weight[k-R][c]
+__global__ void pack_dz_kernel(const float* __restrict__ wr, const float* __restrict__ ws, int R, int D, int S,
+                               float* __restrict__ w) {
+    const int K = R + S;
+    const long long total = (long long)D * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / K), kk = (int)(i % K);
+        const float v = kk < R ? wr[(size_t)kk * D + c] : ws[(size_t)(kk - R) * D + c];
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float hi = __uint_as_float(u);
+        w[i] = hi;
+        w[total + i] = v - hi;
+    }
+}
+// backward dh_in: rows = residual channels r, columns j*2D + n: [filter;gate].weight[n][r][j]
+__global__ void pack_dh_kernel(const float* __restrict__ wf, const float* __restrict__ wg, int R, int D, int k,
+                               float* __restrict__ w) {
+    const int K = k * 2 * D;
+    const long long total = (long long)R * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / K), kk = (int)(i % K);
+        const int j = kk / (2 * D), n = kk % (2 * D);
+        const float v = n < D ? wf[((size_t)n * R + r) * k + j] : wg[((size_t)(n - D) * R + r) * k + j];
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float hi = __uint_as_float(u);
+        w[i] = hi;
+        w[total + i] = v - hi;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -467,6 +579,7 @@ static EncodeTiledFn encode_fn() {
 static int make_act_map(CUtensorMap* m, const float* base, int B, int L, int C, int origin) {
     EncodeTiledFn fn = encode_fn();
     WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    WN_REQUIRE(L - origin >= 1, WN_E_BADARG, "empty activation range");
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)(L - origin), (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)L * C * 4};
     cuuint32_t box[3] = {BK, BM, 1};
@@ -498,7 +611,7 @@ static size_t tc_smem_bytes(int n_total) {
 }
 
 template <int EPI, bool EXACT>
-static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const TcParams& p, cudaStream_t st) {
     int dev = 0, sms = 0;
     WN_CUDA(cudaGetDevice(&dev));
     WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -520,7 +633,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mW, const TcParam
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, frames_gemm_tc<EPI, EXACT>, mA, mW, p));
+    WN_CUDA(cudaLaunchKernelEx(&cfg, frames_gemm_tc<EPI, EXACT>, mA, mA2, mW, p));
     WN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -581,11 +694,65 @@ extern "C" int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream) {
     p.n_total = 2 * a->D; p.n_tiles = p.n_total / tc::BN;
     p.bias = a->d_ba; p.out0 = a->d_z; p.out1 = a->d_fg_save; p.res = nullptr;
     const bool exact = (a->fast_tf32 == 0);
-    if (int rc = exact ? tc::launch_tc<tc::EPI_GATE, true>(mA, mWa, p, st) : tc::launch_tc<tc::EPI_GATE, false>(mA, mWa, p, st))
+    if (int rc = exact ? tc::launch_tc<tc::EPI_GATE, true>(mA, mA, mWa, p, st) : tc::launch_tc<tc::EPI_GATE, false>(mA, mA, mWa, p, st))
         return rc;
     // pass B: residual + skip 1x1
     p.taps = 1; p.dil = 0; p.C = a->D; p.a_origin = a->out_start;
     p.n_total = a->R + a->S; p.n_tiles = p.n_total / tc::BN;
     p.bias = a->d_bb; p.out0 = a->d_h_out; p.out1 = a->d_skip; p.res = a->d_h_in;
-    return exact ? tc::launch_tc<tc::EPI_RES_SKIP, true>(mZ, mWb, p, st) : tc::launch_tc<tc::EPI_RES_SKIP, false>(mZ, mWb, p, st);
+    return exact ? tc::launch_tc<tc::EPI_RES_SKIP, true>(mZ, mZ, mWb, p, st) : tc::launch_tc<tc::EPI_RES_SKIP, false>(mZ, mZ, mWb, p, st);
+}
+
+extern "C" int wn_tc_bwd_supported(int R, int D, int S, int k) {
+    return (R % 256 == 0) && (S % 256 == 0) && (D % 256 == 0) && k >= 1 && (R + S) <= 2048 && k * 2 * D <= 4096;
+}
+
+extern "C" int wn_tc_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws, int R,
+                                            int D, int S, int k, float* d_wdz, float* d_wdh, void* stream) {
+    WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_wdz && d_wdh, WN_E_BADARG, "wn_tc_pack_block_bwd_weights: null pointer");
+    WN_REQUIRE(wn_tc_bwd_supported(R, D, S, k), WN_E_UNSUPP, "wn_tc_pack_block_bwd_weights: shape not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::pack_dz_kernel<<<512, 256, 0, st>>>(d_wr, d_ws, R, D, S, d_wdz);
+    tc::pack_dh_kernel<<<1024, 256, 0, st>>>(d_wf, d_wg, R, D, k, d_wdh);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Tensor-core form of wn_block_bwd_data (same arguments; d_wrs_rows / d_wfg_bwd are replaced by the packed, pre-split
+// d_wdz [2][D][R+S] and d_wdh [2][R][k*2D] of wn_tc_pack_block_bwd_weights).
+extern "C" int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_wdz, const float* d_wdh, void* stream) {
+    WN_REQUIRE(a && d_wdz && d_wdh, WN_E_BADARG, "wn_tc_block_bwd_data: null args");
+    WN_REQUIRE(a->d_dskip && a->d_fg && a->d_dfg && a->d_z && a->d_dh_in, WN_E_BADARG, "wn_tc_block_bwd_data: null pointer");
+    WN_REQUIRE(wn_tc_bwd_supported(a->R, a->D, a->S, a->k), WN_E_UNSUPP, "wn_tc_block_bwd_data: shape not supported");
+    WN_REQUIRE(a->gz >= a->out_start && a->gz < a->L && a->gs_in >= a->in_start && a->gs_in <= a->gz && a->ds_start >= a->out_start &&
+                   a->ds_start < a->L,
+               WN_E_BADARG, "wn_tc_block_bwd_data: bad gradient frame ranges");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = a->R, D = a->D, S = a->S, L = a->L, B = a->B;
+    const bool have_dh = a->d_dh_out != nullptr && a->gs_out < L;
+    CUtensorMap mDh, mDs, mW1, mDfg, mW2;
+    if (int rc = tc::make_act_map(&mDs, a->d_dskip, B, L - a->ds_start, S, 0)) return rc;          // (B, L-ds_start, S): own frame axis
+    if (have_dh) { if (int rc = tc::make_act_map(&mDh, a->d_dh_out, B, L, R, a->gs_out)) return rc; }
+    else mDh = mDs;
+    if (int rc = tc::make_w_map(&mW1, d_wdz + (have_dh ? 0 : R), 2 * D, R + S)) return rc;       // without dh_out: start at column R
+    tc::TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.D = D; p.R = R; p.S = S;
+    // ---- dz + gate backward for frames [gz, L)
+    p.t_begin = a->gz;
+    p.taps = have_dh ? 1 : 0; p.dil = 0; p.C = have_dh ? R : 0; p.a_origin = a->gs_out;
+    p.C2 = S; p.a2_origin = a->ds_start;
+    p.n_total = D; p.n_tiles = D / tc::BN;
+    p.bias = nullptr; p.out0 = a->d_dfg; p.out2 = a->d_z; p.res = a->d_fg;
+    if (int rc = tc::launch_tc<tc::EPI_GATE_BWD, true>(mDh, mDs, mW1, p, st)) return rc;
+    // ---- dh_in = dh_out (identity) + anti-causal taps of dfg, for frames [gs_in, L)
+    if (int rc = tc::make_act_map(&mDfg, a->d_dfg, B, L, 2 * D, a->gz)) return rc;
+    if (int rc = tc::make_w_map(&mW2, d_wdh, 2 * R, a->k * 2 * D)) return rc;
+    p.t_begin = a->gs_in;
+    p.taps = a->k; p.dil = -a->dilation; p.C = 2 * D; p.a_origin = a->gz;
+    p.C2 = 0; p.a2_origin = 0;
+    p.n_total = R; p.n_tiles = R / tc::BN;
+    p.out0 = a->d_dh_in; p.out2 = nullptr; p.res = a->d_dh_out;
+    p.id_start = a->gs_out > a->out_start ? a->gs_out : a->out_start;
+    return tc::launch_tc<tc::EPI_ADD, true>(mDfg, mDfg, mW2, p, st);
 }

@@ -112,6 +112,12 @@ class _Runtime:
                     native.ptr(br), native.ptr(bs), R, D, S, k, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
                     bb.data_ptr(), stream), "pack tc")
                 out.setdefault("tc_layers", []).append((wa, ba, wb, bb))
+            if lib.wn_tc_bwd_supported(R, D, S, k):
+                wdz = torch.empty(2, D, R + S, **f32)
+                wdh = torch.empty(2, R, k * 2 * D, **f32)
+                native.check(lib.wn_tc_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
+                                                              R, D, S, k, wdz.data_ptr(), wdh.data_ptr(), stream), "pack tc bwd")
+                out.setdefault("tc_bwd_layers", []).append((wdz, wdh))
 
         def pack1x1(w, b, N, K):
             wt = torch.empty(K, lib.wn_n2p(N), **f32)
@@ -278,6 +284,8 @@ class _Runtime:
         zbuf = torch.empty(B, L, D, **f32)
         dh_a, dh_b = torch.empty(B, L, R, **f32), torch.empty(B, L, R, **f32)
         dh_out, gs_out = None, L
+        use_tc_bwd = self.block_mode != "ffma" and bool(lib.wn_tc_bwd_supported(R, D, S, k))
+        self.last_bwd_mode = "tc" if use_tc_bwd else "ffma"
         a = native.BlockBwdArgs()
         a.B, a.L, a.R, a.D, a.S, a.k, a.ds_start = B, L, R, D, S, k, ds_start
         a.d_dskip, a.d_dfg, a.d_z = dskip.data_ptr(), dfg.data_ptr(), zbuf.data_ptr()
@@ -289,16 +297,20 @@ class _Runtime:
             gz = max(out_s, min(gs_out, ds_start))
             id_start = max(out_s, gs_out)
             gs_in = max(in_s, min(id_start, gz - (k - 1) * d))
-            wrs_rows = pad_cols(torch.cat([wr.detach()[:, :, 0], wsk.detach()[:, :, 0]], 0), lib.wn_n2p(D))
-            wfg_bwd = pad_cols(torch.cat([wf.detach(), wg.detach()], 0).permute(2, 0, 1).reshape(k * 2 * D, R),
-                               lib.wn_n2p(R))
             dh_in = dh_a if dh_out is not dh_a else dh_b
             a.d_dh_out = None if dh_out is None else dh_out.data_ptr()
             a.d_fg, a.d_dh_in = fg_all[i].data_ptr(), dh_in.data_ptr()
-            a.d_wrs_rows, a.d_wfg_bwd = wrs_rows.data_ptr(), wfg_bwd.data_ptr()
             a.dilation, a.in_start, a.out_start = d, in_s, out_s
             a.gs_out, a.gz, a.gs_in = gs_out, gz, gs_in
-            native.check(lib.wn_block_bwd_data(ctypes.byref(a), stream), f"block bwd {i}")
+            if use_tc_bwd:
+                wdz, wdh = W["tc_bwd_layers"][i]
+                native.check(lib.wn_tc_block_bwd_data(ctypes.byref(a), wdz.data_ptr(), wdh.data_ptr(), stream), f"tc block bwd {i}")
+            else:
+                wrs_rows = pad_cols(torch.cat([wr.detach()[:, :, 0], wsk.detach()[:, :, 0]], 0), lib.wn_n2p(D))
+                wfg_bwd = pad_cols(torch.cat([wf.detach(), wg.detach()], 0).permute(2, 0, 1).reshape(k * 2 * D, R),
+                                   lib.wn_n2p(R))
+                a.d_wrs_rows, a.d_wfg_bwd = wrs_rows.data_ptr(), wfg_bwd.data_ptr()
+                native.check(lib.wn_block_bwd_data(ctypes.byref(a), stream), f"block bwd {i}")
             # weight gradients: plain GEMMs over (frames x channels) slices
             zs = zbuf[:, ds_start:, :]
             grads[f"skip_convs.{i}.weight"] = torch.einsum("bts,btc->sc", dskip, zs).unsqueeze(-1)

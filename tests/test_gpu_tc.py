@@ -90,3 +90,34 @@ def test_fast_tf32_mode_is_opt_in_and_close():
     assert np.array_equal(exact, again)
     err = rel_err(fast, exact)
     assert 1e-6 < err < 2e-2, err
+
+
+def test_tc_backward_matches_simt_backward_and_oracle():
+    """256-channel net: tensor-core data gradients vs the fp32 SIMT kernels and vs autograd over the CPU oracle."""
+    import torch.nn.functional as F
+    import wavenet_model as wmod
+    kw = dict(layers=3, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=150, kernel_size=2, bias=True)
+    torch.manual_seed(11)
+    m = wmod.WaveNetModel(**kw)
+    spec = O.NetSpec(**kw)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    idx = torch.randint(0, 256, (2, 420), generator=torch.Generator().manual_seed(2))
+    tgt = torch.randint(0, 256, (2 * 150,), generator=torch.Generator().manual_seed(3))
+    F.cross_entropy(O.forward(p, spec, O.one_hot(idx, 256)), tgt).backward()
+    m = m.cuda()
+    rt = m._runtime()
+    grads = {}
+    for mode in ("tc", "ffma"):
+        rt.block_mode = mode
+        m.zero_grad()
+        F.cross_entropy(m.forward_indices(idx.cuda()), tgt.cuda()).backward()
+        assert rt.last_bwd_mode == mode
+        grads[mode] = {k: v.grad.detach().cpu().numpy().copy() for k, v in m.named_parameters()}
+    rt.block_mode = "auto"
+    for k, v in p.items():
+        want = np.zeros_like(grads["tc"][k]) if v.grad is None else v.grad.numpy()
+        scale = max(np.abs(want).max(), 1e-30)
+        assert np.abs(grads["ffma"][k] - want).max() / scale < 1e-4 or np.abs(want).max() == 0, k
+        assert np.abs(grads["tc"][k] - want).max() / scale < 1e-4 or np.abs(want).max() == 0, k
+        assert np.abs(grads["tc"][k] - grads["ffma"][k]).max() <= 2e-5 * max(np.abs(grads["ffma"][k]).max(), 1e-30) or np.abs(want).max() == 0, k
