@@ -234,9 +234,10 @@ def valid_lengths(spec: NetSpec, L: int) -> List[int]:
     return out
 
 
-def stack_direct(p: Dict[str, Tensor], spec: NetSpec, x: Tensor) -> Tensor:
+def stack_direct(p: Dict[str, Tensor], spec: NetSpec, x: Tensor, taps: Optional[dict] = None) -> Tensor:
     """Same mathematics as ``stack_folded`` without the fold: everything is right-aligned to the sequence
-    end, history left of a layer's valid start reads as zero."""
+    end, history left of a layer's valid start reads as zero.  ``taps`` (a dict) receives the inputs of the two
+    head ReLUs ("skip", "pre1"); the backward tests use them to find ReLU near-ties."""
     k = spec.kernel_size
     h = F.conv1d(x, p["start_conv.weight"], _b(p, "start_conv"))
     skip = None
@@ -251,7 +252,10 @@ def stack_direct(p: Dict[str, Tensor], spec: NetSpec, x: Tensor) -> Tensor:
         skip = s if skip is None else s + skip[:, :, -s.size(2):]
         h = F.conv1d(z, p[f"residual_convs.{i}.weight"], _b(p, f"residual_convs.{i}")) + hp[:, :, d * (k - 1):]
     y = F.relu(skip)
-    y = F.relu(F.conv1d(y, p["end_conv_1.weight"], p["end_conv_1.bias"]))
+    pre1 = F.conv1d(y, p["end_conv_1.weight"], p["end_conv_1.bias"])
+    if taps is not None:
+        taps["skip"], taps["pre1"] = skip, pre1
+    y = F.relu(pre1)
     return F.conv1d(y, p["end_conv_2.weight"], p["end_conv_2.bias"])
 
 

@@ -284,7 +284,8 @@ class _Runtime:
         zbuf = torch.empty(B, L, D, **f32)
         dh_a, dh_b = torch.empty(B, L, R, **f32), torch.empty(B, L, R, **f32)
         dh_out, gs_out = None, L
-        use_tc_bwd = self.block_mode != "ffma" and bool(lib.wn_tc_bwd_supported(R, D, S, k))
+        bwd_mode = getattr(self, "bwd_mode", None) or self.block_mode      # "tc" / "ffma" / "auto"; defaults to block_mode
+        use_tc_bwd = bwd_mode != "ffma" and bool(lib.wn_tc_bwd_supported(R, D, S, k))
         self.last_bwd_mode = "tc" if use_tc_bwd else "ffma"
         a = native.BlockBwdArgs()
         a.B, a.L, a.R, a.D, a.S, a.k, a.ds_start = B, L, R, D, S, k, ds_start
