@@ -191,6 +191,7 @@ def bench_generate(args, world, rank):
            "h2d_bytes_per_step": int(rt.h2d_bytes_last), "d2h_bytes_per_step": int(rt.d2h_bytes_last),
            "api": "WaveNetModel.generate_fast(16000, temperature=1.0) -> float64 ndarray"}
 
+    import ctypes, native
     # argmax path, for reference
     t_arg = []
     for _ in range(2):
@@ -201,7 +202,32 @@ def bench_generate(args, world, rank):
         torch.cuda.synchronize()
         t_arg.append(e0.elapsed_time(e1))
 
-    import ctypes, native
+    # cfg4: 64 independent streams batched on one GPU (aggregate samples/s); shorter run, same per-sample cost
+    batched = None
+    if not args.no_batched:
+        NB, nb = 64, 1000
+        sb = rt.sampler(NB)
+        first_b = torch.full((NB, 1), 128, dtype=torch.int32, device=dev)
+        uni_b = torch.from_numpy(np.random.random_sample((NB, nb))).to(dev)
+        out_b = torch.zeros(NB, nb, dtype=torch.int32, device=dev)
+        rt.generate_resident(sb, first_b, 1, 64, TEMPERATURE, 0.0, out_b[:, :64].contiguous(), d_uni=uni_b[:, :64].contiguous())
+        tb = []
+        for _ in range(2):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rt.generate_resident(sb, first_b, 1, nb, TEMPERATURE, 0.0, out_b, d_uni=uni_b)
+            e1.record()
+            torch.cuda.synchronize()
+            tb.append(e0.elapsed_time(e1))
+        tbm = max_over_ranks(min(tb), world)
+        gb_, bb_, _bars = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        native.lib().wn_gen_launch_info(sb["handle"], ctypes.byref(gb_), ctypes.byref(bb_), ctypes.byref(_bars))
+        batched = {"workload": "cfg4: 64 independent streams, same net, 1000 samples per stream, temperature=1.0",
+                   "value": world * NB * nb / (tbm / 1e3), "unit": "samples/s (aggregate over streams)",
+                   "per_stream_samples_per_s": nb / (tbm / 1e3), "ms_per_launch": tbm, "grid": gb_.value, "block": bb_.value,
+                   "distinct_streams": int(len({tuple(r) for r in out_b[:, :32].cpu().numpy().tolist()}))}
+
     g, b, bars = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     native.lib().wn_gen_launch_info(s["handle"], ctypes.byref(g), ctypes.byref(b), ctypes.byref(bars))
     weight_bytes = 4 * sum(p.numel() for p in model.parameters())
@@ -220,7 +246,7 @@ def bench_generate(args, world, rank):
             "us_per_sample": per_launch_ms * 1e3 / n, "exchange_stages_per_sample": bars.value,
             "us_per_exchange_stage": per_launch_ms * 1e3 / n / bars.value, "grid": g.value, "block": b.value}
     return dict(value=value, ms_per_step=ms / args.steps, clocks=clk, e2e=e2e, roofline=roof,
-                argmax_samples_per_s=n / (min(t_arg) / 1e3), wall_s=t_wall, launches=args.steps)
+                argmax_samples_per_s=n / (min(t_arg) / 1e3), wall_s=t_wall, launches=args.steps, batched=batched)
 
 
 # ------------------------------------------------------------------------------------------------ training forward
@@ -345,11 +371,14 @@ def bench_train(args, world, rank):
         if i > 0:
             step_ms.append(e0.elapsed_time(e1))
     step_t = max_over_ranks(sum(step_ms) / len(step_ms), world)
-    train_step = {"ms_per_step": step_t, "frames_per_s": world * B * L / (step_t / 1e3), "loss": float(loss),
+    train_step = {"ms_per_step": step_t, "frames_per_s": world * B * L / (step_t / 1e3), "loss": float(loss.detach()),
                   "grad_allreduce_bytes_per_step": red.bytes_reduced // max(1, 1 + len(step_ms)) if world > 1 else 0,
                   "grad_buckets_per_step": red.buckets // max(1, 1 + len(step_ms)) if world > 1 else 0,
-                  "note": "forward (tensor-core blocks, activations saved) + backward data kernels (fp32 SIMT) + weight-gradient "
-                          "GEMMs (cuBLAS fp32) + NCCL all-reduce per block overlapped with the backward"}
+                  "forward_blocks": getattr(rt, "last_block_mode", "ffma"), "backward_data": getattr(rt, "last_bwd_mode", "ffma"),
+                  "weight_gradients": "cuBLAS fp32 einsum" if getattr(rt, "wgrad_mode", "native") == "cublas" else
+                                      "wn_wgrad (split-frames fp32 SIMT kernel)",
+                  "note": "forward with activations saved + backward data kernels + weight-gradient kernels + NCCL all-reduce "
+                          "per block overlapped with the backward (the optimizer step is not part of this figure)"}
     model._runtime().grad_reducer = None
     del loss
     model.zero_grad(set_to_none=True)
@@ -466,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "generate", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the 64-stream (cfg4) generation figure")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -509,6 +539,8 @@ def main():
             line["cpu_baseline"] = cpu
         if gen is not None:
             line["argmax_samples_per_s"] = gen["argmax_samples_per_s"]
+            if gen.get("batched") is not None:
+                line["batched_64_streams"] = gen["batched"]
             if train is not None:
                 line["train"] = train
         else:

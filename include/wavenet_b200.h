@@ -172,6 +172,21 @@ typedef struct wn_head_bwd_args {
 } wn_head_bwd_args;
 int wn_head_bwd_data(const wn_head_bwd_args* a, void* stream);
 
+/* weight gradient of one convolution tap -- what autograd's conv1d backward-weight computes for filter/gate
+ * (wavenet_model.py:145-151), residual/skip (:156,:164) and the head convolutions (:167-169):
+ *     dw[n*dw_n_stride + c*dw_c_stride] = sum_{b<B} sum_{t<rows} g[b*g_seq_stride + t*ldg + n] * x[b*x_seq_stride + t*ldx + c]
+ * for n < N, c < C (overwrites, exact fp32, deterministic).  d_g / d_x point at the first paired frame of sequence 0
+ * (a tap shift is a pointer offset); strides are in floats, so the result can be written straight into column j of
+ * an (out, in, k) weight-gradient tensor (dw_n_stride = in*k, dw_c_stride = k).  d_work: wn_wgrad_workspace_bytes(N, C)
+ * bytes of scratch for the split-frames partial sums.  rows == 0 writes zeros. */
+typedef struct wn_wgrad_args {
+    const float* d_g; const float* d_x; float* d_dw; float* d_work;
+    long long g_seq_stride, x_seq_stride, dw_n_stride, dw_c_stride;
+    int ldg, ldx, B, rows, N, C;
+} wn_wgrad_args;
+size_t wn_wgrad_workspace_bytes(int N, int C);
+int wn_wgrad(const wn_wgrad_args* a, void* stream);
+
 /* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
  * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with
  * DilatedQueue.enqueue/dequeue/reset (wavenet_modules.py:55-77): ONE persistent cooperative kernel runs

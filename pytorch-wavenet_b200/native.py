@@ -41,6 +41,13 @@ class HeadBwdArgs(C.Structure):
                 ("skip_start", C.c_int), ("out_len", C.c_int)]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("d_g", C.c_void_p), ("d_x", C.c_void_p), ("d_dw", C.c_void_p), ("d_work", C.c_void_p),
+                ("g_seq_stride", C.c_longlong), ("x_seq_stride", C.c_longlong),
+                ("dw_n_stride", C.c_longlong), ("dw_c_stride", C.c_longlong),
+                ("ldg", C.c_int), ("ldx", C.c_int), ("B", C.c_int), ("rows", C.c_int), ("N", C.c_int), ("C", C.c_int)]
+
+
 class TcBlockArgs(C.Structure):
     _fields_ = [("d_h_in", C.c_void_p), ("d_h_out", C.c_void_p), ("d_skip", C.c_void_p), ("d_z", C.c_void_p),
                 ("d_wa", C.c_void_p), ("d_ba", C.c_void_p), ("d_wb", C.c_void_p), ("d_bb", C.c_void_p),
@@ -97,6 +104,8 @@ SIGNATURES = {
     "wn_tc_read_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "wn_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p]),
     "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
+    "wn_wgrad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "wn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "wn_tc_bwd_supported": (C.c_int, [C.c_int] * 4),
     "wn_tc_pack_block_bwd_weights": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     "wn_tc_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p, C.c_void_p, C.c_void_p]),

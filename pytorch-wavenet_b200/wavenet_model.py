@@ -271,9 +271,32 @@ class _Runtime:
         native.check(lib.wn_head_bwd_data(ctypes.byref(hb), stream), "head bwd")
         ds_start = L - OL
         rskip = torch.relu(skip[:, ds_start - plan.skip_start:, :])
-        grads["end_conv_2.weight"] = torch.einsum("btc,bte->ce", dlogits, y1).unsqueeze(-1)
+        # weight gradients: wn_wgrad (split-frames fp32 kernel, wgrad.cu) or, with wgrad_mode="cublas", torch einsums
+        native_wgrad = getattr(self, "wgrad_mode", "native") != "cublas"
+        if native_wgrad:
+            wg_work = torch.empty(max(lib.wn_wgrad_workspace_bytes(n_, c_) for n_, c_ in
+                                      ((Cc, E), (E, S), (S, D), (R, D), (2 * D, R))) // 4, **f32)
+            wa = native.WgradArgs()
+            wa.d_work, wa.B = wg_work.data_ptr(), B
+
+            def wgrad(out, g, g_off, ldg, g_seq, x, x_off, ldx, x_seq, rows, N, C, n_stride=None, c_stride=1, out_off=0):
+                """out[n, c] (+ strides) = sum_b sum_t g[b, t, n] * x[b, t, c]; offsets in floats from the tensors' bases"""
+                wa.d_g, wa.d_x = g.data_ptr() + 4 * g_off, x.data_ptr() + 4 * x_off
+                wa.d_dw = out.data_ptr() + 4 * out_off
+                wa.ldg, wa.ldx, wa.g_seq_stride, wa.x_seq_stride = ldg, ldx, g_seq, x_seq
+                wa.rows, wa.N, wa.C = rows, N, C
+                wa.dw_n_stride, wa.dw_c_stride = (C * c_stride if n_stride is None else n_stride), c_stride
+                native.check(lib.wn_wgrad(ctypes.byref(wa), stream), "wgrad")
+
+            rskip = rskip.contiguous()
+            gw2, gw1 = torch.empty(Cc, E, 1, **f32), torch.empty(E, S, 1, **f32)
+            wgrad(gw2, dlogits, 0, Cc, OL * Cc, y1, 0, E, OL * E, OL, Cc, E)
+            wgrad(gw1, dy1, 0, E, OL * E, rskip, 0, S, OL * S, OL, E, S)
+            grads["end_conv_2.weight"], grads["end_conv_1.weight"] = gw2, gw1
+        else:
+            grads["end_conv_2.weight"] = torch.einsum("btc,bte->ce", dlogits, y1).unsqueeze(-1)
+            grads["end_conv_1.weight"] = torch.einsum("bte,bts->es", dy1, rskip).unsqueeze(-1)
         grads["end_conv_2.bias"] = dlogits.sum((0, 1))
-        grads["end_conv_1.weight"] = torch.einsum("bte,bts->es", dy1, rskip).unsqueeze(-1)
         grads["end_conv_1.bias"] = dy1.sum((0, 1))
         reducer = getattr(self, "grad_reducer", None)      # data_parallel.GradientAverager or None
         if reducer is not None:
@@ -313,29 +336,46 @@ class _Runtime:
                 a.d_wrs_rows, a.d_wfg_bwd = wrs_rows.data_ptr(), wfg_bwd.data_ptr()
                 native.check(lib.wn_block_bwd_data(ctypes.byref(a), stream), f"block bwd {i}")
             # weight gradients: plain GEMMs over (frames x channels) slices
-            zs = zbuf[:, ds_start:, :]
-            grads[f"skip_convs.{i}.weight"] = torch.einsum("bts,btc->sc", dskip, zs).unsqueeze(-1)
+            h_in = h_all[i]
+            if native_wgrad:
+                gws = torch.empty(S, D, 1, **f32)
+                wgrad(gws, dskip, 0, S, OL * S, zbuf, ds_start * D, D, L * D, OL, S, D)
+                grads[f"skip_convs.{i}.weight"] = gws
+                if dh_out is not None and id_start < L:
+                    gwr = torch.empty(R, D, 1, **f32)
+                    wgrad(gwr, dh_out, id_start * R, R, L * R, zbuf, id_start * D, D, L * D, L - id_start, R, D)
+                    grads[f"residual_convs.{i}.weight"] = gwr
+                else:
+                    grads[f"residual_convs.{i}.weight"] = torch.zeros_like(wr)
+                gfg = torch.empty(2 * D, R, k, **f32)          # filter rows then gate rows, like the packed dfg columns
+                for j in range(k):
+                    sh = (k - 1 - j) * d
+                    lo = min(L, max(gz, in_s + sh))           # frames whose tap j lands on real (non-padded) input
+                    wgrad(gfg, dfg, lo * 2 * D, 2 * D, L * 2 * D, h_in, (lo - sh) * R, R, L * R, L - lo, 2 * D, R,
+                          n_stride=R * k, c_stride=k, out_off=j)
+                gwf, gwg = gfg[:D], gfg[D:]
+            else:
+                zs = zbuf[:, ds_start:, :]
+                grads[f"skip_convs.{i}.weight"] = torch.einsum("bts,btc->sc", dskip, zs).unsqueeze(-1)
+                if dh_out is not None and id_start < L:
+                    grads[f"residual_convs.{i}.weight"] = torch.einsum("btr,btc->rc", dh_out[:, id_start:, :],
+                                                                       zbuf[:, id_start:, :]).unsqueeze(-1)
+                else:
+                    grads[f"residual_convs.{i}.weight"] = torch.zeros_like(wr)
+                gwf, gwg = torch.empty_like(wf), torch.empty_like(wg)
+                for j in range(k):
+                    sh = (k - 1 - j) * d
+                    lo = max(gz, in_s + sh)
+                    if lo < L:
+                        g2 = torch.einsum("btn,btr->nr", dfg[:, lo:, :], h_in[:, lo - sh:L - sh, :])
+                    else:
+                        g2 = torch.zeros(2 * D, R, **f32)
+                    gwf[:, :, j], gwg[:, :, j] = g2[:D], g2[D:]
             if bs is not None:
                 grads[f"skip_convs.{i}.bias"] = dskip.sum((0, 1))
-            if dh_out is not None and id_start < L:
-                grads[f"residual_convs.{i}.weight"] = torch.einsum("btr,btc->rc", dh_out[:, id_start:, :],
-                                                                   zbuf[:, id_start:, :]).unsqueeze(-1)
-                if br is not None:
-                    grads[f"residual_convs.{i}.bias"] = dh_out[:, id_start:, :].sum((0, 1))
-            else:
-                grads[f"residual_convs.{i}.weight"] = torch.zeros_like(wr)
-                if br is not None:
-                    grads[f"residual_convs.{i}.bias"] = torch.zeros_like(br)
-            gwf, gwg = torch.empty_like(wf), torch.empty_like(wg)
-            h_in = h_all[i]
-            for j in range(k):
-                sh = (k - 1 - j) * d
-                lo = max(gz, in_s + sh)                       # frames whose tap j lands on real (non-padded) input
-                if lo < L:
-                    g2 = torch.einsum("btn,btr->nr", dfg[:, lo:, :], h_in[:, lo - sh:L - sh, :])
-                else:
-                    g2 = torch.zeros(2 * D, R, **f32)
-                gwf[:, :, j], gwg[:, :, j] = g2[:D], g2[D:]
+            if br is not None:
+                grads[f"residual_convs.{i}.bias"] = (dh_out[:, id_start:, :].sum((0, 1)) if dh_out is not None and id_start < L
+                                                     else torch.zeros_like(br))
             grads[f"filter_convs.{i}.weight"], grads[f"gate_convs.{i}.weight"] = gwf, gwg
             if bf is not None:
                 bsum = dfg[:, gz:, :].sum((0, 1))

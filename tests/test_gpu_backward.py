@@ -16,7 +16,7 @@ def oracle_grads(p, spec, x, target):
     p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     loss = F.cross_entropy(O.forward(p, spec, x), target)
     loss.backward()
-    return float(loss), {k: v.grad for k, v in p.items()}
+    return float(loss.detach()), {k: v.grad for k, v in p.items()}
 
 
 @pytest.mark.parametrize("name,out_len", [("odd_bias", 5), ("odd_bias", 40), ("k3", 4), ("deep", 100), ("deep", 3)])
@@ -92,3 +92,63 @@ def test_backward_full_size_smoke():
         assert bool(torch.isfinite(both[k]).all())
         assert rel_err((g0[k] + g1[k]).cpu().numpy(), both[k].cpu().numpy()) < 1e-4, k
     assert float(both["filter_convs.0.weight"].abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,rows,N,C,ldg,ldx,k,j", [
+    (3, 37, 17, 5, 19, 7, 1, 0),            # ragged channel counts and pitches: scalar loads, partial tiles
+    (2, 3001, 512, 256, 512, 256, 2, 1),    # the 256-channel filter+gate shape, strided scatter into (out, in, k)
+    (2, 100, 130, 132, 136, 140, 3, 2),     # tiles that straddle 128 in both directions
+    (1, 9, 8, 8, 8, 8, 1, 0),               # fewer frames than one slab
+    (4, 0, 16, 12, 16, 12, 2, 0),           # no frames: zeros
+])
+def test_wn_wgrad_matches_float64_contraction(B, rows, N, C, ldg, ldx, k, j):
+    """wn_wgrad through the C ABI: dw[n, c, j] = sum_b sum_t g[b, t, n] * x[b, t, c] with pitched, offset operands."""
+    import ctypes, native
+    lib = native.lib()
+    gen = torch.Generator().manual_seed(5)
+    g_off, x_off = 4, 8                                      # floats; keeps 16-byte alignment for the vector path
+    gbuf = torch.randn(g_off + B * (rows + 2) * ldg, generator=gen).cuda()
+    xbuf = torch.randn(x_off + B * (rows + 3) * ldx, generator=gen).cuda()
+    g_seq, x_seq = (rows + 2) * ldg, (rows + 3) * ldx
+    gv = gbuf[g_off:g_off + B * g_seq].view(B, rows + 2, ldg)[:, :rows, :N].double()
+    xv = xbuf[x_off:x_off + B * x_seq].view(B, rows + 3, ldx)[:, :rows, :C].double()
+    want = torch.einsum("btn,btc->nc", gv, xv).cpu().numpy()
+    out = torch.full((N, C, k), 7.0, device="cuda")
+    work = torch.empty(lib.wn_wgrad_workspace_bytes(N, C) // 4, device="cuda")
+    a = native.WgradArgs()
+    a.d_g, a.d_x = gbuf.data_ptr() + 4 * g_off, xbuf.data_ptr() + 4 * x_off
+    a.d_dw, a.d_work = out.data_ptr() + 4 * j, work.data_ptr()
+    a.g_seq_stride, a.x_seq_stride, a.dw_n_stride, a.dw_c_stride = g_seq, x_seq, C * k, k
+    a.ldg, a.ldx, a.B, a.rows, a.N, a.C = ldg, ldx, B, rows, N, C
+    native.check(lib.wn_wgrad(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), "wgrad")
+    got = out.cpu().numpy()
+    if rows == 0:
+        assert np.abs(got[:, :, j]).max() == 0.0
+    else:
+        assert rel_err(got[:, :, j], want) < 1e-5
+    for jj in range(k):                                      # the other taps' columns are untouched
+        if jj != j:
+            assert (got[:, :, jj] == 7.0).all()
+    # bad arguments are reported, not launched
+    a.ldg = N - 1
+    assert lib.wn_wgrad(ctypes.byref(a), None) < 0
+
+
+def test_wgrad_modes_agree(golden):
+    """The library-GEMM weight-gradient path (wgrad_mode="cublas") and wn_wgrad give the same parameter gradients."""
+    g = golden("net_deep.npz")
+    idx = torch.from_numpy(g["idx"]).cuda()
+    m = build_model(g, output_length=50)
+    target = torch.randint(0, 256, (idx.shape[0] * 50,), generator=torch.Generator().manual_seed(4)).cuda()
+    res = {}
+    for mode in ("native", "cublas"):
+        m._runtime().wgrad_mode = mode
+        m.zero_grad()
+        F.cross_entropy(m.forward_indices(idx), target).backward()
+        res[mode] = {k: v.grad.cpu().numpy().copy() for k, v in m.named_parameters()}
+    for k in res["native"]:
+        scale = np.abs(res["cublas"][k]).max()
+        if scale == 0:
+            assert np.abs(res["native"][k]).max() == 0, k
+        else:
+            assert np.abs(res["native"][k] - res["cublas"][k]).max() / scale < 1e-5, k
