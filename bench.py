@@ -352,7 +352,26 @@ def bench_train(args, world, rank):
                 "logits_max_rel_err_vs_exact": err,
                 "hbm_algorithmic_gbs": sum(per_layer_f) / (fms / 1e3) / 1e9,
                 "hbm_frac_of_measured_peak": sum(per_layer_f) / (fms / 1e3) / 1e9 / hbm_peak}
-        del y_exact, y_fast
+        # the other fp32-class operand split, for comparison (3xTF32 when bf16 pairs are the default and vice versa)
+        other = "tf32x3" if getattr(rt, "tc_precision", "tf32x3") == "bf16x2" else "bf16x2"
+        keep = rt.tc_precision
+        with torch.no_grad():
+            rt.tc_precision = other
+            for _ in range(2):
+                y_other = model.forward_indices(d_idx)
+            oe = []
+            for _ in range(max(1, min(args.steps, 3))):
+                flush()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                rt.block_events = (b0, b1)
+                y_other = model.forward_indices(d_idx)
+                torch.cuda.synchronize()
+                oe.append(b0.elapsed_time(b1))
+            rt.block_events = None
+            rt.tc_precision = keep
+        fast["other_operand_split"] = {"operand_split": other, "blocks_ms_per_step": sum(oe) / len(oe),
+                                       "logits_max_rel_diff_vs_default_split": float((y_other - y_exact).abs().max() / y_exact.abs().max())}
+        del y_exact, y_fast, y_other
     # full training step on the same shapes: forward (saving activations) + backward + per-block gradient all-reduce
     import torch.nn.functional as F
     import data_parallel as dp
@@ -390,13 +409,17 @@ def bench_train(args, world, rank):
     mode = getattr(rt, "last_block_mode", "ffma")
     if mode == "tc":
         tpeak, tsrc = measured_peaks("tensor")
-        roof = {"kernel": "frames_gemm_tc<GATE> + frames_gemm_tc<RES_SKIP> (tcgen05 kind::tf32, 3xTF32, one block = 2 launches)",
+        prec = getattr(rt, "tc_precision", "tf32x3")
+        mma_per_flop = 3 if prec == "bf16x2" else 6          # bf16-rate MMA equivalents per algorithmic FLOP
+        roof = {"kernel": "frames_gemm_tc<GATE> + frames_gemm_tc<RES_SKIP> (tcgen05, " +
+                          ("kind::f16 on bf16 hi/lo pairs" if prec == "bf16x2" else "kind::tf32, 3xTF32") + ", one block = 2 launches)",
                 "bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
                 "traffic": None, "peak_source": tsrc, "launches_per_step": 2 * n_layers,
-                "avg_block_ms": block_ms / n_layers,
-                "note": "achieved counts the algorithmic fp32 FLOPs once; every FLOP costs 3 tf32 MMAs (= 6 bf16-rate "
-                        "equivalents), so frac*6 is the share of the measured tensor peak the kernel keeps busy",
-                "tensor_pipe_equiv_frac": 6 * tflops / tpeak,
+                "avg_block_ms": block_ms / n_layers, "operand_split": prec,
+                "note": "achieved counts the algorithmic fp32 FLOPs once; fp32-class accuracy costs three MMAs per product "
+                        f"(hi*hi + lo*hi + hi*lo) = {mma_per_flop} bf16-rate equivalents per FLOP with the {prec} split, so "
+                        f"frac*{mma_per_flop} is the share of the measured tensor peak the kernel keeps busy",
+                "tensor_pipe_equiv_frac": mma_per_flop * tflops / tpeak,
                 "hbm_achieved_gbs": ach, "hbm_peak_gbs": peak, "hbm_frac": ach / peak,
                 "alg_bytes_per_block": sum(per_layer) / n_layers,
                 "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L)}

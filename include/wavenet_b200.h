@@ -109,10 +109,17 @@ typedef struct wn_tc_block_args {
     int B, L, R, D, S, k, dilation;
     int in_start, out_start, skip_start, skip_init;
     float* d_fg_save;
-    int fast_tf32;      /* 0 = 3xTF32 (parity path).  1 = single TF32 pass: 3x fewer MMAs, ~1e-3 relative on the logits
-                         * after 50 layers -- OUTSIDE the 1e-4 parity bar; opt-in, reported separately by bench.py */
+    int fast_tf32;      /* precision mode.  0 = 3xTF32 (hi/lo tf32 split of both operands, ~6e-7 on the logits after 50
+                         * layers).  2 = bf16 pairs (hi/lo bf16 split, the same three products at twice the MMA rate,
+                         * ~3e-6 on the logits after 50 layers; d_wa / d_wb must then be the arrays made by
+                         * wn_tc_convert_weights_bf16).  1 = single TF32 pass: ~1e-3 on the logits -- OUTSIDE the 1e-4
+                         * parity bar; opt-in, reported separately by bench.py */
 } wn_tc_block_args;
 int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream);
+/* Re-split a packed fp32 pair array [2][n_per_half] (hi | lo, as written by wn_tc_pack_block_weights /
+ * wn_tc_pack_block_bwd_weights) into bf16 pairs [2][n_per_half] for precision mode 2: x = hi + lo exactly,
+ * out_hi = bf16(x), out_lo = bf16(x - out_hi).  d_out: 4 * n_per_half bytes. */
+int wn_tc_convert_weights_bf16(const float* d_pairs, void* d_out, long long n_per_half, void* stream);
 /* Debug aid (WN_TC_TRACE=1): per-stage clock64 stamps of CTA 0 of the most recent tensor-core launch, 8 per stage:
  * producer before/after the empty wait, MMA warp before/after the operand wait and after issue, splitter start/end. */
 int wn_tc_read_trace(long long* host_out, int n);
@@ -159,6 +166,8 @@ int wn_tc_bwd_supported(int R, int D, int S, int k);
 int wn_tc_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws,
                                  int R, int D, int S, int k, float* d_wdz, float* d_wdh, void* stream);
 int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_wdz, const float* d_wdh, void* stream);
+/* the same with a precision mode: 0 = 3xTF32 (fp32 pair arrays), 2 = bf16 pairs (arrays from wn_tc_convert_weights_bf16) */
+int wn_tc_block_bwd_data_prec(const wn_block_bwd_args* a, const void* d_wdz, const void* d_wdh, int precision, void* stream);
 
 /* head: given d_dlogits (B*out_len, classes) and the saved skip sum (B, L-skip_start, S) produce
  * d_y1 (B*out_len, E) = relu(W1 relu(skip)+b1) (recomputed), d_dy1 (B*out_len, E) and d_dskip (B, out_len, S).

@@ -16,6 +16,7 @@
 // mbarriers: full (TMA landed), split (lo ready), empty (MMAs of the stage retired), acc_full / acc_empty.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -32,6 +33,13 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB
 constexpr int W_BYTES = BN * BK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;      // A_hi | A_lo | W_hi | W_lo = 48 KB
+// bf16x2 precision (PREC_BF16X2): the operand tiles are bf16 (hi, lo) pairs with 32-byte rows; the raw fp32 A slab keeps
+// its own buffer, so a stage is A_raw 8K | A_hi 4K | A_lo 4K | W_hi 8K | W_lo 8K = 32 KB and six stages fit
+constexpr int STAGES_BF = 6;
+constexpr int ABF_BYTES = BM * BK * 2;        // 4 KB
+constexpr int WBF_BYTES = BN * BK * 2;        // 8 KB
+constexpr int STAGE_BYTES_BF = A_BYTES + 2 * ABF_BYTES + 2 * WBF_BYTES;     // 32 KB
+enum { PREC_TF32X3 = 0, PREC_TF32X1 = 1, PREC_BF16X2 = 2 };
 constexpr int NTHREADS = 448;             // 14 warps: TMA, MMA, 4 split (2,3,8,9), 2 x 4 epilogue (4-7 and 10-13)
 constexpr int EPI_THREADS = 256;
 constexpr int SPLIT_THREADS = 128;
@@ -99,6 +107,11 @@ __device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a_
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc,
+                                         unsigned accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {       // arrives when all prior MMAs of this thread retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
@@ -120,8 +133,8 @@ __device__ __forceinline__ bool elect_one() {
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major rows of BK*4 bytes with the matching swizzle
 // (64B rows -> SWIZZLE_64B, 128B rows -> SWIZZLE_128B); 8-row atoms are 8*row_bytes apart
+template <unsigned row_bytes = BK * 4>
 __device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
-    constexpr unsigned row_bytes = BK * 4;
     constexpr unsigned long long layout = (row_bytes == 128) ? 2ull : (row_bytes == 64 ? 4ull : 6ull);   // SWIZZLE_128B/64B/32B
     unsigned long long d = 0;
     d |= (unsigned long long)((saddr >> 4) & 0x3fff);            // start address, 16-byte units
@@ -131,9 +144,10 @@ __device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
     d |= layout << 61;
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32, both K-major, M=128, N=256
-__host__ __device__ constexpr unsigned make_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32 (format 2, kind::tf32) or bf16 (format 1,
+// kind::f16), both K-major, M=128, N=256
+__host__ __device__ constexpr unsigned make_idesc(bool bf16 = false) {
+    return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -160,26 +174,31 @@ struct TcParams {
 
 __device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
 
-// EXACT = true : 3xTF32 (hi*hi + lo*hi + hi*lo), fp32-class accuracy -- the parity path.
-// EXACT = false: one TF32 MMA per k-step on the raw fp32 operands (the tensor core drops the low mantissa bits):
-//                ~1e-3 relative on the logits after 50 layers, i.e. outside the 1e-4 parity bar; offered as an opt-in
-//                "fast" mode and reported separately.
-template <int EPI, bool EXACT>
+// PREC_TF32X3: 3xTF32 (hi*hi + lo*hi + hi*lo, hi = rna_tf32(x)): ~6e-7 on the logits after 50 layers.
+// PREC_BF16X2: both operands as bf16 pairs (hi = bf16(x), lo = bf16(x - hi)), the same three products on kind::f16 at
+//              twice the tf32 rate: 16 mantissa bits per operand, ~3e-6 on the logits after 50 layers (inside the 1e-4 bar).
+// PREC_TF32X1: one TF32 MMA per k-step on the raw fp32 operands (the tensor core drops the low mantissa bits):
+//              ~1e-3 relative on the logits after 50 layers, i.e. outside the parity bar; opt-in, reported separately.
+template <int EPI, int PREC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+    constexpr bool EXACT = PREC == PREC_TF32X3;
+    constexpr bool BF = PREC == PREC_BF16X2;
+    constexpr int ST = BF ? STAGES_BF : STAGES;                // ring depth
+    constexpr int SB = BF ? STAGE_BYTES_BF : STAGE_BYTES;      // bytes per stage
     // mapW's box is BN/CS rows: every CTA of the cluster fetches its share of a weight slab and multicasts it to all
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* stage_mem = base;                                           // STAGES * STAGE_BYTES
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + STAGES * STAGE_BYTES);
-    unsigned long long* full = bars;                 // [STAGES]
-    unsigned long long* split = bars + STAGES;       // [STAGES]
-    unsigned long long* empty = bars + 2 * STAGES;   // [STAGES]
-    unsigned long long* acc_full = bars + 3 * STAGES;      // [2]
-    unsigned long long* acc_empty = bars + 3 * STAGES + 2; // [2]
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * STAGES + 4);
-    float* bias_s = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES + 512);                   // [n_total]
+    unsigned char* stage_mem = base;                                           // ST * SB
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + ST * SB);
+    unsigned long long* full = bars;                 // [ST]
+    unsigned long long* split = bars + ST;           // [ST]
+    unsigned long long* empty = bars + 2 * ST;       // [ST]
+    unsigned long long* acc_full = bars + 3 * ST;          // [2]
+    unsigned long long* acc_empty = bars + 3 * ST + 2;     // [2]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * ST + 4);
+    float* bias_s = reinterpret_cast<float*>(base + ST * SB + 512);                                // [n_total]
     float* stage_t = bias_s + ((p.n_total + 3) & ~3);                          // [4 warps][32][TP] epilogue transpose tiles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -196,7 +215,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int slabs = slabs1 + p.C2 / BK;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, CS); }
+        for (int i = 0; i < ST; ++i) { mbar_init(full + i, 1); mbar_init(split + i, SPLIT_THREADS); mbar_init(empty + i, CS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -220,30 +239,32 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int b = ghost ? 0 : item / m_tiles, t0 = ghost ? p.L : p.t_begin + (item % m_tiles) * BM;
                 for (int nt = 0; nt < p.n_tiles; ++nt)
                     for (int sl = 0; sl < slabs; ++sl, ++it) {
-                        const int st = it % STAGES;
-                        const unsigned ph = (it / STAGES) & 1;
+                        const int st = it % ST;
+                        const unsigned ph = (it / ST) & 1;
                         if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it * 8 + 0] = clock64();
                         mbar_wait(empty + st, ph ^ 1);           // every CTA of the cluster is done with this stage
                         if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it * 8 + 1] = clock64();
-                        unsigned char* sm = stage_mem + st * STAGE_BYTES;
-                        mbar_expect_tx(full + st, A_BYTES + (EXACT ? 2 : 1) * W_BYTES);
+                        unsigned char* sm = stage_mem + st * SB;
+                        mbar_expect_tx(full + st, BF ? A_BYTES + 2 * WBF_BYTES : A_BYTES + (EXACT ? 2 : 1) * W_BYTES);
                         if (sl < slabs1) {
                             const int j = sl / slabs_per_tap, c0 = (sl % slabs_per_tap) * BK;
                             tma_load_3d(sm, &mapA, c0, t0 - (p.taps - 1 - j) * p.dil - p.a_origin, b, full + st);
                         } else {
                             tma_load_3d(sm, &mapA2, (sl - slabs1) * BK, t0 - p.a2_origin, b, full + st);
                         }
-                        constexpr int WR = BN / CS, WB = W_BYTES / CS;      // this CTA's rows / bytes of the slab
-                        tma_load_2d_mc(sm + 2 * A_BYTES + crank * WB, &mapW, sl * BK, nt * BN + crank * WR, full + st, mc_mask);
-                        if (EXACT)
-                            tma_load_2d_mc(sm + 2 * A_BYTES + W_BYTES + crank * WB, &mapW, sl * BK, p.n_total + nt * BN + crank * WR,
+                        constexpr int WR = BN / CS;                          // this CTA's rows of the slab
+                        constexpr int WT = BF ? WBF_BYTES : W_BYTES;        // bytes of one weight tile (hi or lo)
+                        constexpr int W0 = BF ? A_BYTES + 2 * ABF_BYTES : 2 * A_BYTES;      // offset of W_hi in the stage
+                        tma_load_2d_mc(sm + W0 + crank * (WT / CS), &mapW, sl * BK, nt * BN + crank * WR, full + st, mc_mask);
+                        if (EXACT || BF)
+                            tma_load_2d_mc(sm + W0 + WT + crank * (WT / CS), &mapW, sl * BK, p.n_total + nt * BN + crank * WR,
                                            full + st, mc_mask);
                     }
             }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        constexpr unsigned idesc = make_idesc();
+        constexpr unsigned idesc = make_idesc(BF);
         unsigned it = 0, tile = 0;
         for (int rd = 0; rd < rounds; ++rd)
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
@@ -252,23 +273,33 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_fence_after();
                 const unsigned d_tmem = tmem_base + ab * BN;
                 for (int sl = 0; sl < slabs; ++sl, ++it) {
-                    const int st = it % STAGES;
-                    const unsigned ph = (it / STAGES) & 1;
+                    const int st = it % ST;
+                    const unsigned ph = (it / ST) & 1;
                     if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 2] = clock64();
                     mbar_wait(split + st, ph);                   // TMA landed and the splitter produced hi/lo
                     if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[it * 8 + 3] = clock64();
                     tc_fence_after();
                     if (elect_one()) {
-                        const unsigned sa = s32(stage_mem + st * STAGE_BYTES);
-                        const unsigned long long a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_BYTES);
-                        const unsigned long long w_hi = smem_desc(sa + 2 * A_BYTES), w_lo = smem_desc(sa + 2 * A_BYTES + W_BYTES);
+                        const unsigned sa = s32(stage_mem + st * SB);
+                        if constexpr (BF) {
+                            // one k-step per slab: 16 bf16 = one 32-byte swizzle row
+                            const unsigned long long a_hi = smem_desc<32>(sa + A_BYTES), a_lo = smem_desc<32>(sa + A_BYTES + ABF_BYTES);
+                            const unsigned long long w_hi = smem_desc<32>(sa + A_BYTES + 2 * ABF_BYTES);
+                            const unsigned long long w_lo = smem_desc<32>(sa + A_BYTES + 2 * ABF_BYTES + WBF_BYTES);
+                            umma_f16(d_tmem, a_hi, w_hi, idesc, sl != 0);
+                            umma_f16(d_tmem, a_lo, w_hi, idesc, 1);
+                            umma_f16(d_tmem, a_hi, w_lo, idesc, 1);
+                        } else {
+                            const unsigned long long a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_BYTES);
+                            const unsigned long long w_hi = smem_desc(sa + 2 * A_BYTES), w_lo = smem_desc(sa + 2 * A_BYTES + W_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {    // 8 tf32 = 32 bytes = 2 descriptor units per k-step
-                            const unsigned long long o = (unsigned long long)(kk * 2);
-                            umma_tf32(d_tmem, a_hi + o, w_hi + o, idesc, (sl | kk) != 0);
-                            if (EXACT) {
-                                umma_tf32(d_tmem, a_lo + o, w_hi + o, idesc, 1);
-                                umma_tf32(d_tmem, a_hi + o, w_lo + o, idesc, 1);
+                            for (int kk = 0; kk < BK / 8; ++kk) {    // 8 tf32 = 32 bytes = 2 descriptor units per k-step
+                                const unsigned long long o = (unsigned long long)(kk * 2);
+                                umma_tf32(d_tmem, a_hi + o, w_hi + o, idesc, (sl | kk) != 0);
+                                if (EXACT) {
+                                    umma_tf32(d_tmem, a_lo + o, w_hi + o, idesc, 1);
+                                    umma_tf32(d_tmem, a_hi + o, w_lo + o, idesc, 1);
+                                }
                             }
                         }
                         umma_commit_mc(empty + st, mc_mask);     // stage reusable (in every CTA) once these MMAs retire
@@ -285,12 +316,33 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int rd = 0; rd < rounds; ++rd)
             for (int nt = 0; nt < p.n_tiles; ++nt)
                 for (int sl = 0; sl < slabs; ++sl, ++it) {
-                    const int st = it % STAGES;
-                    const unsigned ph = (it / STAGES) & 1;
+                    const int st = it % ST;
+                    const unsigned ph = (it / ST) & 1;
                     mbar_wait(full + st, ph);
                     if (p.dbg && blockIdx.x == 0 && it < 512 && st_tid == 0) p.dbg[it * 8 + 5] = clock64();
-                    float4* hi = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES);
-                    float4* lo = reinterpret_cast<float4*>(stage_mem + st * STAGE_BYTES + A_BYTES);
+                    float4* hi = reinterpret_cast<float4*>(stage_mem + st * SB);
+                    float4* lo = reinterpret_cast<float4*>(stage_mem + st * SB + A_BYTES);
+                    if constexpr (BF) {
+                        // raw slab: 128 rows x 64 bytes, 64B-swizzled by the TMA (16-byte chunk c of row r sits at c ^ ((r>>1)&3));
+                        // operand tiles: 128 rows x 32 bytes of bf16, 32B swizzle (chunk c of row r sits at c ^ ((r>>2)&1))
+                        unsigned char* ahi = stage_mem + st * SB + A_BYTES;
+                        unsigned char* alo = ahi + ABF_BYTES;
+#pragma unroll
+                        for (int i = st_tid; i < A_BYTES / 16; i += SPLIT_THREADS) {
+                            const float4 x = hi[i];
+                            const int row = i >> 2, lch = (i & 3) ^ ((row >> 1) & 3);      // logical chunk: fp32 k = 4*lch .. 4*lch+3
+                            const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+                            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                            const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y);
+                            const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+                            const unsigned off = (unsigned)row * 32u + ((unsigned)((lch >> 1) ^ ((row >> 2) & 1)) << 4) + (unsigned)(lch & 1) * 8u;
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<const unsigned*>(&h01); hv.y = *reinterpret_cast<const unsigned*>(&h23);
+                            lv.x = *reinterpret_cast<const unsigned*>(&l01); lv.y = *reinterpret_cast<const unsigned*>(&l23);
+                            *reinterpret_cast<uint2*>(ahi + off) = hv;
+                            *reinterpret_cast<uint2*>(alo + off) = lv;
+                        }
+                    }
 #pragma unroll
                     for (int i = st_tid; EXACT && i < A_BYTES / 16; i += SPLIT_THREADS) {
                         const float4 x = hi[i];
@@ -561,6 +613,17 @@ __global__ void pack_dh_kernel(const float* __restrict__ wf, const float* __rest
     }
 }
 
+// fp32 (hi | lo) tf32-split pair arrays -> bf16 (hi | lo) pair arrays of the same shape.  hi + lo is the original
+// weight exactly (lo = x - rna_tf32(x) is exact in fp32), so x is recovered and re-split for bf16.
+__global__ void convert_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = src[i] + src[n + i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        dst[i] = h;
+        dst[n + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -591,32 +654,37 @@ static int make_act_map(CUtensorMap* m, const float* base, int B, int L, int C, 
     return 0;
 }
 // weights (rows, K) fp32 K-major: dims {K, rows}, box {32, 256}
-static int make_w_map(CUtensorMap* m, const float* base, int rows, int K) {
+// `col0`: first K column (element offset into every row); bf16 = true: the array holds bf16 pairs (32-byte slab rows)
+static int make_w_map(CUtensorMap* m, const void* base, int rows, int K, int col0 = 0, bool bf16 = false) {
     EncodeTiledFn fn = encode_fn();
     WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    const int es = bf16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)K * es};
     cuuint32_t box[2] = {BK, BN / CS};          // one CTA's share of a slab; the multicast assembles the rest
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    (BK * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : (BK * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+    const int row_bytes = BK * es;
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    (void*)((const unsigned char*)base + (size_t)col0 * es), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
     return 0;
 }
 
-static size_t tc_smem_bytes(int n_total) {
-    return 1024 + (size_t)STAGES * STAGE_BYTES + 512 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 8 * 32 * TP;
+static size_t tc_smem_bytes(int n_total, int prec) {
+    const size_t ring = prec == PREC_BF16X2 ? (size_t)STAGES_BF * STAGE_BYTES_BF : (size_t)STAGES * STAGE_BYTES;
+    return 1024 + ring + 512 + sizeof(float) * ((n_total + 3) & ~3) + sizeof(float) * 8 * 32 * TP;
 }
 
-template <int EPI, bool EXACT>
+template <int EPI, int PREC>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const TcParams& p, cudaStream_t st) {
     int dev = 0, sms = 0;
     WN_CUDA(cudaGetDevice(&dev));
     WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = tc_smem_bytes(p.n_total);
-    WN_CUDA(cudaFuncSetAttribute(frames_gemm_tc<EPI, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = tc_smem_bytes(p.n_total, PREC);
+    WN_CUDA(cudaFuncSetAttribute(frames_gemm_tc<EPI, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int items = p.B * ((p.L - p.t_begin + BM - 1) / BM);
     int grid = ((items + CS - 1) / CS) * CS;
     const int max_grid = (sms / CS) * CS;
@@ -633,9 +701,16 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtens
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, frames_gemm_tc<EPI, EXACT>, mA, mA2, mW, p));
+    WN_CUDA(cudaLaunchKernelEx(&cfg, frames_gemm_tc<EPI, PREC>, mA, mA2, mW, p));
     WN_CUDA(cudaGetLastError());
     return 0;
+}
+template <int EPI>
+static int launch_tc_prec(int prec, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const TcParams& p,
+                          cudaStream_t st) {
+    if (prec == PREC_BF16X2) return launch_tc<EPI, PREC_BF16X2>(mA, mA2, mW, p, st);
+    if (prec == PREC_TF32X1) return launch_tc<EPI, PREC_TF32X1>(mA, mA2, mW, p, st);
+    return launch_tc<EPI, PREC_TF32X3>(mA, mA2, mW, p, st);
 }
 
 }  // namespace tc
@@ -678,9 +753,12 @@ extern "C" int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap mA, mWa, mZ, mWb;
     if (int rc = tc::make_act_map(&mA, a->d_h_in, a->B, a->L, a->R, a->in_start)) return rc;
-    if (int rc = tc::make_w_map(&mWa, a->d_wa, 2 * 2 * a->D, a->k * a->R)) return rc;
+    const int prec = a->fast_tf32;            // 0: 3xTF32, 1: single TF32, 2: bf16 pairs (d_wa / d_wb from wn_tc_convert_weights_bf16)
+    WN_REQUIRE(prec >= 0 && prec <= 2, WN_E_BADARG, "wn_tc_block_fwd: fast_tf32 (precision mode) must be 0, 1 or 2");
+    const bool bf = prec == tc::PREC_BF16X2;
+    if (int rc = tc::make_w_map(&mWa, a->d_wa, 2 * 2 * a->D, a->k * a->R, 0, bf)) return rc;
     if (int rc = tc::make_act_map(&mZ, a->d_z, a->B, a->L, a->D, a->out_start)) return rc;
-    if (int rc = tc::make_w_map(&mWb, a->d_wb, 2 * (a->R + a->S), a->D)) return rc;
+    if (int rc = tc::make_w_map(&mWb, a->d_wb, 2 * (a->R + a->S), a->D, 0, bf)) return rc;
     tc::TcParams p;
     memset(&p, 0, sizeof(p));
     if (getenv("WN_TC_TRACE")) {
@@ -693,14 +771,13 @@ extern "C" int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream) {
     p.taps = a->k; p.dil = a->dilation; p.C = a->R; p.a_origin = a->in_start;
     p.n_total = 2 * a->D; p.n_tiles = p.n_total / tc::BN;
     p.bias = a->d_ba; p.out0 = a->d_z; p.out1 = a->d_fg_save; p.res = nullptr;
-    const bool exact = (a->fast_tf32 == 0);
-    if (int rc = exact ? tc::launch_tc<tc::EPI_GATE, true>(mA, mA, mWa, p, st) : tc::launch_tc<tc::EPI_GATE, false>(mA, mA, mWa, p, st))
-        return rc;
+    if (int rc = tc::launch_tc_prec<tc::EPI_GATE>(prec, mA, mA, mWa, p, st)) return rc;
     // pass B: residual + skip 1x1
+    if (const char* which = getenv("WN_TC_TRACE_PASS")) { if (which[0] == 'A') p.dbg = nullptr; }     // keep pass A's stamps
     p.taps = 1; p.dil = 0; p.C = a->D; p.a_origin = a->out_start;
     p.n_total = a->R + a->S; p.n_tiles = p.n_total / tc::BN;
     p.bias = a->d_bb; p.out0 = a->d_h_out; p.out1 = a->d_skip; p.res = a->d_h_in;
-    return exact ? tc::launch_tc<tc::EPI_RES_SKIP, true>(mZ, mZ, mWb, p, st) : tc::launch_tc<tc::EPI_RES_SKIP, false>(mZ, mZ, mWb, p, st);
+    return tc::launch_tc_prec<tc::EPI_RES_SKIP>(prec, mZ, mZ, mWb, p, st);
 }
 
 extern "C" int wn_tc_bwd_supported(int R, int D, int S, int k) {
@@ -721,7 +798,15 @@ extern "C" int wn_tc_pack_block_bwd_weights(const float* d_wf, const float* d_wg
 // Tensor-core form of wn_block_bwd_data (same arguments; d_wrs_rows / d_wfg_bwd are replaced by the packed, pre-split
 // d_wdz [2][D][R+S] and d_wdh [2][R][k*2D] of wn_tc_pack_block_bwd_weights).
 extern "C" int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_wdz, const float* d_wdh, void* stream) {
+    return wn_tc_block_bwd_data_prec(a, d_wdz, d_wdh, 0, stream);
+}
+
+// precision: 0 = 3xTF32 on the fp32 pair arrays, 2 = bf16 pairs (arrays converted by wn_tc_convert_weights_bf16)
+extern "C" int wn_tc_block_bwd_data_prec(const wn_block_bwd_args* a, const void* d_wdz, const void* d_wdh, int precision,
+                                         void* stream) {
     WN_REQUIRE(a && d_wdz && d_wdh, WN_E_BADARG, "wn_tc_block_bwd_data: null args");
+    WN_REQUIRE(precision == 0 || precision == 2, WN_E_BADARG, "wn_tc_block_bwd_data: precision must be 0 (3xTF32) or 2 (bf16 pairs)");
+    const bool bf = precision == 2;
     WN_REQUIRE(a->d_dskip && a->d_fg && a->d_dfg && a->d_z && a->d_dh_in, WN_E_BADARG, "wn_tc_block_bwd_data: null pointer");
     WN_REQUIRE(wn_tc_bwd_supported(a->R, a->D, a->S, a->k), WN_E_UNSUPP, "wn_tc_block_bwd_data: shape not supported");
     WN_REQUIRE(a->gz >= a->out_start && a->gz < a->L && a->gs_in >= a->in_start && a->gs_in <= a->gz && a->ds_start >= a->out_start &&
@@ -734,7 +819,7 @@ extern "C" int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_w
     if (int rc = tc::make_act_map(&mDs, a->d_dskip, B, L - a->ds_start, S, 0)) return rc;          // (B, L-ds_start, S): own frame axis
     if (have_dh) { if (int rc = tc::make_act_map(&mDh, a->d_dh_out, B, L, R, a->gs_out)) return rc; }
     else mDh = mDs;
-    if (int rc = tc::make_w_map(&mW1, d_wdz + (have_dh ? 0 : R), 2 * D, R + S)) return rc;       // without dh_out: start at column R
+    if (int rc = tc::make_w_map(&mW1, d_wdz, 2 * D, R + S, have_dh ? 0 : R, bf)) return rc;       // without dh_out: start at column R
     tc::TcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.L = L; p.D = D; p.R = R; p.S = S;
@@ -744,15 +829,22 @@ extern "C" int wn_tc_block_bwd_data(const wn_block_bwd_args* a, const float* d_w
     p.C2 = S; p.a2_origin = a->ds_start;
     p.n_total = D; p.n_tiles = D / tc::BN;
     p.bias = nullptr; p.out0 = a->d_dfg; p.out2 = a->d_z; p.res = a->d_fg;
-    if (int rc = tc::launch_tc<tc::EPI_GATE_BWD, true>(mDh, mDs, mW1, p, st)) return rc;
+    if (int rc = tc::launch_tc_prec<tc::EPI_GATE_BWD>(precision, mDh, mDs, mW1, p, st)) return rc;
     // ---- dh_in = dh_out (identity) + anti-causal taps of dfg, for frames [gs_in, L)
     if (int rc = tc::make_act_map(&mDfg, a->d_dfg, B, L, 2 * D, a->gz)) return rc;
-    if (int rc = tc::make_w_map(&mW2, d_wdh, 2 * R, a->k * 2 * D)) return rc;
+    if (int rc = tc::make_w_map(&mW2, d_wdh, 2 * R, a->k * 2 * D, 0, bf)) return rc;
     p.t_begin = a->gs_in;
     p.taps = a->k; p.dil = -a->dilation; p.C = 2 * D; p.a_origin = a->gz;
     p.C2 = 0; p.a2_origin = 0;
     p.n_total = R; p.n_tiles = R / tc::BN;
     p.out0 = a->d_dh_in; p.out2 = nullptr; p.res = a->d_dh_out;
     p.id_start = a->gs_out > a->out_start ? a->gs_out : a->out_start;
-    return tc::launch_tc<tc::EPI_ADD, true>(mDfg, mDfg, mW2, p, st);
+    return tc::launch_tc_prec<tc::EPI_ADD>(precision, mDfg, mDfg, mW2, p, st);
+}
+
+extern "C" int wn_tc_convert_weights_bf16(const float* d_pairs, void* d_out, long long n_per_half, void* stream) {
+    WN_REQUIRE(d_pairs && d_out && n_per_half > 0, WN_E_BADARG, "wn_tc_convert_weights_bf16: null pointer or empty array");
+    tc::convert_bf16_kernel<<<512, 256, 0, (cudaStream_t)stream>>>(d_pairs, (__nv_bfloat16*)d_out, n_per_half);
+    WN_CUDA(cudaGetLastError());
+    return 0;
 }

@@ -109,6 +109,8 @@ SIGNATURES = {
     "wn_tc_bwd_supported": (C.c_int, [C.c_int] * 4),
     "wn_tc_pack_block_bwd_weights": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     "wn_tc_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wn_tc_block_bwd_data_prec": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "wn_tc_convert_weights_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "wn_gen_workspace_bytes": (C.c_int, [C.POINTER(GenShape), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "wn_gen_create": (C.c_int, [C.POINTER(GenShape), C.POINTER(GenWeights), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),

@@ -60,6 +60,7 @@ class _Runtime:
         self.samplers = {}
         self.block_mode = "auto"     # "auto": tensor-core blocks when the shape allows, "ffma": exact-fp32 SIMT, "tc"
         self.fast_tf32 = False       # opt-in single-pass TF32 blocks (~1e-3 on the logits: outside the parity bar)
+        self.tc_precision = "bf16x2"  # tensor-core operand split: "tf32x3" (3xTF32) or "bf16x2" (bf16 pairs, 2x the MMA rate)
 
     # ------------------------------------------------------------------ weights
     def _params(self):
@@ -76,6 +77,14 @@ class _Runtime:
             raise RuntimeError("wavenet_b200: the model must be on a CUDA device (model.cuda()); "
                                "there is no CPU path in this implementation")
         return dev
+
+    @staticmethod
+    def _bf16_pairs(pairs, stream):
+        """(2, rows, K) fp32 tf32-split pair array -> (2, rows, K) bf16 pair array (wn_tc_convert_weights_bf16)."""
+        out = torch.empty(pairs.shape, device=pairs.device, dtype=torch.bfloat16)
+        native.check(native.lib().wn_tc_convert_weights_bf16(pairs.data_ptr(), out.data_ptr(), pairs.numel() // 2, stream),
+                     "convert bf16")
+        return out
 
     def packed_weights(self, stream):
         """Pack (or re-pack after an optimizer step / load_state_dict) the K-outer weight copies."""
@@ -112,12 +121,14 @@ class _Runtime:
                     native.ptr(br), native.ptr(bs), R, D, S, k, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
                     bb.data_ptr(), stream), "pack tc")
                 out.setdefault("tc_layers", []).append((wa, ba, wb, bb))
+                out.setdefault("tc_layers_bf16", []).append((self._bf16_pairs(wa, stream), ba, self._bf16_pairs(wb, stream), bb))
             if lib.wn_tc_bwd_supported(R, D, S, k):
                 wdz = torch.empty(2, D, R + S, **f32)
                 wdh = torch.empty(2, R, k * 2 * D, **f32)
                 native.check(lib.wn_tc_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
                                                               R, D, S, k, wdz.data_ptr(), wdh.data_ptr(), stream), "pack tc bwd")
                 out.setdefault("tc_bwd_layers", []).append((wdz, wdh))
+                out.setdefault("tc_bwd_layers_bf16", []).append((self._bf16_pairs(wdz, stream), self._bf16_pairs(wdh, stream)))
 
         def pack1x1(w, b, N, K):
             wt = torch.empty(K, lib.wn_n2p(N), **f32)
@@ -194,7 +205,10 @@ class _Runtime:
             a = native.TcBlockArgs()
             a.B, a.L, a.R, a.D, a.S, a.k = B, L, R, D, S, k
             a.d_z = zws.data_ptr()
-            a.fast_tf32 = int(bool(self.fast_tf32))
+            if self.tc_precision not in ("tf32x3", "bf16x2"):
+                raise ValueError(f"tc_precision must be 'tf32x3' or 'bf16x2', not {self.tc_precision!r}")
+            a.fast_tf32 = 1 if self.fast_tf32 else (2 if self.tc_precision == "bf16x2" else 0)
+            tc_key = "tc_layers_bf16" if a.fast_tf32 == 2 else "tc_layers"
         else:
             a = native.BlockArgs()
             a.B, a.L, a.R, a.D, a.S, a.k, a.mode = B, L, R, D, S, k, 0
@@ -208,7 +222,7 @@ class _Runtime:
             a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
             a.d_fg_save = None if save is None else fg_all[i].data_ptr()
             if use_tc:
-                wa, ba, wb, bb = W["tc_layers"][i]
+                wa, ba, wb, bb = W[tc_key][i]
                 a.d_wa, a.d_ba, a.d_wb, a.d_bb = wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr()
                 native.check(lib.wn_tc_block_fwd(ctypes.byref(a), stream), f"tc block {i}")
             else:
@@ -327,8 +341,13 @@ class _Runtime:
             a.dilation, a.in_start, a.out_start = d, in_s, out_s
             a.gs_out, a.gz, a.gs_in = gs_out, gz, gs_in
             if use_tc_bwd:
-                wdz, wdh = W["tc_bwd_layers"][i]
-                native.check(lib.wn_tc_block_bwd_data(ctypes.byref(a), wdz.data_ptr(), wdh.data_ptr(), stream), f"tc block bwd {i}")
+                if self.tc_precision == "bf16x2":
+                    wdz, wdh = W["tc_bwd_layers_bf16"][i]
+                    native.check(lib.wn_tc_block_bwd_data_prec(ctypes.byref(a), wdz.data_ptr(), wdh.data_ptr(), 2, stream),
+                                 f"tc block bwd {i}")
+                else:
+                    wdz, wdh = W["tc_bwd_layers"][i]
+                    native.check(lib.wn_tc_block_bwd_data(ctypes.byref(a), wdz.data_ptr(), wdh.data_ptr(), stream), f"tc block bwd {i}")
             else:
                 wrs_rows = pad_cols(torch.cat([wr.detach()[:, :, 0], wsk.detach()[:, :, 0]], 0), lib.wn_n2p(D))
                 wfg_bwd = pad_cols(torch.cat([wf.detach(), wg.detach()], 0).permute(2, 0, 1).reshape(k * 2 * D, R),

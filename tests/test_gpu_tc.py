@@ -1,5 +1,5 @@
-"""Tensor-core (tcgen05, 3xTF32) residual blocks vs the exact-fp32 SIMT blocks, the golden reference outputs and the
-CPU oracle.  The 3xTF32 path must hold the same 1e-4 parity bar (it is expected around 1e-6)."""
+"""Tensor-core (tcgen05) residual blocks vs the exact-fp32 SIMT blocks, the golden reference outputs and the CPU oracle.
+Both operand splits -- bf16 pairs (default) and 3xTF32 -- must hold the same 1e-4 parity bar (expected around 1e-6)."""
 import numpy as np
 import pytest
 import torch
@@ -10,7 +10,8 @@ from helpers import build_model, one_hot_cuda, rel_err, separate_head_relu_ties
 pytestmark = pytest.mark.gpu
 
 
-def test_tc_blocks_match_ffma_and_oracle():
+@pytest.mark.parametrize("precision", ["bf16x2", "tf32x3"])
+def test_tc_blocks_match_ffma_and_oracle(precision):
     import wavenet_model as wmod
     kw = dict(layers=4, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
               classes=256, output_length=300, kernel_size=2, bias=True)
@@ -23,6 +24,8 @@ def test_tc_blocks_match_ffma_and_oracle():
         want = O.forward(p, spec, O.one_hot(idx, 256)).numpy()
     m = m.cuda()
     rt = m._runtime()
+    assert rt.tc_precision == "bf16x2"                          # the default operand split
+    rt.tc_precision = precision
     with torch.no_grad():
         rt.block_mode = "ffma"
         y0 = m.forward_indices(idx.cuda()).cpu().numpy()
@@ -67,9 +70,13 @@ def test_tc_full_size_batch_independence():
         y2 = m.forward_indices(idx[2:3]).view(1, -1, 256)
         rt.block_mode = "ffma"
         y_ref = m.forward_indices(idx[2:3]).view(1, -1, 256)
+        rt.block_mode, rt.tc_precision = "tc", "tf32x3"
+        y3 = m.forward_indices(idx[2:3]).view(1, -1, 256)
     assert bool(torch.isfinite(y).all())
     assert torch.equal(y[2], y2[0])
-    assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) < 2e-5
+    assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) < 2e-5          # bf16 pairs, 50 layers deep
+    assert rel_err(y3.cpu().numpy(), y_ref.cpu().numpy()) < 2e-5          # 3xTF32
+    assert not torch.equal(y3, y2)                                         # the two splits are different arithmetic
 
 
 def test_fast_tf32_mode_is_opt_in_and_close():
@@ -81,6 +88,11 @@ def test_fast_tf32_mode_is_opt_in_and_close():
     idx = torch.randint(0, 256, (2, 6000), generator=torch.Generator().manual_seed(4)).cuda()
     rt = m._runtime()
     assert rt.fast_tf32 is False
+    with pytest.raises(ValueError):
+        rt.tc_precision = "fp8"
+        with torch.no_grad():
+            m.forward_indices(idx)
+    rt.tc_precision = "bf16x2"
     with torch.no_grad():
         exact = m.forward_indices(idx).cpu().numpy()
         rt.fast_tf32 = True
@@ -112,13 +124,13 @@ def test_tc_backward_matches_simt_backward_and_oracle():
     m = m.cuda()
     rt = m._runtime()
     grads = {}
-    for mode in ("tc", "ffma"):
-        rt.block_mode = mode
+    for mode, prec in (("tc", "bf16x2"), ("tc3", "tf32x3"), ("ffma", "bf16x2")):
+        rt.block_mode, rt.tc_precision = mode[:2] if mode.startswith("tc") else mode, prec
         m.zero_grad()
         F.cross_entropy(m.forward_indices(idx.cuda()), tgt.cuda()).backward()
-        assert rt.last_bwd_mode == mode
+        assert rt.last_bwd_mode == rt.block_mode
         grads[mode] = {k: v.grad.detach().cpu().numpy().copy() for k, v in m.named_parameters()}
-    rt.block_mode = "auto"
+    rt.block_mode, rt.tc_precision = "auto", "bf16x2"
     bad = []
     for k, v in p.items():
         want = np.zeros_like(grads["tc"][k]) if v.grad is None else v.grad.numpy()
@@ -128,7 +140,7 @@ def test_tc_backward_matches_simt_backward_and_oracle():
             continue
         e_f = np.abs(grads["ffma"][k] - want).max() / scale
         e_t = np.abs(grads["tc"][k] - want).max() / scale
-        e_tf = np.abs(grads["tc"][k] - grads["ffma"][k]).max() / scale
+        e_tf = max(np.abs(grads["tc"][k] - grads["ffma"][k]).max(), np.abs(grads["tc3"][k] - want).max()) / scale
         if not (e_f < 1e-4 and e_t < 1e-4 and e_tf < 1e-4):
             bad.append((k, float(scale), float(e_f), float(e_t), float(e_tf)))
     assert not bad, bad[:12]
