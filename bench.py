@@ -394,8 +394,9 @@ def bench_train(args, world, rank):
                   "grad_allreduce_bytes_per_step": red.bytes_reduced // max(1, 1 + len(step_ms)) if world > 1 else 0,
                   "grad_buckets_per_step": red.buckets // max(1, 1 + len(step_ms)) if world > 1 else 0,
                   "forward_blocks": getattr(rt, "last_block_mode", "ffma"), "backward_data": getattr(rt, "last_bwd_mode", "ffma"),
-                  "weight_gradients": "cuBLAS fp32 einsum" if getattr(rt, "wgrad_mode", "native") == "cublas" else
-                                      "wn_wgrad (split-frames fp32 SIMT kernel)",
+                  "weight_gradients": {"cublas": "cuBLAS fp32 einsum", "native": "wn_wgrad (split-frames fp32 FMA kernel)",
+                                       "tc": f"wn_tc_wgrad (tcgen05, bf16 pairs; {getattr(rt, 'wgrad_tc_calls', 0)} of the calls) else wn_wgrad"
+                                       }[getattr(rt, "wgrad_mode", "tc")],
                   "note": "forward with activations saved + backward data kernels + weight-gradient kernels + NCCL all-reduce "
                           "per block overlapped with the backward (the optimizer step is not part of this figure)"}
     model._runtime().grad_reducer = None

@@ -195,6 +195,11 @@ typedef struct wn_wgrad_args {
 } wn_wgrad_args;
 size_t wn_wgrad_workspace_bytes(int N, int C);
 int wn_wgrad(const wn_wgrad_args* a, void* stream);
+/* The same contraction on the tensor cores (tcgen05 kind::f16 on bf16 hi/lo pairs, fp32 accumulation; the operand
+ * tiles are transposed to K-major while they are split): C == 256, N % 128 == 0, rows >= 1, ldg / ldx / sequence
+ * strides multiples of 4 floats, d_g / d_x 16-byte aligned.  Same argument block and workspace as wn_wgrad. */
+int wn_tc_wgrad_supported(int N, int C);
+int wn_tc_wgrad(const wn_wgrad_args* a, void* stream);
 
 /* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
  * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with

@@ -713,6 +713,186 @@ static int launch_tc_prec(int prec, const CUtensorMap& mA, const CUtensorMap& mA
     return launch_tc<EPI, PREC_TF32X3>(mA, mA2, mW, p, st);
 }
 
+
+// ============================================================================================== weight gradients
+// dW[n][c] = sum over sequences b and frames t of g[b][t][n] * x[b][t][c]  (what wn_wgrad computes on the FMA pipe,
+// wgrad.cu) on the tensor cores.  The contraction runs over frames, the SLOW axis of both row-major operands, so the
+// tiles arrive "MN-major"; instead of MN-major descriptors the splitter -- which has to rewrite every element as a
+// bf16 (hi, lo) pair anyway -- writes the operand tiles TRANSPOSED, i.e. in the same K-major, 32-byte-swizzled form the
+// block kernels use.  One CTA = one 128-row tile of n (UMMA M) x all C = 256 columns (UMMA N) x one range of K slabs
+// (16 frames each); its fp32 partial goes to the split-frames workspace and wgrad_tc_reduce_kernel adds the partials.
+//   warp 0      TMA producer: raw fp32 tiles g[16 frames][128 ch] and x[16 frames][256 ch] (no swizzle), 4-stage ring
+//   warp 1      TMEM (256 columns), tcgen05.mma kind::f16: hi*hi + lo*hi + hi*lo per slab
+//   warps 2-9   splitter: thread = (channel, 8 frames): 8 conflict-free LDS.32 down a column, bf16 hi/lo split,
+//               one 16-byte store per operand tile row chunk
+//   warps 2-9   after the last slab: TMEM -> registers -> workspace
+constexpr int WG_THREADS = 320;
+constexpr int WG_SPLIT_THREADS = 256;
+constexpr int WG_STAGES = 4;
+constexpr int WG_RAW_A = BK * BM * 4;            // 8 KB   [16 frames][128 ch] fp32
+constexpr int WG_RAW_B = BK * BN * 4;            // 16 KB  [16 frames][256 ch] fp32
+constexpr int WG_STAGE_BYTES = WG_RAW_A + WG_RAW_B + 2 * ABF_BYTES + 2 * WBF_BYTES;      // 48 KB
+
+struct WgTcParams {
+    int slabs_per_seq, total_slabs, slabs_per_split, m_tiles;
+    int N, C;
+    float* work;                  // [splits][N][C]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX, const WgTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + WG_STAGES * WG_STAGE_BYTES);
+    unsigned long long* full = bars;                       // [WG_STAGES] TMA landed
+    unsigned long long* split = bars + WG_STAGES;          // [WG_STAGES] operand tiles written
+    unsigned long long* empty = bars + 2 * WG_STAGES;      // [WG_STAGES] MMAs of the stage retired
+    unsigned long long* acc_full = bars + 3 * WG_STAGES;   // [1]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3 * WG_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_tile = blockIdx.x % p.m_tiles, sp = blockIdx.x / p.m_tiles;
+    const int s_beg = sp * p.slabs_per_split;
+    const int s_end = (s_beg + p.slabs_per_split < p.total_slabs) ? s_beg + p.slabs_per_split : p.total_slabs;
+    const int n_slabs = s_end > s_beg ? s_end - s_beg : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(split + i, WG_SPLIT_THREADS); mbar_init(empty + i, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < n_slabs; ++i) {
+                const int st = i % WG_STAGES;
+                const unsigned ph = (i / WG_STAGES) & 1;
+                mbar_wait(empty + st, ph ^ 1);
+                unsigned char* sm = base + st * WG_STAGE_BYTES;
+                const int s = s_beg + i, b = s / p.slabs_per_seq, t0 = (s % p.slabs_per_seq) * BK;
+                mbar_expect_tx(full + st, WG_RAW_A + WG_RAW_B);
+                tma_load_3d(sm, &mapG, m_tile * BM, t0, b, full + st);           // frames past the sequence end: zero fill
+                tma_load_3d(sm + WG_RAW_A, &mapX, 0, t0, b, full + st);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr unsigned idesc = make_idesc(true);
+        for (int i = 0; i < n_slabs; ++i) {
+            const int st = i % WG_STAGES;
+            const unsigned ph = (i / WG_STAGES) & 1;
+            mbar_wait(split + st, ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const unsigned sa = s32(base + st * WG_STAGE_BYTES) + WG_RAW_A + WG_RAW_B;
+                const unsigned long long a_hi = smem_desc<32>(sa), a_lo = smem_desc<32>(sa + ABF_BYTES);
+                const unsigned long long b_hi = smem_desc<32>(sa + 2 * ABF_BYTES), b_lo = smem_desc<32>(sa + 2 * ABF_BYTES + WBF_BYTES);
+                umma_f16(tmem_base, a_hi, b_hi, idesc, i != 0);
+                umma_f16(tmem_base, a_lo, b_hi, idesc, 1);
+                umma_f16(tmem_base, a_hi, b_lo, idesc, 1);
+                umma_commit(empty + st);
+                if (i == n_slabs - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------------------- splitter (256 threads), then epilogue
+        const int stid = tid - 64;
+        for (int i = 0; i < n_slabs; ++i) {
+            const int st = i % WG_STAGES;
+            const unsigned ph = (i / WG_STAGES) & 1;
+            mbar_wait(full + st, ph);
+            unsigned char* sm = base + st * WG_STAGE_BYTES;
+            const float* rawA = reinterpret_cast<const float*>(sm);
+            const float* rawB = reinterpret_cast<const float*>(sm + WG_RAW_A);
+            unsigned char* tiles = sm + WG_RAW_A + WG_RAW_B;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                // groups 0..255: A (128 channels x 2 halves of 8 frames); groups 256..767: B (256 channels x 2 halves)
+                const int g = stid + WG_SPLIT_THREADS * j;
+                const bool isA = g < 2 * BM;
+                const int gg = isA ? g : g - 2 * BM;
+                const int nch = isA ? BM : BN;
+                const int ch = gg % nch, half = gg / nch;
+                const float* src = (isA ? rawA : rawB) + (half * 8) * nch + ch;
+                float x[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = src[k * nch];
+                unsigned hv[4], lv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+                    const float2 hf = __bfloat1622float2(h);
+                    const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
+                    hv[k] = *reinterpret_cast<const unsigned*>(&h);
+                    lv[k] = *reinterpret_cast<const unsigned*>(&l);
+                }
+                // K-major tile, 32-byte rows (16 bf16), 32B swizzle: 16-byte chunk `half` of row `ch` sits at half ^ ((ch>>2)&1)
+                const unsigned off = (unsigned)ch * 32u + ((unsigned)(half ^ ((ch >> 2) & 1)) << 4);
+                unsigned char* hi_t = tiles + (isA ? 0 : 2 * ABF_BYTES);
+                unsigned char* lo_t = hi_t + (isA ? ABF_BYTES : WBF_BYTES);
+                *reinterpret_cast<uint4*>(hi_t + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<uint4*>(lo_t + off) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(split + st);
+        }
+        // epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (= rows of the n tile); warps 2-5 take columns [0,128), 6-9 [128,256)
+        const int q = warp & 3, grp = (warp - 2) >> 2;
+        const int n = m_tile * BM + q * 32 + lane;
+        float* out = p.work + ((size_t)sp * p.N + n) * p.C;
+        if (n_slabs > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(out + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        } else {
+            for (int c = grp * 128; c < grp * 128 + 128; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ work, float* __restrict__ dw, int N, int C, int splits,
+                                       long long n_stride, long long c_stride) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * C) return;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += work[(size_t)k * N * C + idx];
+    const int n = idx / C, c = idx - n * C;
+    dw[n * n_stride + c * c_stride] = s;
+}
+
+// raw (B, rows, ld) fp32 rows as a 3D map {channels, rows, B}, box {box_ch, 16, 1}, no swizzle, zero fill past `rows`
+static int make_rows_map(CUtensorMap* m, const float* base, int channels, int rows, int B, int ld, long long seq, int box_ch) {
+    EncodeTiledFn fn = encode_fn();
+    WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)seq * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_ch, BK, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(wgrad rows) failed with %d", (int)r);
+    return 0;
+}
+
 }  // namespace tc
 }  // namespace wn
 
@@ -845,6 +1025,51 @@ extern "C" int wn_tc_block_bwd_data_prec(const wn_block_bwd_args* a, const void*
 extern "C" int wn_tc_convert_weights_bf16(const float* d_pairs, void* d_out, long long n_per_half, void* stream) {
     WN_REQUIRE(d_pairs && d_out && n_per_half > 0, WN_E_BADARG, "wn_tc_convert_weights_bf16: null pointer or empty array");
     tc::convert_bf16_kernel<<<512, 256, 0, (cudaStream_t)stream>>>(d_pairs, (__nv_bfloat16*)d_out, n_per_half);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Tensor-core form of wn_wgrad (same argument block and workspace): C must be 256 and N a multiple of 128, pitches and
+// strides multiples of 4 floats, pointers 16-byte aligned; bf16-pair split, fp32 accumulation.
+extern "C" int wn_tc_wgrad_supported(int N, int C) { return C == tc::BN && N > 0 && N % tc::BM == 0; }
+
+extern "C" int wn_tc_wgrad(const wn_wgrad_args* a, void* stream) {
+    WN_REQUIRE(a != nullptr, WN_E_BADARG, "wn_tc_wgrad: null argument block");
+    WN_REQUIRE(wn_tc_wgrad_supported(a->N, a->C), WN_E_UNSUPP, "wn_tc_wgrad: needs C == 256 and N %% 128 == 0 (got N=%d C=%d)", a->N, a->C);
+    WN_REQUIRE(a->B > 0 && a->rows >= 1, WN_E_BADARG, "wn_tc_wgrad: bad sizes B=%d rows=%d", a->B, a->rows);
+    WN_REQUIRE(a->d_g && a->d_x && a->d_dw && a->d_work, WN_E_BADARG, "wn_tc_wgrad: null device pointer");
+    WN_REQUIRE(a->ldg >= a->N && a->ldx >= a->C && a->ldg % 4 == 0 && a->ldx % 4 == 0 && a->g_seq_stride % 4 == 0 &&
+                   a->x_seq_stride % 4 == 0 && (uintptr_t)a->d_g % 16 == 0 && (uintptr_t)a->d_x % 16 == 0,
+               WN_E_BADARG, "wn_tc_wgrad: pitches / strides must be multiples of 4 floats and pointers 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    tc::WgTcParams p;
+    p.N = a->N; p.C = a->C; p.work = a->d_work;
+    p.m_tiles = a->N / tc::BM;
+    p.slabs_per_seq = (a->rows + tc::BK - 1) / tc::BK;
+    const long long total = (long long)a->B * p.slabs_per_seq;
+    WN_REQUIRE(total < (1ll << 30), WN_E_UNSUPP, "wn_tc_wgrad: too many frames");
+    p.total_slabs = (int)total;
+    // the workspace holds wn_wgrad_workspace_bytes(N, C) = ceil(296 / (N/128 * C/128)) partials of N x C
+    const int max_splits = (296 + 2 * p.m_tiles - 1) / (2 * p.m_tiles);
+    int splits = sms / p.m_tiles;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > p.total_slabs / 4) splits = p.total_slabs / 4;
+    if (splits < 1) splits = 1;
+    p.slabs_per_split = (p.total_slabs + splits - 1) / splits;
+    splits = (p.total_slabs + p.slabs_per_split - 1) / p.slabs_per_split;
+    CUtensorMap mG, mX;
+    if (int rc = tc::make_rows_map(&mG, a->d_g, a->N, a->rows, a->B, a->ldg, a->g_seq_stride, tc::BM)) return rc;
+    if (int rc = tc::make_rows_map(&mX, a->d_x, a->C, a->rows, a->B, a->ldx, a->x_seq_stride, tc::BN)) return rc;
+    const size_t smem = 1024 + (size_t)tc::WG_STAGES * tc::WG_STAGE_BYTES + 256;
+    WN_CUDA(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::wgrad_tc_kernel<<<p.m_tiles * splits, tc::WG_THREADS, smem, st>>>(mG, mX, p);
+    WN_CUDA(cudaGetLastError());
+    const int total_out = a->N * a->C;
+    tc::wgrad_tc_reduce_kernel<<<(total_out + 255) / 256, 256, 0, st>>>(a->d_work, a->d_dw, a->N, a->C, splits, a->dw_n_stride,
+                                                                         a->dw_c_stride);
     WN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -106,6 +106,8 @@ SIGNATURES = {
     "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
     "wn_wgrad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "wn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "wn_tc_wgrad_supported": (C.c_int, [C.c_int, C.c_int]),
+    "wn_tc_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "wn_tc_bwd_supported": (C.c_int, [C.c_int] * 4),
     "wn_tc_pack_block_bwd_weights": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     "wn_tc_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -61,6 +61,7 @@ class _Runtime:
         self.block_mode = "auto"     # "auto": tensor-core blocks when the shape allows, "ffma": exact-fp32 SIMT, "tc"
         self.fast_tf32 = False       # opt-in single-pass TF32 blocks (~1e-3 on the logits: outside the parity bar)
         self.tc_precision = "bf16x2"  # tensor-core operand split: "tf32x3" (3xTF32) or "bf16x2" (bf16 pairs, 2x the MMA rate)
+        self.wgrad_mode = "tc"        # weight gradients: "tc" (tensor cores where the shape allows), "native" (fp32 FMA), "cublas"
 
     # ------------------------------------------------------------------ weights
     def _params(self):
@@ -285,8 +286,13 @@ class _Runtime:
         native.check(lib.wn_head_bwd_data(ctypes.byref(hb), stream), "head bwd")
         ds_start = L - OL
         rskip = torch.relu(skip[:, ds_start - plan.skip_start:, :])
-        # weight gradients: wn_wgrad (split-frames fp32 kernel, wgrad.cu) or, with wgrad_mode="cublas", torch einsums
-        native_wgrad = getattr(self, "wgrad_mode", "native") != "cublas"
+        # weight gradients: wgrad_mode "native" = wn_wgrad (split-frames fp32 FMA kernel, wgrad.cu); "tc" = wn_tc_wgrad
+        # (tensor cores, bf16 pairs) where the shape allows, else wn_wgrad; "cublas" = torch einsums (library GEMMs)
+        wgrad_mode = getattr(self, "wgrad_mode", "tc")
+        if wgrad_mode not in ("native", "tc", "cublas"):
+            raise ValueError(f"wgrad_mode must be 'native', 'tc' or 'cublas', not {wgrad_mode!r}")
+        native_wgrad = wgrad_mode != "cublas"
+        self.wgrad_tc_calls = 0
         if native_wgrad:
             wg_work = torch.empty(max(lib.wn_wgrad_workspace_bytes(n_, c_) for n_, c_ in
                                       ((Cc, E), (E, S), (S, D), (R, D), (2 * D, R))) // 4, **f32)
@@ -300,7 +306,12 @@ class _Runtime:
                 wa.ldg, wa.ldx, wa.g_seq_stride, wa.x_seq_stride = ldg, ldx, g_seq, x_seq
                 wa.rows, wa.N, wa.C = rows, N, C
                 wa.dw_n_stride, wa.dw_c_stride = (C * c_stride if n_stride is None else n_stride), c_stride
-                native.check(lib.wn_wgrad(ctypes.byref(wa), stream), "wgrad")
+                if (wgrad_mode == "tc" and rows >= 64 and lib.wn_tc_wgrad_supported(N, C) and ldg % 4 == 0 and ldx % 4 == 0
+                        and g_seq % 4 == 0 and x_seq % 4 == 0 and wa.d_g % 16 == 0 and wa.d_x % 16 == 0):
+                    native.check(lib.wn_tc_wgrad(ctypes.byref(wa), stream), "tc wgrad")
+                    self.wgrad_tc_calls += 1
+                else:
+                    native.check(lib.wn_wgrad(ctypes.byref(wa), stream), "wgrad")
 
             rskip = rskip.contiguous()
             gw2, gw1 = torch.empty(Cc, E, 1, **f32), torch.empty(E, S, 1, **f32)

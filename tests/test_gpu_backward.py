@@ -152,3 +152,43 @@ def test_wgrad_modes_agree(golden):
             assert np.abs(res["native"][k]).max() == 0, k
         else:
             assert np.abs(res["native"][k] - res["cublas"][k]).max() / scale < 1e-5, k
+
+
+@pytest.mark.parametrize("B,rows,N,ldg,ldx,k,j", [
+    (2, 3001, 512, 512, 256, 2, 1),         # the filter+gate shape: 4 row tiles, ragged last slab, strided scatter
+    (3, 100, 128, 136, 260, 1, 0),          # one row tile, pitched operands, few slabs per split
+    (1, 16, 256, 256, 256, 1, 0),           # a single slab
+    (5, 37, 256, 256, 256, 3, 2),           # sequences shorter than three slabs, zero fill at every sequence end
+])
+def test_wn_tc_wgrad_matches_float64_contraction(B, rows, N, ldg, ldx, k, j):
+    """wn_tc_wgrad (tensor cores, bf16 pairs) against the float64 contraction and against wn_wgrad."""
+    import ctypes, native
+    lib = native.lib()
+    C = 256
+    assert lib.wn_tc_wgrad_supported(N, C) and not lib.wn_tc_wgrad_supported(N, 128) and not lib.wn_tc_wgrad_supported(100, C)
+    gen = torch.Generator().manual_seed(7)
+    g_off, x_off = 4, 8
+    gbuf = torch.randn(g_off + B * (rows + 2) * ldg, generator=gen).cuda()
+    xbuf = torch.randn(x_off + B * (rows + 3) * ldx, generator=gen).cuda()
+    g_seq, x_seq = (rows + 2) * ldg, (rows + 3) * ldx
+    gv = gbuf[g_off:g_off + B * g_seq].view(B, rows + 2, ldg)[:, :rows, :N].double()
+    xv = xbuf[x_off:x_off + B * x_seq].view(B, rows + 3, ldx)[:, :rows, :C].double()
+    want = torch.einsum("btn,btc->nc", gv, xv).cpu().numpy()
+    work = torch.empty(lib.wn_wgrad_workspace_bytes(N, C) // 4, device="cuda")
+    outs = {}
+    for name, fn in (("tc", lib.wn_tc_wgrad), ("fma", lib.wn_wgrad)):
+        out = torch.full((N, C, k), 7.0, device="cuda")
+        a = native.WgradArgs()
+        a.d_g, a.d_x = gbuf.data_ptr() + 4 * g_off, xbuf.data_ptr() + 4 * x_off
+        a.d_dw, a.d_work = out.data_ptr() + 4 * j, work.data_ptr()
+        a.g_seq_stride, a.x_seq_stride, a.dw_n_stride, a.dw_c_stride = g_seq, x_seq, C * k, k
+        a.ldg, a.ldx, a.B, a.rows, a.N, a.C = ldg, ldx, B, rows, N, C
+        native.check(fn(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), name)
+        outs[name] = out.cpu().numpy()
+    assert rel_err(outs["fma"][:, :, j], want) < 1e-5
+    assert rel_err(outs["tc"][:, :, j], want) < 5e-5, rel_err(outs["tc"][:, :, j], want)
+    for jj in range(k):
+        if jj != j:
+            assert (outs["tc"][:, :, jj] == 7.0).all()
+    a.ldx = 258                                              # pitch not a multiple of 4 floats: rejected, not launched
+    assert lib.wn_tc_wgrad(ctypes.byref(a), None) < 0

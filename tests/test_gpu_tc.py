@@ -124,13 +124,14 @@ def test_tc_backward_matches_simt_backward_and_oracle():
     m = m.cuda()
     rt = m._runtime()
     grads = {}
-    for mode, prec in (("tc", "bf16x2"), ("tc3", "tf32x3"), ("ffma", "bf16x2")):
-        rt.block_mode, rt.tc_precision = mode[:2] if mode.startswith("tc") else mode, prec
+    for mode, prec, wgrad in (("tc", "bf16x2", "tc"), ("tc3", "tf32x3", "native"), ("ffma", "bf16x2", "native")):
+        rt.block_mode, rt.tc_precision, rt.wgrad_mode = mode[:2] if mode.startswith("tc") else mode, prec, wgrad
         m.zero_grad()
         F.cross_entropy(m.forward_indices(idx.cuda()), tgt.cuda()).backward()
         assert rt.last_bwd_mode == rt.block_mode
+        assert (rt.wgrad_tc_calls > 0) == (wgrad == "tc")        # tensor-core weight gradients ran iff asked for
         grads[mode] = {k: v.grad.detach().cpu().numpy().copy() for k, v in m.named_parameters()}
-    rt.block_mode, rt.tc_precision = "auto", "bf16x2"
+    rt.block_mode, rt.tc_precision, rt.wgrad_mode = "auto", "bf16x2", "tc"
     bad = []
     for k, v in p.items():
         want = np.zeros_like(grads["tc"][k]) if v.grad is None else v.grad.numpy()
