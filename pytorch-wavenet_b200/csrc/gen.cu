@@ -2136,8 +2136,12 @@ extern "C" int wn_gen_destroy(wn_gen_handle* h) {
 
 extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_launch_info: null handle");
-    if (grid) *grid = h->grid;
-    if (block) *block = GEN_NT;
+    // the kernel wn_gen_run would pick in the handle's current mode (same selection as in wn_gen_run)
+    const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
+    const bool cluster = (auto_cluster || h->mode == 4) && h->cluster_ok;
+    const bool fast = !cluster && (h->mode == 0 || h->mode == 3) && h->fast_ok;
+    if (grid) *grid = cluster ? h->shape.n_streams * CL : h->grid;
+    if (block) *block = (cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer warp
     if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
     return 0;
 }
