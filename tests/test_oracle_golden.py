@@ -169,3 +169,29 @@ def test_cfg2_shape_spot_check(golden):
 def test_mu_law_roundtrip():
     x = np.linspace(-1, 1, 41)
     assert np.allclose(O.mu_law_expansion(O.mu_law_encoding(x, 256), 256), x, atol=1e-12)
+
+
+def test_relu_tie_separation_helper_moves_only_two_biases():
+    """helpers.separate_head_relu_ties (used by the GPU backward tests): afterwards no head ReLU input of the case is within
+    the margin of zero, and nothing but the last skip bias and the end_conv_1 bias has changed."""
+    from helpers import separate_head_relu_ties
+    kw = dict(layers=2, blocks=2, dilation_channels=16, residual_channels=16, skip_channels=24, end_channels=20,
+              classes=256, output_length=40, kernel_size=2, bias=True)
+    spec = O.NetSpec(**kw)
+    p = O.init_params(spec, seed=3)
+    idx = torch.randint(0, 256, (2, 120), generator=torch.Generator().manual_seed(1))
+    x = O.one_hot(idx, 256)
+    # plant exact ties: a zero skip channel bias pattern would be luck, so force one pre-activation to ~0 via the bias
+    taps = {}
+    O.stack_direct(p, spec, x, taps)
+    p["end_conv_1.bias"][3] -= taps["pre1"][0, 3, -1]
+    taps1 = {}
+    O.stack_direct(p, spec, x, taps1)
+    assert float(taps1["pre1"][..., -40:].abs().min()) < 1e-6          # the planted tie is there
+    sep = separate_head_relu_ties(p, spec, x, 40, margin=2e-5)
+    changed = {k for k in p if not torch.equal(p[k], sep[k])}
+    assert changed and changed <= {"skip_convs.3.bias", "end_conv_1.bias"}
+    taps2 = {}
+    O.stack_direct({k: v.double() for k, v in sep.items()}, spec, x.double(), taps2)
+    assert float(taps2["skip"][..., -40:].abs().min()) >= 1.9e-5
+    assert float(taps2["pre1"][..., -40:].abs().min()) >= 1.9e-5
