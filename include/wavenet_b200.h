@@ -121,7 +121,8 @@ int wn_tc_block_fwd(const wn_tc_block_args* a, void* stream);
  * out_hi = bf16(x), out_lo = bf16(x - out_hi).  d_out: 4 * n_per_half bytes. */
 int wn_tc_convert_weights_bf16(const float* d_pairs, void* d_out, long long n_per_half, void* stream);
 /* Debug aid (WN_TC_TRACE=1): per-stage clock64 stamps of CTA 0 of the most recent tensor-core launch, 8 per stage:
- * producer before/after the empty wait, MMA warp before/after the operand wait and after issue, splitter start/end. */
+ * producer before/after the empty wait, MMA warp before/after the operand wait and after issue, splitter start/end
+ * (first splitter warp), end of the last splitter warp. */
 int wn_tc_read_trace(long long* host_out, int n);
 
 /* ---------------------------------------------------------------- (T) head

@@ -357,6 +357,7 @@ frames_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
                     if (p.dbg && blockIdx.x == 0 && it < 512 && st_tid == 0) p.dbg[it * 8 + 6] = clock64();
+                    if (p.dbg && blockIdx.x == 0 && it < 512 && warp == 9 && lane == 0) p.dbg[it * 8 + 7] = clock64();   // last splitter warp
                     mbar_arrive(split + st);
                 }
     } else if ((warp >= 4 && warp < 8) || warp >= 10) {

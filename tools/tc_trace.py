@@ -39,6 +39,7 @@ print(f"producer waiting for an empty stage       mean {prod_wait.mean():7.0f}")
 print(f"TMA issue -> full barrier (load latency)  mean {tma_to_full.mean():7.0f}  median {np.median(tma_to_full):7.0f}")
 print(f"splitter work incl. proxy fence           mean {split_work.mean():7.0f}")
 print(f"splitter start-to-start                   mean {np.diff(t[:, 5]).mean():7.0f}")
-print(f"splitter done -> MMA warp released        mean {split_to_mma.mean():7.0f}")
+print(f"splitter done -> MMA warp released        mean {split_to_mma.mean():7.0f}  median {np.median(split_to_mma):7.0f}")
+print(f"splitter warp 9 done - warp 2 done        mean {(t[:, 7] - t[:, 6]).mean():7.0f}  median {np.median(t[:, 7] - t[:, 6]):7.0f}")
 print(f"MMA warp waiting for operands             mean {mma_wait.mean():7.0f}")
 print(f"MMA warp issuing (MMAs + commits)         mean {mma_issue.mean():7.0f}")
