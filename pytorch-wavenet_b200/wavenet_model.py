@@ -1,9 +1,12 @@
 """WaveNetModel with the reference's constructor, attributes, state_dict and methods
 (reference wavenet_model.py), running its two hot paths on hand-written sm_100a CUDA kernels:
 
-* ``forward`` / ``wavenet``   -> start gather/GEMM, ONE fused kernel per residual block, fused head
-                                 (libwavenet_b200: wn_start_fwd_*, wn_block_fwd, wn_head_fwd)
-* ``generate_fast``           -> ONE persistent cooperative kernel for the whole sampling loop (wn_gen_run)
+* ``forward`` / ``wavenet``   -> start gather/GEMM, the residual blocks (256-channel nets: two tcgen05 launches per
+                                 block with bf16-pair operands, wn_tc_block_fwd; any other shape: ONE fused fp32 kernel
+                                 per block, wn_block_fwd), fused head (wn_start_fwd_*, wn_head_fwd)
+* ``loss.backward()``         -> wn_head_bwd_data, per block wn_tc_block_bwd_data_prec / wn_block_bwd_data for the data
+                                 gradients and wn_tc_wgrad / wn_wgrad for the weight gradients (a custom autograd node)
+* ``generate_fast``           -> ONE persistent kernel for the whole sampling loop (wn_gen_run)
 
 Host code is plumbing only (shape planning, buffer ownership, weight packing cache).  There is no eager /
 CPU fallback: tensors must live on a CUDA device and the native library must be built, otherwise the calls
@@ -252,7 +255,8 @@ class _Runtime:
     # ------------------------------------------------------------------ training-path backward
     def stack_backward(self, saved, dlogits):
         """Gradients of all parameters given d(loss)/d(logits) (B*out_len, classes).  Data gradients run on the
-        wn_*_bwd_data kernels; the weight gradients are plain GEMMs over the buffers those kernels produce.
+        wn_*_bwd_data kernels, the weight gradients on wn_tc_wgrad / wn_wgrad over the buffers those kernels produce
+        (bias gradients are row sums; the start-conv gradient is a scatter-add of dh over the input indices).
         Returns a dict name -> gradient tensor shaped like the parameter."""
         m, lib = self.model, native.lib()
         dev = self.device()
