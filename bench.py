@@ -415,7 +415,12 @@ def bench_train(args, world, rank):
         roof = {"kernel": "frames_gemm_tc<GATE> + frames_gemm_tc<RES_SKIP> (tcgen05, " +
                           ("kind::f16 on bf16 hi/lo pairs" if prec == "bf16x2" else "kind::tf32, 3xTF32") + ", one block = 2 launches)",
                 "bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
-                "traffic": None, "peak_source": tsrc, "launches_per_step": 2 * n_layers,
+                # dram__bytes_read+write of the two launches of one block from the ncu --set full capture
+                # profiles/prof_tc_block_r1_e.txt (layer of the cfg-3 forward, 3xTF32 variant: same activation traffic)
+                "traffic": 128.15e6 + 85.84e6 + 363.67e6 + 189.49e6,
+                "traffic_note": "per block (2 launches), ncu capture profiles/prof_tc_block_r1_e.txt; 1.67x the algorithmic "
+                                "bytes because z is written by the first launch and read back by the second",
+                "peak_source": tsrc, "launches_per_step": 2 * n_layers,
                 "avg_block_ms": block_ms / n_layers, "operand_split": prec,
                 "note": "achieved counts the algorithmic fp32 FLOPs once; fp32-class accuracy costs three MMAs per product "
                         f"(hi*hi + lo*hi + hi*lo) = {mma_per_flop} bf16-rate equivalents per FLOP with the {prec} split, so "
