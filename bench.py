@@ -492,6 +492,21 @@ def cpu_train_forward(B, threads):
     return B * TRAIN_L / dt
 
 
+def cpu_train_step(threads):
+    """frames/s of one forward + backward of the CPU port at B=1, L=16000 (autograd over the oracle; ~5 GB of host memory)."""
+    import torch.nn.functional as F
+    from oracle import wavenet_oracle as O
+    torch.set_num_threads(threads)
+    spec = O.NetSpec(**GEN_KW)
+    p = {k: v.requires_grad_(True) for k, v in O.init_params(spec, seed=0).items()}
+    idx = torch.randint(0, 256, (1, TRAIN_L), generator=torch.Generator().manual_seed(1234))
+    x = O.one_hot(idx, 256)
+    tgt = torch.randint(0, 256, (spec.output_length,), generator=torch.Generator().manual_seed(3))
+    t0 = time.perf_counter()
+    F.cross_entropy(O.forward(p, spec, x), tgt).backward()
+    return TRAIN_L / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference (oracle/) on the host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -546,6 +561,10 @@ def main():
             for th in sorted({min(8, threads), min(32, threads), threads}):
                 res[th] = cpu_train_forward(1, th)
             best = max(res, key=lambda k: res[k])
+            if "train_step" in train:
+                train["train_step"]["cpu_baseline"] = {
+                    "value": cpu_train_step(best), "unit": "frames/s", "cores": best, "kind": "port",
+                    "sample": "one forward + backward (torch autograd over the oracle port) at B=1, L=16000"}
             train["cpu_baseline"] = {"value": res[best], "unit": "frames/s", "cores": best, "kind": "port",
                                      "sample": "one no_grad forward of B=1, L=16000 one-hot input per thread setting (best kept): "
                                                + ", ".join(f"{k} threads: {v:.0f} frames/s" for k, v in res.items())}
