@@ -120,3 +120,27 @@ def test_no_cpu_fallback():
         m.generate_fast(4)
     with pytest.raises(NotImplementedError):
         m.generate(4)
+
+
+def test_shape_predicates_and_workspace_sizes_are_host_side():
+    """The capability predicates and the workspace query need no device; argument errors are reported before any launch."""
+    import ctypes
+    import native
+    lib = native.lib()
+    assert lib.wn_tc_supported(256, 256, 256, 2) and lib.wn_tc_supported(512, 512, 512, 2)
+    assert not lib.wn_tc_supported(32, 32, 256, 2) and not lib.wn_tc_supported(256, 64, 256, 2)
+    assert lib.wn_tc_bwd_supported(256, 256, 256, 2) and not lib.wn_tc_bwd_supported(256, 128, 256, 2)
+    assert lib.wn_tc_wgrad_supported(512, 256) and lib.wn_tc_wgrad_supported(128, 256)
+    assert not lib.wn_tc_wgrad_supported(512, 512) and not lib.wn_tc_wgrad_supported(100, 256)
+    # split-frames workspace: ceil(296 / number of 128x128 output tiles) partials of N x C floats
+    assert lib.wn_wgrad_workspace_bytes(512, 256) == 37 * 512 * 256 * 4
+    assert lib.wn_wgrad_workspace_bytes(256, 256) == 74 * 256 * 256 * 4
+    assert lib.wn_wgrad_workspace_bytes(17, 5) == 296 * 17 * 5 * 4
+    assert lib.wn_wgrad_workspace_bytes(0, 5) == 0
+    a = native.WgradArgs()
+    a.N, a.C, a.B, a.rows = 0, 4, 1, 8
+    assert lib.wn_wgrad(ctypes.byref(a), None) < 0 and b"bad sizes" in lib.wn_last_error_string()
+    a.N, a.C = 512, 128
+    assert lib.wn_tc_wgrad(ctypes.byref(a), None) < 0 and b"C == 256" in lib.wn_last_error_string()
+    assert lib.wn_tc_block_bwd_data_prec(None, None, None, 0, None) < 0
+    assert lib.wn_tc_convert_weights_bf16(None, None, 0, None) < 0
