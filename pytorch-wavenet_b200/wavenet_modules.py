@@ -19,21 +19,24 @@ def dilate(x, dilation, init_dilation=1, pad_start=True):
     of f, then row j of the result takes every f-th column starting at j // N of input row j % N.
     Expressed as one reshape/permute of the padded tensor instead of two permute+contiguous passes.
     """
-    n, c, l = x.shape
-    factor = dilation / init_dilation
-    if factor == 1:
+    batch, chans, length = x.shape
+    ratio = dilation / init_dilation
+    if ratio == 1:
         return x
-    padded_l = int(np.ceil(l / factor) * factor)
-    if padded_l != l:
-        x = constant_pad_1d(x, padded_l, dimension=2, pad_start=pad_start)
-        l = padded_l
-    new_l = math.ceil(l * init_dilation / dilation)
-    new_n = math.ceil(n * dilation / init_dilation)
-    if factor > 1:
-        f = new_n // n                      # (n, c, new_l, f) -> (f, n, c, new_l): out[p*n + q, c, u] = x[q, c, u*f + p]
-        return x.reshape(n, c, new_l, f).permute(3, 0, 1, 2).reshape(new_n, c, new_l).contiguous()
-    f = n // new_n                          # inverse: out[q, c, u*f + p] = x[p*new_n + q, c, u]
-    return x.reshape(f, new_n, c, l).permute(1, 2, 3, 0).reshape(new_n, c, new_l).contiguous()
+    # pad the time axis to a whole number of folds
+    target = int(np.ceil(length / ratio) * ratio)
+    if target != length:
+        x = constant_pad_1d(x, target, dimension=2, pad_start=pad_start)
+        length = target
+    out_len = math.ceil(length * init_dilation / dilation)
+    out_batch = math.ceil(batch * dilation / init_dilation)
+    if ratio > 1:
+        fold = out_batch // batch           # out[p*batch + q, c, u] = x[q, c, u*fold + p]
+        y = x.reshape(batch, chans, out_len, fold).permute(3, 0, 1, 2)
+    else:
+        fold = batch // out_batch           # inverse: out[q, c, u*fold + p] = x[p*out_batch + q, c, u]
+        y = x.reshape(fold, out_batch, chans, length).permute(1, 2, 3, 0)
+    return y.reshape(out_batch, chans, out_len).contiguous()
 
 
 class DilatedQueue:
@@ -45,33 +48,29 @@ class DilatedQueue:
     """
 
     def __init__(self, max_length, data=None, dilation=1, num_deq=1, num_channels=1, dtype=torch.FloatTensor):
-        self.in_pos = 0
-        self.out_pos = 0
-        self.num_deq = num_deq
-        self.num_channels = num_channels
-        self.dilation = dilation
-        self.max_length = max_length
-        self.dtype = dtype
-        self.data = data
-        if data is None:
-            self.data = self._zeros()
+        self.max_length, self.num_channels, self.dtype = max_length, num_channels, dtype
+        self.dilation, self.num_deq = dilation, num_deq
+        self.in_pos = self.out_pos = 0
+        self.data = self._blank() if data is None else data
 
-    def _zeros(self):
+    def _blank(self):
         return torch.zeros(self.num_channels, self.max_length).type(self.dtype)
+
+    def _step(self, pos):
+        return (pos + 1) % self.max_length
 
     def enqueue(self, input):
         self.data[:, self.in_pos] = input.reshape(-1)
-        self.in_pos = (self.in_pos + 1) % self.max_length
+        self.in_pos = self._step(self.in_pos)
 
     def dequeue(self, num_deq=1, dilation=1):
-        cols = (self.out_pos - dilation * torch.arange(num_deq - 1, -1, -1)) % self.max_length
-        self.out_pos = (self.out_pos + 1) % self.max_length
-        return self.data[:, cols.to(self.data.device)]
+        taps = (self.out_pos - dilation * torch.arange(num_deq - 1, -1, -1)) % self.max_length
+        self.out_pos = self._step(self.out_pos)
+        return self.data[:, taps.to(self.data.device)]
 
     def reset(self):
-        self.data = self._zeros()
-        self.in_pos = 0
-        self.out_pos = 0
+        self.data = self._blank()
+        self.in_pos = self.out_pos = 0
 
 
 class ConstantPad1d(Function):
