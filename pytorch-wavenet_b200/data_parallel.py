@@ -51,8 +51,10 @@ def make_data_parallel(model, group=None):
     ``p.grad``.  Also broadcasts rank 0's parameters so that every replica starts from the same weights."""
     avg = GradientAverager(group)
     if avg.world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, src=0, group=group)
+        with torch.no_grad():
+            for p in model.parameters():
+                dist.broadcast(p, src=0, group=group)        # in place on the parameter itself: bumps its version counter
+    model._runtime().invalidate()                            # packed copies made before the broadcast are stale on rank > 0
     model._runtime().grad_reducer = avg
     return avg
 

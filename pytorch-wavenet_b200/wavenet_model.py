@@ -75,6 +75,13 @@ class _Runtime:
                     gate=[g(m.gate_convs[i]) for i in range(n)], res=[g(m.residual_convs[i]) for i in range(n)],
                     skip=[g(m.skip_convs[i]) for i in range(n)], end1=g(m.end_conv_1), end2=g(m.end_conv_2))
 
+    def invalidate(self):
+        """Forget the packed weight copies.  The cache is keyed on (data_ptr, tensor version); writes through ``p.data``
+        (the reference's optimizers.py:100, ``dist.broadcast(p.data)``) do not bump the version, so every backward and
+        make_data_parallel call this, and code that edits ``p.data`` by hand between no-grad forwards must too
+        (``model.invalidate_packed_weights()``)."""
+        self.pack_key = None
+
     def device(self):
         dev = self.model.start_conv.weight.device
         if dev.type != "cuda":
@@ -97,6 +104,10 @@ class _Runtime:
         if key == self.pack_key:
             return self.packed
         dev = self.device()
+        for name, p in m.named_parameters():
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError(f"wavenet_b200: parameter {name} must be a contiguous float32 tensor "
+                                   f"(got {p.dtype}, contiguous={p.is_contiguous()}); the kernels read raw fp32 memory")
         P = self._params()
         R, D, S = m.residual_channels, m.dilation_channels, m.skip_channels
         E, Cc, k = m.end_conv_1.out_channels, m.classes, m.kernel_size
@@ -500,6 +511,7 @@ class _Runtime:
         callbacks: optional list of (eval_index, fn) -- fn() is called once evaluations <= eval_index are done."""
         m = self.model
         dev = self.device()
+        self.step_session = None             # a generate_fast run restarts the device queues (wavenet_model.py:250)
         first = np.ascontiguousarray(first, dtype=np.int32)
         NS, n_given = first.shape
         if n_given < 1:
@@ -549,17 +561,23 @@ class _StackFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, out_len, index_input, *params):
         saved = {}
-        with torch.no_grad():
-            y = model._runtime().stack_forward(x, out_len, index_input=index_input, save=saved)
+        rt = model._runtime()
+        with torch.no_grad(), torch.cuda.device(rt.device()):
+            y = rt.stack_forward(x, out_len, index_input=index_input, save=saved)
         ctx.model, ctx.saved = model, saved
         ctx.names = [n for n, _ in model.named_parameters()]
         return y
 
     @staticmethod
     def backward(ctx, dlogits):
-        with torch.no_grad():
-            g = ctx.model._runtime().stack_backward(ctx.saved, dlogits)
+        if ctx.saved is None:
+            raise RuntimeError("wavenet_b200: the saved activations of this forward were freed by a previous backward "
+                               "(retain_graph=True is not supported: run the forward again)")
+        rt = ctx.model._runtime()
+        with torch.no_grad(), torch.cuda.device(rt.device()):
+            g = rt.stack_backward(ctx.saved, dlogits)
         ctx.saved = None
+        rt.invalidate()          # an optimizer step follows; it may write through p.data, which no version counter sees
         return (None, None, None, None) + tuple(g.get(n) for n in ctx.names)
 
 
@@ -639,6 +657,7 @@ class WaveNetModel(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_rt", None)               # device workspaces / native handles are not part of a snapshot
+        state.pop("_shadow", None)
         return state
 
     # ------------------------------------------------------------------ training-time path
@@ -665,7 +684,9 @@ class WaveNetModel(nn.Module):
             if input.requires_grad:
                 raise NotImplementedError("wavenet_b200: no gradient with respect to the input (it is one-hot data)")
             return _StackFunction.apply(self, input, out_len, index_input, *self.parameters())
-        return self._runtime().stack_forward(input, out_len, index_input=index_input)
+        rt = self._runtime()
+        with torch.cuda.device(rt.device()):       # native launches go to the CURRENT device: make it the model's
+            return rt.stack_forward(input, out_len, index_input=index_input)
 
     def forward(self, input):
         """(N, classes, L) -> (N * output_length, classes): logits of the last ``output_length`` frames."""
@@ -689,6 +710,27 @@ class WaveNetModel(nn.Module):
             first_samples = first_samples.detach().cpu().numpy()
         return np.asarray(first_samples).astype(np.int64).reshape(-1)
 
+    def _cuda_shadow(self):
+        """A CUDA copy of a CPU-resident model, refreshed when the parameters change.  The reference's own scripts
+        generate from a *CPU copy* of the model in a logging thread (train_script.py:48, model_logging.py:55-58); that
+        call lands here and still runs the persistent CUDA sampler -- only the weights are copied over."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("wavenet_b200: generate_fast needs a CUDA device (there is no CPU sampler)")
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        sh = self.__dict__.get("_shadow")
+        if sh is None or sh[0] != key:
+            twin = WaveNetModel(layers=self.layers, blocks=self.blocks, dilation_channels=self.dilation_channels,
+                                residual_channels=self.residual_channels, skip_channels=self.skip_channels,
+                                end_channels=self.end_conv_1.out_channels, classes=self.classes,
+                                output_length=self.output_length, kernel_size=self.kernel_size,
+                                bias=self.start_conv.bias is not None)
+            twin.load_state_dict(self.state_dict())
+            sh = (key, twin.cuda())
+            self.__dict__["_shadow"] = sh
+        else:
+            sh[1].load_state_dict(self.state_dict())       # cheap, and immune to writes through p.data
+        return sh[1]
+
     def generate_fast(self, num_samples, first_samples=None, temperature=1., regularize=0.,
                       progress_callback=None, progress_interval=100):
         """Fast-WaveNet sampling; returns the mu-law expanded waveform, float64 ndarray of ``num_samples`` values.
@@ -698,6 +740,15 @@ class WaveNetModel(nn.Module):
         numpy's GLOBAL RNG (one ``random_sample()`` per sample, which is what ``np.random.choice`` consumes), so
         ``np.random.seed(s)`` reproduces the reference's stream; ``temperature == 0`` takes the argmax.
         """
+        if self.start_conv.weight.device.type != "cuda":
+            twin = self._cuda_shadow()
+            audio = twin.generate_fast(num_samples, first_samples=first_samples, temperature=temperature,
+                                       regularize=regularize, progress_callback=progress_callback,
+                                       progress_interval=progress_interval)
+            for q, tq in zip(self.dilated_queues, twin.dilated_queues):
+                q.data, q.in_pos, q.out_pos = tq.data, tq.in_pos, tq.out_pos
+            self.train()
+            return audio
         self.eval()
         first = self._first_array(first_samples)
         num_given = first.shape[0]
@@ -710,7 +761,9 @@ class WaveNetModel(nn.Module):
             for i in range(num_samples):                                 # sampling loop, :309-311
                 if (i + num_given) % progress_interval == 0:
                     callbacks.append((num_given - 1 + i, lambda i=i: progress_callback(i + num_given, total)))
-        idx, _, _ = self._runtime().generate(num_samples, first[None, :], temperature, regularize, callbacks=callbacks)
+        rt = self._runtime()
+        with torch.cuda.device(rt.device()):
+            idx, _, _ = rt.generate(num_samples, first[None, :], temperature, regularize, callbacks=callbacks)
         self._export_queues()
         self.train()
         generated = (idx[0] / self.classes) * 2. - 1
@@ -726,8 +779,10 @@ class WaveNetModel(nn.Module):
         self.eval()
         first = np.asarray(first_samples.detach().cpu().numpy() if torch.is_tensor(first_samples) else first_samples)
         first = first.astype(np.int64).reshape(first.shape[0], -1) if first.ndim > 1 else first.astype(np.int64)[None, :]
-        idx, logits, _ = self._runtime().generate(num_samples, first, temperature, regularize, uniforms=uniforms,
-                                                  forced=forced, want_logits=return_logits)
+        rt = self._runtime()
+        with torch.cuda.device(rt.device()):
+            idx, logits, _ = rt.generate(num_samples, first, temperature, regularize, uniforms=uniforms,
+                                         forced=forced, want_logits=return_logits)
         self._export_queues()
         self.train()
         return (idx, logits) if return_logits else idx
@@ -746,8 +801,56 @@ class WaveNetModel(nn.Module):
             off += n
 
     def _queue_step(self, input):
-        raise NotImplementedError("wavenet(input, queue_dilate): drive the sampler through generate_fast / "
-                                  "generate_fast_batch (forced=...) instead")
+        """``wavenet(input, self.queue_dilate)`` (reference wavenet_model.py:177-184, the body of generate_fast's loops):
+        push the one-hot column(s) of ``input`` (1, classes, n) through the cached queues, one evaluation of the
+        persistent sampler kernel each, and return the logits of the last column as (1, classes, 1).  The device rings
+        are the queue state; a new session starts when every ``dilated_queues[i].reset()`` has been called since the
+        last step (what generate_fast does first, wavenet_model.py:250), or on the first call."""
+        rt = self._runtime()
+        dev = rt.device()
+        if input.dim() != 3 or input.size(0) != 1 or input.size(1) != self.classes:
+            raise RuntimeError(f"queue_dilate handles a single stream: input must be (1, {self.classes}, n), "
+                               f"got {tuple(input.shape)} (the reference enqueues input.data[0] only)")
+        col = input.detach().to(dev, torch.float32)[0]                        # (classes, n)
+        idx = col.argmax(0)
+        if not bool(((col.max(0).values == 1) & (col.sum(0) == 1) & (col.min(0).values == 0)).all()):
+            raise NotImplementedError("wavenet(input, queue_dilate) needs one-hot columns (the sampler gathers the "
+                                      "start_conv column of the sample index)")
+        ses = rt.__dict__.get("step_session")
+        with torch.cuda.device(dev):
+            if ses is None or all(getattr(q, "was_reset", False) for q in self.dilated_queues) \
+                    or ses["sampler"] is not rt.samplers.get(1):
+                s = rt.sampler(1)
+                native.check(native.lib().wn_gen_reset(s["handle"], torch.cuda.current_stream(dev).cuda_stream), "gen reset")
+                ses = dict(sampler=s, t=0, inp=torch.zeros(1, dtype=torch.int32, device=dev),
+                           out=torch.zeros(1, dtype=torch.int32, device=dev),
+                           logits=torch.zeros(self.classes, dtype=torch.float32, device=dev))
+                rt.step_session = ses
+                for q in self.dilated_queues:
+                    q.was_reset = False
+            lib, stream = native.lib(), torch.cuda.current_stream(dev).cuda_stream
+            for j in range(col.size(1)):
+                t = ses["t"]
+                ses["inp"].copy_(idx[j:j + 1].to(torch.int32))
+                a = native.GenRunArgs()
+                # schedule "1 given sample, t+1 samples": evaluation t reads first[0] (t == 0) or forced[t-1] and writes
+                # sample t; the buffers hold ONE element each, so the pointers are biased to put element t at their start
+                a.d_first, a.n_given = ses["inp"].data_ptr(), 1
+                a.d_forced = ses["inp"].data_ptr() - 4 * (t - 1) if t > 0 else None
+                a.d_uniforms = None
+                a.d_out_idx = ses["out"].data_ptr() - 4 * t
+                a.d_out_logits = ses["logits"].data_ptr() - 4 * self.classes * t
+                a.n_samples, a.t0, a.n_evals = t + 1, t, 1
+                a.temperature, a.regularize = 0.0, 0.0
+                native.check(lib.wn_gen_run(ses["sampler"]["handle"], ctypes.byref(a), stream), "gen run (queue step)")
+                ses["t"] = t + 1
+            rt.last_run = dict(evals=ses["t"], sampler=ses["sampler"])
+        self._export_queues()
+        return ses["logits"].clone().view(1, self.classes, 1)
+
+    def invalidate_packed_weights(self):
+        """Call after writing parameters through ``p.data`` outside a training step (see _Runtime.invalidate)."""
+        self._runtime().invalidate()
 
     # ------------------------------------------------------------------ utilities (reference wavenet_model.py:318-346)
     def parameter_count(self):

@@ -71,6 +71,7 @@ class DilatedQueue:
     def reset(self):
         self.data = self._blank()
         self.in_pos = self.out_pos = 0
+        self.was_reset = True          # WaveNetModel.wavenet(x, queue_dilate) restarts its device session when all queues say so
 
 
 class ConstantPad1d(Function):

@@ -109,3 +109,29 @@ def test_full_size_properties_cfg3():
         m.output_length = 64
         x = one_hot_cuda(idx[:2].numpy())
         assert torch.equal(m(x), m.forward_indices(idx[:2].cuda()))
+
+
+def test_cfg3_full_size_vs_oracle():
+    """The benchmarked shape itself against the CPU oracle: cfg-3 net (10x5 layers, 256 ch), one L=16000 sequence,
+    output_length = 10885, default (tensor-core) blocks; then B=8 where every row must equal its B=1 run bit for bit."""
+    import wavenet_model as wmod
+    kw = dict(layers=10, blocks=5, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=16000 - 5116 + 1, kernel_size=2, bias=False)
+    torch.manual_seed(0)
+    m = wmod.WaveNetModel(**kw)
+    spec = O.NetSpec(**kw)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    idx = torch.randint(0, 256, (8, 16000), generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        want = O.forward(p, spec, O.one_hot(idx[3:4], 256)).numpy()           # ~2 s of CPU
+    m = m.cuda()
+    rt = m._runtime()
+    with torch.no_grad():
+        y1 = m.forward_indices(idx[3:4].cuda())
+        assert rt.last_block_mode == "tc"
+        err = rel_err(y1.cpu().numpy(), want)
+        assert err < TOL, f"cfg3 full size vs oracle: {err:.3e}"
+        y8 = m.forward_indices(idx.cuda()).view(8, -1, 256)
+        assert torch.equal(y8[3], y1.view(-1, 256))
+        y0 = m.forward_indices(idx[0:1].cuda())
+        assert torch.equal(y8[0], y0.view(-1, 256))

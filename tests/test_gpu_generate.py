@@ -82,8 +82,14 @@ def test_generate_cfg2_net(golden):
                                   uniforms=g["gen_sample_uniforms"][None, :], forced=g["gen_sample_idx"][None, :],
                                   return_logits=True)
     assert rel_err(lg[0], g["gen_sample_logits"]) < TOL
-    agree = int((got == g["gen_sample_idx"]).sum())
-    assert agree >= 40, f"only {agree}/48 sampled indices agree"      # near-uniform logits: CDF edges are dense
+    # the free-running sampled stream: identical, or it parts ways at a draw whose uniform lies within float noise of
+    # a CDF edge of the reference's own distribution (the classification used for the small nets above)
+    if not np.array_equal(got, g["gen_sample_idx"]):
+        i = int(np.nonzero(got != g["gen_sample_idx"])[0][0])
+        lg64 = g["gen_sample_logits"][i].astype(np.float64)
+        pr = np.exp(lg64 - lg64.max()); pr /= pr.sum()
+        edge = np.abs(np.cumsum(pr) - g["gen_sample_uniforms"][i]).min()
+        assert edge < 1e-5, f"sampled stream diverges at step {i}, {edge:.3e} away from the nearest CDF edge"
 
 
 def test_streams_are_independent_and_bitwise_reproducible(golden):
@@ -215,3 +221,70 @@ def test_cluster_kernel_cfg2(golden):
                         progress_interval=9)
     b = m.generate_fast(40, first_samples=first[0], temperature=0.0)
     assert np.array_equal(a, b) and len(calls) > 3
+
+
+def test_cfg4_64_streams_vs_oracle(golden):
+    """cfg 4: 64 independent streams of the cfg-2 net in one launch.  The reference has no batch dimension in its queues
+    (wavenet_model.py:179), so the oracle is 64 single-stream runs: teacher-forced per-step logits of EVERY stream within
+    1e-4, and the free-running argmax streams bit-exact up to a reference near-tie."""
+    g = golden("net_cfg2.npz")
+    m = build_model(g)
+    from helpers import spec_from_golden
+    spec, p = spec_from_golden(g), params_from_golden(g)
+    if not p:
+        p = O.init_params(spec, seed=0)
+    NS, n = 64, 32
+    rng = np.random.RandomState(21)
+    firsts = rng.randint(0, 256, size=(NS, 2))
+    torch.set_num_threads(min(8, torch.get_num_threads()))
+    refs = [O.generate_fast(p, spec, n, first_samples=firsts[s], temperature=0.0, keep_logits=True) for s in range(NS)]
+    ref_idx = np.stack([r.indices for r in refs])
+    ref_lg = np.stack([r.logits for r in refs])
+    _, lg = m.generate_fast_batch(n, firsts, temperature=0.0, forced=ref_idx, return_logits=True)
+    errs = [rel_err(lg[s], ref_lg[s]) for s in range(NS)]
+    assert max(errs) < TOL, f"worst stream {int(np.argmax(errs))}: {max(errs):.3e}"
+    idx = m.generate_fast_batch(n, firsts, temperature=0.0)
+    for s in range(NS):
+        assert_stream_parity(idx[s], ref_idx[s], ref_lg[s])
+    assert len({tuple(r) for r in idx.tolist()}) > 1
+
+
+def test_wavenet_queue_dilate_single_steps(golden):
+    """``model.wavenet(x, model.queue_dilate)`` (reference wavenet_model.py:177-184, :262, :277): one evaluation per one-hot
+    column on the device-resident queues; the sequence of returned logits equals the teacher-forced generate_fast run."""
+    g = golden("net_odd_bias.npz")
+    m = build_model(g)
+    first = g["first"]
+    seq = np.concatenate([first, g["gen_argmax_idx"][:-1]])             # inputs of all evaluations of the golden run
+    for q in m.dilated_queues:
+        q.reset()
+    outs = []
+    for i, s in enumerate(seq):
+        x = torch.zeros(1, 256, 1, device="cuda")
+        x[0, int(s), 0] = 1.0
+        y = m.wavenet(x, dilation_func=m.queue_dilate)
+        assert y.shape == (1, 256, 1)
+        if i >= len(first) - 1:
+            outs.append(y[0, :, 0].cpu().numpy())
+    assert rel_err(np.stack(outs), g["gen_argmax_logits"]) < TOL
+    assert m.dilated_queues[0].in_pos == len(seq) % m.dilated_queues[0].max_length
+    # several columns in one call, after a reset: same state as column by column
+    for q in m.dilated_queues:
+        q.reset()
+    x = torch.zeros(1, 256, len(first), device="cuda")
+    x[0, torch.from_numpy(first).long().cuda(), torch.arange(len(first)).cuda()] = 1.0
+    y = m.wavenet(x, dilation_func=m.queue_dilate)
+    assert rel_err(y[0, :, 0].cpu().numpy(), g["gen_argmax_logits"][0]) < TOL
+    with pytest.raises(NotImplementedError):
+        m.wavenet(torch.rand(1, 256, 1, device="cuda"), dilation_func=m.queue_dilate)
+
+
+def test_generate_fast_from_cpu_model(golden):
+    """The reference's training script samples from a CPU copy of the model (train_script.py:48): that call must work and
+    give the same stream as the CUDA model (it runs the same sampler on a CUDA shadow of the weights)."""
+    g = golden("net_cfg1.npz")
+    m_cpu = build_model(g, device="cpu")
+    a = m_cpu.generate_fast(24, first_samples=g["first"], temperature=0.0)
+    b = build_model(g).generate_fast(24, first_samples=g["first"], temperature=0.0)
+    assert np.array_equal(a, b) and m_cpu.start_conv.weight.device.type == "cpu"
+    assert m_cpu.dilated_queues[0].data.shape[0] == m_cpu.residual_channels

@@ -145,3 +145,36 @@ def test_tc_backward_matches_simt_backward_and_oracle():
         if not (e_f < 1e-4 and e_t < 1e-4 and e_tf < 1e-4):
             bad.append((k, float(scale), float(e_f), float(e_t), float(e_tf)))
     assert not bad, bad[:12]
+
+
+def test_packed_weights_follow_parameter_writes():
+    """the packed-weight cache is keyed on tensor versions, which writes through ``p.data`` do not bump (the
+    reference's optimizers.py:100 updates that way).  A backward invalidates the cache; so does the explicit call."""
+    import torch.nn.functional as F
+    import wavenet_model as wmod
+    kw = dict(layers=2, blocks=1, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=32, kernel_size=2, bias=False)
+    torch.manual_seed(3)
+    m = wmod.WaveNetModel(**kw).cuda()
+    idx = torch.randint(0, 256, (1, 200), generator=torch.Generator().manual_seed(1)).cuda()
+    tgt = torch.randint(0, 256, (32,), generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        y0 = m.forward_indices(idx).clone()
+    w = m.residual_convs[0].weight
+    # (1) a training step whose "optimizer" writes through .data, then a no-grad forward (train -> validate)
+    F.cross_entropy(m.forward_indices(idx), tgt).backward()
+    w.data.mul_(1.5)
+    with torch.no_grad():
+        y1 = m.forward_indices(idx).clone()
+    assert not torch.equal(y1, y0)
+    # (2) a hand edit between no-grad forwards needs the explicit invalidate
+    w.data.mul_(1.0 / 1.5)
+    m.invalidate_packed_weights()
+    with torch.no_grad():
+        y2 = m.forward_indices(idx)
+    assert rel_err(y2.cpu().numpy(), y0.cpu().numpy()) < 1e-5
+    # (3) a second backward through a freed graph raises a clear error
+    loss = F.cross_entropy(m.forward_indices(idx), tgt)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="saved activations"):
+        loss.backward()
