@@ -125,6 +125,42 @@ int wn_tc_convert_weights_bf16(const float* d_pairs, void* d_out, long long n_pe
  * (first splitter warp), end of the last splitter warp. */
 int wn_tc_read_trace(long long* host_out, int n);
 
+/* ---------------------------------------------------------------- (T) the block as ONE tensor-core launch (round 2 default)
+ * Same mathematics as wn_block_fwd (reference wavenet_model.py:142-165) for R = D = S = 256, k = 2 (wn_tb_supported), with
+ * fp32-class accuracy from bf16 (hi, lo) operand pairs on tcgen05.mma cta_group::2 (fp32 accumulation in tensor memory); the
+ * gated activation z never leaves the SM.  Activations use the CHUNKED PAIR LAYOUT: a (B, L, C) activation is stored as
+ *     bf16 [b][plane: 0 = hi, 1 = lo][c / 8][t][c % 8]         x = hi + lo, hi = bf16(x), lo = bf16(x - hi)
+ * (the same number of bytes as fp32 frames), and skip as fp32 [b][c / 4][t - skip_start][c % 4].  wn_pair_from_frames /
+ * wn_frames_from_pair / wn_frames_from_chunks4 convert to and from the frames layout of the other entry points.
+ * Weights: wn_tb_pack_block_weights writes one layer's pre-split, pre-tiled image (wn_tb_weight_bytes_per_layer() bytes) and
+ * its four bias vectors [bf | bg | br | bs] (4*256 floats); all layers live in ONE array d_w_all [n_layers][bytes_per_layer].
+ * wn_tb_start_index_* is start_conv on class indices (wavenet_model.py:65-68,127) writing that layout; *d_err (optional) is
+ * set to 1 when an index is outside [0, classes) -- the reference's one-hot scatter would raise there. */
+int    wn_tb_supported(int R, int D, int S, int k);
+size_t wn_tb_weight_bytes_per_layer(void);
+int    wn_tb_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
+                                const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
+                                void* d_w_layer, float* d_bias4, void* stream);
+int    wn_tb_start_index_u8(const uint8_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair,
+                            int B, int classes, int L, int R, int* d_err, void* stream);
+int    wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair,
+                             int B, int classes, int L, int R, int* d_err, void* stream);
+int    wn_pair_from_frames(const float* d_frames, void* d_pair, int B, int L, int C, int t_begin, void* stream);
+int    wn_frames_from_pair(const void* d_pair, float* d_frames, int B, int L, int C, int t_begin, void* stream);
+/* frames [t_first, t_first + n) of a chunked fp32 tensor (B, C/4, T, 4) -> (B, n, C) */
+int    wn_frames_from_chunks4(const float* d_chunked, float* d_frames, int B, int T, int C, int t_first, int n, void* stream);
+typedef struct wn_tb_block_args {
+    const void* d_h_in; void* d_h_out;     /* chunked pairs (B, 2, 32, L, 8) bf16                                   */
+    float* d_skip;                         /* chunked (B, 64, L - skip_start, 4) fp32                               */
+    const void* d_w_all; const float* d_bias4;   /* all layers' packed weights; THIS layer's biases               */
+    int layer, n_layers;
+    int B, L, dilation;
+    int in_start, out_start, skip_start, skip_init;
+    float* d_fg_save;                      /* optional chunked (B, 128, L, 4) fp32: tanh | sigmoid outputs (for the backward) */
+    void* d_z_save;                        /* optional chunked pair (B, 2, 32, L, 8): z = tanh * sigmoid             */
+} wn_tb_block_args;
+int    wn_tb_block_fwd(const wn_tb_block_args* a, void* stream);
+
 /* ---------------------------------------------------------------- (T) head
  * replaces relu -> end_conv_1 -> relu -> end_conv_2 (wavenet_model.py:167-169) and forward()'s
  * slice/transpose/view (:191-196): logits (B*out_len, classes) for the LAST out_len frames only.

@@ -1,0 +1,610 @@
+// tc_block.cu -- the training-time residual block (reference wavenet_model.py:142-165) as ONE tensor-core kernel per layer.
+//
+//   z[t]     = tanh(Wf0 h[t-d] + Wf1 h[t] + bf) * sigmoid(Wg0 h[t-d] + Wg1 h[t] + bg)          (h[t] = 0 left of in_start)
+//   h_out[t] = Wr z[t] + br + h[t]                                                             t in [out_start, L)
+//   skip[t]  (+)= Ws z[t] + bs                                                                 t in [skip_start, L)
+//
+// Numerics: fp32-class through bf16 PAIRS -- every operand x is carried as hi = bf16(x), lo = bf16(x - hi) and a product is
+// hi*hi + lo*hi + hi*lo on tcgen05 kind::f16 with fp32 accumulation in tensor memory (16 mantissa bits per operand; measured
+// 6.5e-6 on the logits of the 50-layer cfg-2/3 net, tools/split_sim.py; the parity bar is 1e-4).
+//
+// Data layout ("chunked pair layout"): an activation tensor of C channels over L frames is stored as
+//   [sequence b][plane: hi, lo][channel chunk c/8][frame t][8 channels] bf16            (same bytes as fp32 (B,L,C))
+// so that  (1) a TMA box {128 frames, 4 chunks, 2 planes} lands in shared memory exactly as the SWIZZLE_NONE K-major
+// core-matrix image tcgen05 consumes ([k-chunk][row][16 B], LBO = 2048, SBO = 128): no splitter, no swizzle, no conflicts;
+//          (2) an epilogue thread (= one frame, tcgen05.ld 32x32b) reads/writes 16-byte pieces that are CONTIGUOUS across the
+// lanes of its warp (consecutive frames): fully coalesced global accesses with no shared-memory transpose;
+//          (3) the same image is the MN-major operand of the weight-gradient GEMM (contraction over frames).
+// skip is [b][channel chunk c/4][frame][4 channels] fp32 for the same reason.  Weights are pre-split and pre-tiled into the
+// shared-memory image of every (n-tile, k-slab, CTA half), so a weight slab is one contiguous 16 KB TMA box.
+//
+// Kernel: clusters of 2 CTAs (one per SM of a TPC), cta_group::2 MMAs M256 N256 K16: CTA r owns frames t0+128r..+127 of a
+// 256-frame item (its A rows, its 128 accumulator lanes) and stages half of every weight slab (its 128 of the 256 B rows).
+//   warp 0      TMA producer (both CTAs): ring of six 16 KB slots; a k-slab of pass A = one activation slot (32 channels of
+//               one tap, hi+lo) + one weight slot; pass B = weight slots only (its A operand z is resident)
+//   warp 1      tensor memory (512 columns = two 256-column accumulators) and, in the leader CTA, the MMA issue loop
+//   warps 2-9   epilogue: two groups x four TMEM lane quadrants
+// Per item the MMA warp runs  A0 -> acc0, A1 -> acc1  (filter|gate of channels 0..127 / 128..255, K = 2 taps x 256),
+// B0 -> acc0 (residual), B1 -> acc1 (skip; skipped for items left of skip_start).  The gate epilogue writes z as a bf16 pair
+// image into shared memory (128 KB: the A operand of pass B never leaves the SM) and signals it per 32-channel slab, so pass
+// B starts on the first slabs while the rest of the gate is still being computed.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace wn {
+namespace tb {
+using namespace px;
+
+constexpr int CH = 256;                   // residual = dilation = skip channels
+constexpr int BM = 128;                   // frames per CTA
+constexpr int PM = 256;                   // frames per item (CTA pair)
+constexpr int KS = 32;                    // channels per k-slab
+constexpr int SLOT = 16384;               // one ring slot: [plane 2][chunk 4][row 128][16 B]
+constexpr int NSLOT = 6;
+constexpr int ZPLANE = 65536;             // z image: [plane 2][chunk 32][row 128][16 B]
+constexpr int NTHREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr unsigned LBO = BM * 16, SBO = 128;
+constexpr int SLABS_A = 2 * CH / KS;      // 16 k-slabs per pass-A n-tile (2 taps)
+constexpr int SLABS_B = CH / KS;          // 8 k-slabs per pass-B n-tile
+constexpr int WROWS_A = 2 * SLABS_A * 2 * 8;      // 2 KB rows of the packed pass-A weights of one layer (512)
+constexpr int WROWS_LAYER = WROWS_A + 2 * SLABS_B * 2 * 8;      // 768
+constexpr size_t W_LAYER_BYTES = (size_t)WROWS_LAYER * 2048;    // 1.5 MB
+constexpr size_t SMEM_BYTES = 128 + 2 * ZPLANE + NSLOT * SLOT + 256;
+
+struct BlockParams {
+    int B, L, t_begin, in_start, skip_start, skip_init, dil;
+    int tiles_per_seq, n_items;
+    int w_row0;                    // first 2 KB row of this layer in the packed weight array
+    const float* bias;             // [bf 256 | bg 256 | br 256 | bs 256]
+    const uint4* h_in;             // chunked pair (B, 2, 32, L, 8) bf16, viewed as 16-byte pieces
+    uint4* h_out;
+    float4* skip;                  // chunked (B, 64, L - skip_start, 4) fp32
+    float4* fg_save;               // optional chunked (B, 128, L, 4) fp32: tanh outputs in chunks [0,64), sigmoid in [64,128)
+    uint4* z_save;                 // optional chunked pair (B, 2, 32, L, 8) bf16
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW, const BlockParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    unsigned char* zbuf = base;
+    unsigned char* ring = base + 2 * ZPLANE;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + NSLOT * SLOT);
+    unsigned long long* full = bars;                   // [NSLOT]  leader: both CTAs' bytes of the slot have landed
+    unsigned long long* empty = bars + NSLOT;          // [NSLOT]  per CTA: the MMAs reading the slot have retired
+    unsigned long long* acc_full = bars + 2 * NSLOT;   // [2]      per CTA: accumulator complete
+    unsigned long long* acc_empty = acc_full + 2;      // [2]      leader: both CTAs' epilogues are done with the accumulator
+    unsigned long long* z_ready = acc_empty + 2;       // [8]      leader: both CTAs wrote z slab s of the current item
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(z_ready + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned rank = cluster_rank();
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * EPI_WARPS); }
+        for (int i = 0; i < 8; ++i) mbar_init(z_ready + i, 2 * (EPI_WARPS / 2));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    }
+    if (warp == 1) tmem2_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (one lane, both CTAs)
+        if (elect_one()) {
+            unsigned it = 0;
+            auto acquire = [&](unsigned& bar_addr) -> unsigned char* {
+                const unsigned s = it % NSLOT, ph = (it / NSLOT) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                if (rank == 0) mbar_expect_tx(full + s, 2 * SLOT);
+                bar_addr = mapa(s32(full + s), 0);
+                ++it;
+                return ring + s * SLOT;
+            };
+            for (int item = cluster_id; item < p.n_items; item += n_clusters) {
+                const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+                const bool need_skip = t0 + PM > p.skip_start;
+                const int tc = t0 + (int)rank * BM - p.in_start;           // this CTA's first frame, relative to the map origin
+                for (int j = 0; j < 2; ++j)
+                    for (int sl = 0; sl < SLABS_A; ++sl) {
+                        unsigned bar;
+                        unsigned char* dst = acquire(bar);
+                        const int tap = sl >> 3;                            // tap 0 reads h[t - d], tap 1 reads h[t]
+                        tma2_load_4d(dst, &mapH, 2 * (tc - (1 - tap) * p.dil), (sl & 7) * 4, 0, b, bar);
+                        dst = acquire(bar);
+                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + ((j * SLABS_A + sl) * 2 + (int)rank) * 8, bar);
+                    }
+                for (int j = 0; j < (need_skip ? 2 : 1); ++j)
+                    for (int s8 = 0; s8 < SLABS_B; ++s8) {
+                        unsigned bar;
+                        unsigned char* dst = acquire(bar);
+                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + WROWS_A + ((j * SLABS_B + s8) * 2 + (int)rank) * 8, bar);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA)
+        if (rank == 0) {
+            constexpr unsigned idesc = make_idesc_bf16(PM, 256);
+            unsigned it = 0, use[2] = {0, 0}, n_item = 0;
+            // the three products of one k-step (16 channels = 2 chunks): a/b = byte addresses of the hi planes, lo planes
+            // a_lo / b_lo bytes further
+            auto mma3 = [&](unsigned d, unsigned a, unsigned a_lo, unsigned bw, unsigned accumulate) {
+                const unsigned long long ah = smem_desc(a, LBO, SBO), al = smem_desc(a + a_lo, LBO, SBO);
+                const unsigned long long bh = smem_desc(bw, LBO, SBO), bl = smem_desc(bw + SLOT / 2, LBO, SBO);
+                umma2_f16(d, ah, bh, idesc, accumulate);
+                umma2_f16(d, al, bh, idesc, 1);
+                umma2_f16(d, ah, bl, idesc, 1);
+            };
+            for (int item = cluster_id; item < p.n_items; item += n_clusters, ++n_item) {
+                const int t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+                const bool need_skip = t0 + PM > p.skip_start;
+                // ---------------- pass A: two n-tiles of [tanh | sigmoid] pre-activations
+                for (int j = 0; j < 2; ++j) {
+                    const unsigned u = use[j]++;
+                    if (u > 0) mbar_wait_cluster(acc_empty + j, (u - 1) & 1);
+                    tc_fence_after();
+                    const unsigned d = tmem_base + j * 256;
+                    for (int sl = 0; sl < SLABS_A; ++sl) {
+                        const unsigned sa = it % NSLOT, pa = (it / NSLOT) & 1; ++it;
+                        const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
+                        mbar_wait_cluster(full + sa, pa);
+                        mbar_wait_cluster(full + sw, pw);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const unsigned a = s32(ring + sa * SLOT), w = s32(ring + sw * SLOT);
+#pragma unroll
+                            for (int ks = 0; ks < KS / 16; ++ks)
+                                mma3(d, a + ks * 2 * LBO, SLOT / 2, w + ks * 2 * LBO, (sl | ks) != 0);
+                            umma2_commit(empty + sa);
+                            umma2_commit(empty + sw);
+                            if (sl == SLABS_A - 1) umma2_commit(acc_full + j);
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ---------------- pass B: residual (acc0) and skip (acc1) from the resident z image
+                for (int j = 0; j < (need_skip ? 2 : 1); ++j) {
+                    const unsigned u = use[j]++;
+                    mbar_wait_cluster(acc_empty + j, (u - 1) & 1);
+                    tc_fence_after();
+                    const unsigned d = tmem_base + j * 256;
+                    for (int s8 = 0; s8 < SLABS_B; ++s8) {
+                        const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
+                        mbar_wait_cluster(z_ready + s8, n_item & 1);
+                        mbar_wait_cluster(full + sw, pw);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const unsigned a = s32(zbuf) + (unsigned)s8 * 4 * LBO, w = s32(ring + sw * SLOT);
+#pragma unroll
+                            for (int ks = 0; ks < KS / 16; ++ks)
+                                mma3(d, a + ks * 2 * LBO, ZPLANE, w + ks * 2 * LBO, (s8 | ks) != 0);
+                            umma2_commit(empty + sw);
+                            if (s8 == SLABS_B - 1) umma2_commit(acc_full + j);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue: warps 2..9
+        const int q = warp & 3, grp = (warp - 2) >> 2;                // TMEM lane quadrant (= warp id mod 4), column group
+        const int row = q * 32 + lane;
+        const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
+        const unsigned acc_empty_addr[2] = {mapa(s32(acc_empty), 0), mapa(s32(acc_empty + 1), 0)};
+        const unsigned z_ready_addr = mapa(s32(z_ready), 0);
+        const size_t plane_stride = (size_t)(CH / 8) * p.L;            // 16-byte pieces per plane of a pair tensor
+        const int Tsk = p.L - p.skip_start;
+        unsigned use[2] = {0, 0};
+        for (int item = cluster_id; item < p.n_items; item += n_clusters) {
+            const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+            const bool need_skip = t0 + PM > p.skip_start;
+            const int t = t0 + (int)rank * BM + row;                   // this thread's frame
+            const bool live = t < p.L;
+            // ---------------- gate: z = tanh(F + bf) * sigmoid(G + bg) -> shared-memory pair image (+ optional saves)
+            for (int j = 0; j < 2; ++j) {
+                const unsigned u = use[j]++;
+                mbar_wait(acc_full + j, u & 1);
+                tc_fence_after();
+                const unsigned ta = lane_addr + j * 256;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+                    for (int c = grp * 64 + half * 32; c < grp * 64 + half * 32 + 32; c += 16) {
+                        float f[16], g[16];
+                        tmem_ld16(ta + c, f);
+                        tmem_ld16(ta + 128 + c, g);
+                        tmem_ld_wait();
+                        const int ch = j * 128 + c;                    // first of the 16 dilation channels
+                        const float4* bf4 = reinterpret_cast<const float4*>(p.bias + ch);
+                        const float4* bg4 = reinterpret_cast<const float4*>(p.bias + CH + ch);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 x = __ldg(bf4 + i), y = __ldg(bg4 + i);
+                            f[4 * i] = tanh_fast(f[4 * i] + x.x); f[4 * i + 1] = tanh_fast(f[4 * i + 1] + x.y);
+                            f[4 * i + 2] = tanh_fast(f[4 * i + 2] + x.z); f[4 * i + 3] = tanh_fast(f[4 * i + 3] + x.w);
+                            g[4 * i] = sigmoid_fast(g[4 * i] + y.x); g[4 * i + 1] = sigmoid_fast(g[4 * i + 1] + y.y);
+                            g[4 * i + 2] = sigmoid_fast(g[4 * i + 2] + y.z); g[4 * i + 3] = sigmoid_fast(g[4 * i + 3] + y.w);
+                        }
+                        if (p.fg_save != nullptr && live) {
+                            float4* fs = p.fg_save + ((size_t)b * (2 * CH / 4) + ch / 4) * p.L + t;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                fs[(size_t)i * p.L] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                                fs[(size_t)(CH / 4 + i) * p.L] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+                            }
+                        }
+                        unsigned hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split2(f[2 * i] * g[2 * i], f[2 * i + 1] * g[2 * i + 1], hi[i], lo[i]);
+                        unsigned char* zr = zbuf + (ch / 8) * (BM * 16) + row * 16;
+                        *reinterpret_cast<uint4*>(zr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(zr + BM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(zr + ZPLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(zr + ZPLANE + BM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        if (p.z_save != nullptr && live) {
+                            uint4* zs = p.z_save + ((size_t)b * 2 * (CH / 8) + ch / 8) * p.L + t;
+                            zs[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            zs[p.L] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                            zs[plane_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            zs[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        }
+                    }
+                    // z slab (32 channels) 4j + 2*grp + half of this CTA is complete for this warp's 32 rows
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(z_ready_addr + 8u * (unsigned)(4 * j + 2 * grp + half));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[j]);
+            }
+            // ---------------- residual: h_out = acc0 + br + h_in  -> pair
+            {
+                const unsigned u = use[0]++;
+                mbar_wait(acc_full + 0, u & 1);
+                tc_fence_after();
+                const unsigned ta = lane_addr;
+                const uint4* hin = p.h_in + (size_t)b * 2 * plane_stride + t;
+                uint4* hout = p.h_out + (size_t)b * 2 * plane_stride + t;
+#pragma unroll 1
+                for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                    float v[16];
+                    tmem_ld16(ta + c, v);
+                    uint4 xh0, xh1, xl0, xl1;
+                    xh0 = xh1 = xl0 = xl1 = make_uint4(0, 0, 0, 0);
+                    if (live) {
+                        const uint4* s = hin + (size_t)(c / 8) * p.L;
+                        xh0 = __ldg(s); xh1 = __ldg(s + p.L); xl0 = __ldg(s + plane_stride); xl1 = __ldg(s + plane_stride + p.L);
+                    }
+                    tmem_ld_wait();
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + 2 * CH + c);
+                    const unsigned xh[8] = {xh0.x, xh0.y, xh0.z, xh0.w, xh1.x, xh1.y, xh1.z, xh1.w};
+                    const unsigned xl[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
+                    unsigned hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 bb = __ldg(b4 + i);
+                        const float2 h0 = unpack_bf16x2(xh[2 * i]), l0 = unpack_bf16x2(xl[2 * i]);
+                        const float2 h1 = unpack_bf16x2(xh[2 * i + 1]), l1 = unpack_bf16x2(xl[2 * i + 1]);
+                        split2(v[4 * i] + bb.x + (h0.x + l0.x), v[4 * i + 1] + bb.y + (h0.y + l0.y), hi[2 * i], lo[2 * i]);
+                        split2(v[4 * i + 2] + bb.z + (h1.x + l1.x), v[4 * i + 3] + bb.w + (h1.y + l1.y), hi[2 * i + 1], lo[2 * i + 1]);
+                    }
+                    if (live) {
+                        uint4* o = hout + (size_t)(c / 8) * p.L;
+                        o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        o[p.L] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        o[plane_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        o[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[0]);
+            }
+            // ---------------- skip: skip (+)= acc1 + bs
+            if (need_skip) {
+                const unsigned u = use[1]++;
+                mbar_wait(acc_full + 1, u & 1);
+                tc_fence_after();
+                const unsigned ta = lane_addr + 256;
+                const bool on = live && t >= p.skip_start;
+                float4* sk = p.skip + (size_t)b * (CH / 4) * Tsk + (t - p.skip_start);
+#pragma unroll 1
+                for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                    float v[16];
+                    tmem_ld16(ta + c, v);
+                    float4 x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (on && !p.skip_init) x[i] = sk[(size_t)(c / 4 + i) * Tsk];
+                    }
+                    tmem_ld_wait();
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + 3 * CH + c);
+                    if (on) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bb = __ldg(b4 + i);
+                            sk[(size_t)(c / 4 + i) * Tsk] = make_float4(v[4 * i] + bb.x + x[i].x, v[4 * i + 1] + bb.y + x[i].y,
+                                                                        v[4 * i + 2] + bb.z + x[i].z, v[4 * i + 3] + bb.w + x[i].w);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[1]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                               // the peer may still multicast commits at this CTA's barriers until here
+    if (warp == 1) tmem2_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- weight packing
+// Packed image of one layer (bf16): pass A blocks [n-tile j 2][k-slab sl 16][half r 2], pass B blocks [j 2][s 8][r 2]; a block
+// is the 16 KB slot image [plane 2][chunk 4][row 128][8].  Pass A: N row n = r*128 + row is filter (r = 0) or gate (r = 1)
+// channel 128j + row; K index sl*32 + ck*8 + e = tap*256 + input channel (tap 0 = weight[:, :, 0], the older frame).
+// Pass B: j = 0 residual rows, j = 1 skip rows, output channel r*128 + row; K = dilation channel.
+__global__ void pack_block_kernel(const float* __restrict__ wf, const float* __restrict__ wg, const float* __restrict__ wr,
+                                  const float* __restrict__ ws, __nv_bfloat16* __restrict__ out) {
+    const int n_a = 2 * SLABS_A * 2, n_blocks = n_a + 2 * SLABS_B * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
+         i += (long long)gridDim.x * blockDim.x) {
+        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));     // w: element index inside one plane of the block
+        const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
+        float v;
+        if (blk < n_a) {
+            const int j = blk / (SLABS_A * 2), sl = (blk / 2) % SLABS_A, r = blk % 2;
+            const int kk = sl * KS + ck * 8 + e, tap = kk / CH, cin = kk % CH, cout = j * 128 + row;
+            v = (r == 0 ? wf : wg)[((size_t)cout * CH + cin) * 2 + tap];
+        } else {
+            const int bb = blk - n_a, j = bb / (SLABS_B * 2), s8 = (bb / 2) % SLABS_B, r = bb % 2;
+            const int cin = s8 * KS + ck * 8 + e, cout = r * 128 + row;
+            v = (j == 0 ? wr : ws)[(size_t)cout * CH + cin];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
+        o[0] = h;
+        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+__global__ void pack_bias_kernel(const float* bf, const float* bg, const float* br, const float* bs, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * CH) return;
+    const float* src = i < CH ? bf : (i < 2 * CH ? bg : (i < 3 * CH ? br : bs));
+    out[i] = src ? src[i % CH] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- layout converters
+// fp32 frames (B, L, C) -> chunked pair (B, 2, C/8, L, 8) for frames [t_begin, L)
+__global__ void pair_from_frames_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int L, int C, int t_begin) {
+    const int chunks = C / 8;
+    const long long total = (long long)B * chunks * (L - t_begin);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = t_begin + (int)(i % (L - t_begin)), ck = (int)((i / (L - t_begin)) % chunks), b = (int)(i / ((long long)(L - t_begin) * chunks));
+        const float4* s = reinterpret_cast<const float4*>(x + ((size_t)b * L + t) * C + ck * 8);
+        const float4 a = s[0], c = s[1];
+        unsigned hi[4], lo[4];
+        split2(a.x, a.y, hi[0], lo[0]); split2(a.z, a.w, hi[1], lo[1]); split2(c.x, c.y, hi[2], lo[2]); split2(c.z, c.w, hi[3], lo[3]);
+        uint4* o = out + ((size_t)b * 2 * chunks + ck) * L + t;
+        o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        o[(size_t)chunks * L] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+// chunked pair -> fp32 frames (hi + lo) for frames [t_begin, L)
+__global__ void frames_from_pair_kernel(const uint4* __restrict__ in, float* __restrict__ x, int B, int L, int C, int t_begin) {
+    const int chunks = C / 8;
+    const long long total = (long long)B * chunks * (L - t_begin);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ck = (int)(i % chunks), t = t_begin + (int)((i / chunks) % (L - t_begin)), b = (int)(i / ((long long)(L - t_begin) * chunks));
+        const uint4* s = in + ((size_t)b * 2 * chunks + ck) * L + t;
+        const uint4 h = s[0], l = s[(size_t)chunks * L];
+        const unsigned hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 a = unpack_bf16x2(hw[k]), c = unpack_bf16x2(lw[k]);
+            o[2 * k] = a.x + c.x; o[2 * k + 1] = a.y + c.y;
+        }
+        float4* d = reinterpret_cast<float4*>(x + ((size_t)b * L + t) * C + ck * 8);
+        d[0] = make_float4(o[0], o[1], o[2], o[3]);
+        d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+// chunked fp32 (B, C/4, T, 4) <-> frames (B, T, C) for frames [t_first, t_first + n) of the chunked tensor
+__global__ void frames_from_chunks4_kernel(const float4* __restrict__ in, float* __restrict__ x, int B, int T, int C, int t_first, int n) {
+    const int chunks = C / 4;
+    const long long total = (long long)B * chunks * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ck = (int)(i % chunks), tt = (int)((i / chunks) % n), b = (int)(i / ((long long)n * chunks));
+        reinterpret_cast<float4*>(x + ((size_t)b * n + tt) * C)[ck] = in[((size_t)b * chunks + ck) * T + t_first + tt];
+    }
+}
+// start conv on class indices (reference wavenet_model.py:65-68,127 on one-hot input == a gather of one weight column):
+// h0 pair <- table[idx[b][t]] where table (classes, ldt) holds start_conv.weight^T (+ bias) as packed by wn_pack_1x1_weights
+template <typename IDX>
+__global__ void start_pair_kernel(const IDX* __restrict__ idx, const float* __restrict__ table, const float* __restrict__ bias,
+                                  uint4* __restrict__ out, int B, int L, int classes, int ldt, int* __restrict__ err) {
+    const int chunks = CH / 8;
+    const long long total = (long long)B * chunks * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % L), ck = (int)((i / L) % chunks), b = (int)(i / ((long long)L * chunks));
+        long long cls = (long long)idx[(size_t)b * L + t];
+        if (cls < 0 || cls >= classes) { if (err) atomicExch(err, 1); cls = cls < 0 ? 0 : classes - 1; }
+        const float4* s = reinterpret_cast<const float4*>(table + (size_t)cls * ldt + ck * 8);
+        const float4* bb = reinterpret_cast<const float4*>(bias + ck * 8);
+        const float4 a = __ldg(s), c = __ldg(s + 1), ba = __ldg(bb), bc = __ldg(bb + 1);
+        unsigned hi[4], lo[4];
+        split2(a.x + ba.x, a.y + ba.y, hi[0], lo[0]); split2(a.z + ba.z, a.w + ba.w, hi[1], lo[1]);
+        split2(c.x + bc.x, c.y + bc.y, hi[2], lo[2]); split2(c.z + bc.z, c.w + bc.w, hi[3], lo[3]);
+        uint4* o = out + ((size_t)b * 2 * chunks + ck) * L + t;
+        o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        o[(size_t)chunks * L] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// chunked pair tensor (B, 2, C/8, L, 8) bf16 as 8-byte elements: dims {2(L - origin), C/8, 2, B}; box {256, box_chunks, 2, 1}:
+// 128 frames x box_chunks chunks x both planes.  Frames left of `origin` (and right of L) are out of bounds -> zeros.
+int make_pair_map(CUtensorMap* m, const void* base, int B, int L, int C, int origin, int box_frames, int box_chunks) {
+    EncodeTiledFn fn = encode_fn();
+    WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    WN_REQUIRE(L - origin >= 1, WN_E_BADARG, "empty activation range");
+    const cuuint64_t chunks = (cuuint64_t)(C / 8);
+    cuuint64_t dims[4] = {(cuuint64_t)2 * (L - origin), chunks, 2, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L * 16, chunks * L * 16, 2 * chunks * L * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * box_frames), (cuuint32_t)box_chunks, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)((const unsigned char*)base + (size_t)origin * 16), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(pair activations) failed with %d", (int)r);
+    return 0;
+}
+// packed weights: rows of 2 KB (256 8-byte elements); box = 8 rows = one 16 KB slot image
+int make_wrows_map(CUtensorMap* m, const void* base, long long rows) {
+    EncodeTiledFn fn = encode_fn();
+    WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {2048};
+    cuuint32_t box[2] = {256, 8};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WN_REQUIRE(r == CUDA_SUCCESS, WN_E_UNSUPP, "cuTensorMapEncodeTiled(packed weights) failed with %d", (int)r);
+    return 0;
+}
+
+}  // namespace tb
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" int wn_tb_supported(int R, int D, int S, int k) { return R == tb::CH && D == tb::CH && S == tb::CH && k == 2; }
+extern "C" size_t wn_tb_weight_bytes_per_layer(void) { return tb::W_LAYER_BYTES; }
+
+extern "C" int wn_tb_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
+                                        const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
+                                        void* d_w_layer, float* d_bias4, void* stream) {
+    WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_w_layer && d_bias4, WN_E_BADARG, "wn_tb_pack_block_weights: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    tb::pack_block_kernel<<<296, 256, 0, st>>>(d_wf, d_wg, d_wr, d_ws, (__nv_bfloat16*)d_w_layer);
+    tb::pack_bias_kernel<<<4, 256, 0, st>>>(d_bf, d_bg, d_br, d_bs, d_bias4);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_pair_from_frames(const float* d_frames, void* d_pair, int B, int L, int C, int t_begin, void* stream) {
+    WN_REQUIRE(d_frames && d_pair && B > 0 && L > 0 && C > 0 && C % 8 == 0 && t_begin >= 0 && t_begin < L, WN_E_BADARG,
+               "wn_pair_from_frames: bad arguments");
+    tb::pair_from_frames_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(d_frames, (uint4*)d_pair, B, L, C, t_begin);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int wn_frames_from_pair(const void* d_pair, float* d_frames, int B, int L, int C, int t_begin, void* stream) {
+    WN_REQUIRE(d_frames && d_pair && B > 0 && L > 0 && C > 0 && C % 8 == 0 && t_begin >= 0 && t_begin < L, WN_E_BADARG,
+               "wn_frames_from_pair: bad arguments");
+    tb::frames_from_pair_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((const uint4*)d_pair, d_frames, B, L, C, t_begin);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int wn_frames_from_chunks4(const float* d_chunked, float* d_frames, int B, int T, int C, int t_first, int n, void* stream) {
+    WN_REQUIRE(d_chunked && d_frames && B > 0 && T > 0 && C > 0 && C % 4 == 0 && t_first >= 0 && n >= 1 && t_first + n <= T, WN_E_BADARG,
+               "wn_frames_from_chunks4: bad arguments");
+    tb::frames_from_chunks4_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((const float4*)d_chunked, d_frames, B, T, C, t_first, n);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int start_pair(const void* d_idx, bool u8, const float* d_w_t, const float* d_b_p, void* d_h_pair, int B, int classes, int L,
+                      int R, int* d_err, void* stream) {
+    WN_REQUIRE(d_idx && d_w_t && d_b_p && d_h_pair && B > 0 && L > 0 && classes > 0, WN_E_BADARG, "wn_tb_start_index: bad arguments");
+    WN_REQUIRE(R == tb::CH, WN_E_UNSUPP, "wn_tb_start_index: R must be %d", tb::CH);
+    const int ldt = wn_n2p(R);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (u8) tb::start_pair_kernel<uint8_t><<<1184, 256, 0, st>>>((const uint8_t*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, d_err);
+    else tb::start_pair_kernel<long long><<<1184, 256, 0, st>>>((const long long*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, d_err);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int wn_tb_start_index_u8(const uint8_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair, int B, int classes,
+                                    int L, int R, int* d_err, void* stream) {
+    return start_pair(d_idx, true, d_w_t, d_b_p, d_h_pair, B, classes, L, R, d_err, stream);
+}
+extern "C" int wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair, int B, int classes,
+                                     int L, int R, int* d_err, void* stream) {
+    return start_pair(d_idx, false, d_w_t, d_b_p, d_h_pair, B, classes, L, R, d_err, stream);
+}
+
+extern "C" int wn_tb_block_fwd(const wn_tb_block_args* a, void* stream) {
+    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_block_fwd: null args");
+    WN_REQUIRE(a->d_h_in && a->d_h_out && a->d_skip && a->d_w_all && a->d_bias4, WN_E_BADARG, "wn_tb_block_fwd: null pointer");
+    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->in_start >= 0 && a->out_start >= a->in_start && a->out_start < a->L &&
+                   a->skip_start >= a->out_start && a->skip_start < a->L && a->layer >= 0 && a->layer < a->n_layers,
+               WN_E_BADARG, "wn_tb_block_fwd: bad frame ranges or layer index");
+    WN_REQUIRE(((uintptr_t)a->d_h_in | (uintptr_t)a->d_h_out | (uintptr_t)a->d_skip | (uintptr_t)a->d_w_all) % 16 == 0, WN_E_BADARG,
+               "wn_tb_block_fwd: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUtensorMap mH, mW;
+    if (int rc = tb::make_pair_map(&mH, a->d_h_in, a->B, a->L, tb::CH, a->in_start, tb::BM, tb::KS / 8)) return rc;
+    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)a->n_layers * tb::WROWS_LAYER)) return rc;
+    tb::BlockParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.L = a->L; p.t_begin = a->out_start; p.in_start = a->in_start; p.skip_start = a->skip_start;
+    p.skip_init = a->skip_init; p.dil = a->dilation;
+    p.tiles_per_seq = (a->L - a->out_start + tb::PM - 1) / tb::PM;
+    p.n_items = a->B * p.tiles_per_seq;
+    p.w_row0 = a->layer * tb::WROWS_LAYER;
+    p.bias = a->d_bias4;
+    p.h_in = (const uint4*)a->d_h_in; p.h_out = (uint4*)a->d_h_out; p.skip = (float4*)a->d_skip;
+    p.fg_save = (float4*)a->d_fg_save; p.z_save = (uint4*)a->d_z_save;
+    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    int grid = 2 * p.n_items;
+    const int max_grid = (sms / 2) * 2;
+    if (grid > max_grid) grid = max_grid;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tb::NTHREADS);
+    cfg.dynamicSmemBytes = tb::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel, mH, mW, p));
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -56,6 +56,14 @@ class TcBlockArgs(C.Structure):
                 ("skip_init", C.c_int), ("d_fg_save", C.c_void_p), ("fast_tf32", C.c_int)]
 
 
+class TbBlockArgs(C.Structure):
+    _fields_ = [("d_h_in", C.c_void_p), ("d_h_out", C.c_void_p), ("d_skip", C.c_void_p),
+                ("d_w_all", C.c_void_p), ("d_bias4", C.c_void_p), ("layer", C.c_int), ("n_layers", C.c_int),
+                ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
+                ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int), ("skip_init", C.c_int),
+                ("d_fg_save", C.c_void_p), ("d_z_save", C.c_void_p)]
+
+
 class HeadArgs(C.Structure):
     _fields_ = [("d_skip", C.c_void_p), ("d_logits", C.c_void_p),
                 ("d_w1_t", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2_t", C.c_void_p), ("d_b2", C.c_void_p),
@@ -102,6 +110,15 @@ SIGNATURES = {
     "wn_tc_pack_block_weights": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p] * 5),
     "wn_tc_block_fwd": (C.c_int, [C.POINTER(TcBlockArgs), C.c_void_p]),
     "wn_tc_read_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    "wn_tb_supported": (C.c_int, [C.c_int] * 4),
+    "wn_tb_weight_bytes_per_layer": (C.c_size_t, []),
+    "wn_tb_pack_block_weights": (C.c_int, [C.c_void_p] * 10 + [C.c_void_p]),
+    "wn_tb_start_index_u8": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 2),
+    "wn_tb_start_index_i64": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 2),
+    "wn_pair_from_frames": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
+    "wn_frames_from_pair": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
+    "wn_frames_from_chunks4": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
+    "wn_tb_block_fwd": (C.c_int, [C.POINTER(TbBlockArgs), C.c_void_p]),
     "wn_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p]),
     "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
     "wn_wgrad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

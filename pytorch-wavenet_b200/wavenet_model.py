@@ -145,6 +145,19 @@ class _Runtime:
                 out.setdefault("tc_bwd_layers", []).append((wdz, wdh))
                 out.setdefault("tc_bwd_layers_bf16", []).append((self._bf16_pairs(wdz, stream), self._bf16_pairs(wdh, stream)))
 
+        if lib.wn_tb_supported(R, D, S, k):
+            nl = m.layers * m.blocks
+            per = lib.wn_tb_weight_bytes_per_layer()
+            tb_w = torch.empty(nl, per, device=dev, dtype=torch.uint8)
+            tb_b = torch.empty(nl, 4 * 256, **f32)
+            for i in range(nl):
+                (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
+                (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+                native.check(lib.wn_tb_pack_block_weights(
+                    wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
+                    native.ptr(br), native.ptr(bs), tb_w[i].data_ptr(), tb_b[i].data_ptr(), stream), "pack tb")
+            out["tb"] = (tb_w, tb_b)
+
         def pack1x1(w, b, N, K):
             wt = torch.empty(K, lib.wn_n2p(N), **f32)
             bp = torch.empty(lib.wn_n2p(N), **f32)
@@ -189,6 +202,17 @@ class _Runtime:
                                f"(shape '[{B * out_len}, {Cc}]' is invalid for input of size {B * plan.t_final * Cc})")
         f32 = dict(device=dev, dtype=torch.float32)
         n_layers = len(dil)
+        if os.environ.get("WN_CHECK_INDICES") and index_input and (int(x.min()) < 0 or int(x.max()) >= Cc):
+            raise RuntimeError(f"wavenet_b200: class index outside [0, {Cc}) (the reference's one-hot scatter raises here)")
+        if self.block_mode not in ("auto", "tb", "tc", "ffma"):
+            raise ValueError(f"block_mode must be 'auto', 'tb', 'tc' or 'ffma', not {self.block_mode!r}")
+        use_tb = (self.block_mode in ("auto", "tb") and save is None and not self.fast_tf32 and
+                  bool(lib.wn_tb_supported(R, D, S, k)))
+        if self.block_mode == "tb" and not use_tb:
+            raise RuntimeError("wavenet_b200: the fused tensor-core block needs R = D = S = 256, kernel_size = 2 "
+                               f"(got {R},{D},{S},{k}) and, for now, a no-grad forward")
+        if use_tb:
+            return self._forward_tb(x, index_input, B, L, plan, out_len, W, stream)
         if save is not None:
             h_all = torch.empty(n_layers + 1, B, L, R, **f32)      # h_all[i] = input of layer i
             fg_all = torch.empty(n_layers, B, L, 2 * D, **f32)     # tanh / sigmoid outputs
@@ -208,7 +232,7 @@ class _Runtime:
         else:
             native.check(lib.wn_start_fwd_dense(x.data_ptr(), ws_t.data_ptr(), bs_p.data_ptr(), h0.data_ptr(),
                                                 B, Cc, L, R, stream), "start")
-        use_tc = self.block_mode != "ffma" and bool(lib.wn_tc_supported(R, D, S, k))
+        use_tc = self.block_mode != "ffma" and bool(lib.wn_tc_supported(R, D, S, k))     # "auto" with autograd / "tb" n/a
         if self.block_mode == "tc" and not use_tc:
             raise RuntimeError(f"wavenet_b200: tensor-core blocks need R%256==0, S%256==0, D%128==0 (got {R},{S},{D})")
         self.last_block_mode = "tc" if use_tc else "ffma"
@@ -261,6 +285,63 @@ class _Runtime:
         if save is not None:
             save.update(h_all=h_all, fg_all=fg_all, skip=skip, plan=plan, out_len=out_len, x=x,
                         index_input=index_input, B=B, L=L)
+        return logits
+
+    def _forward_tb(self, x, index_input, B, L, plan, out_len, W, stream):
+        """No-grad forward on the fused tensor-core blocks (wn_tb_block_fwd): chunked bf16-pair activations, one launch per
+        residual block, z resident on the SM (csrc/tc_block.cu)."""
+        m, lib = self.model, native.lib()
+        dev = self.device()
+        R, S, Cc = m.residual_channels, m.skip_channels, m.classes
+        E = m.end_conv_1.out_channels
+        dil = [d for d, _ in m.dilations]
+        key = ("tb", B, L)
+        if key not in self.ws:
+            self.ws.clear()
+            bf16 = dict(device=dev, dtype=torch.bfloat16)
+            self.ws[key] = (torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16),
+                            torch.empty(B, S // 4, plan.t_final, 4, device=dev, dtype=torch.float32))
+        h0, h1, skip = self.ws[key]
+        ws_t, bs_p = W["start"]
+        if index_input:
+            fn = lib.wn_tb_start_index_u8 if x.dtype == torch.uint8 else lib.wn_tb_start_index_i64
+            native.check(fn(x.data_ptr(), ws_t.data_ptr(), bs_p.data_ptr(), h0.data_ptr(), B, Cc, L, R, None, stream), "tb start")
+        else:
+            frames = torch.empty(B, L, R, device=dev, dtype=torch.float32)
+            native.check(lib.wn_start_fwd_dense(x.data_ptr(), ws_t.data_ptr(), bs_p.data_ptr(), frames.data_ptr(),
+                                                B, Cc, L, R, stream), "start")
+            native.check(lib.wn_pair_from_frames(frames.data_ptr(), h0.data_ptr(), B, L, R, 0, stream), "pair from frames")
+            del frames
+        tb_w, tb_b = W["tb"]
+        a = native.TbBlockArgs()
+        a.B, a.L, a.n_layers = B, L, len(dil)
+        a.d_skip, a.skip_start, a.d_w_all = skip.data_ptr(), plan.skip_start, tb_w.data_ptr()
+        a.d_fg_save = a.d_z_save = None
+        src, dst = h0, h1
+        ev = getattr(self, "block_events", None)
+        if ev is not None:
+            ev[0].record(torch.cuda.current_stream(dev))
+        for i, d in enumerate(dil):
+            a.d_h_in, a.d_h_out, a.layer, a.d_bias4 = src.data_ptr(), dst.data_ptr(), i, tb_b[i].data_ptr()
+            a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
+            native.check(lib.wn_tb_block_fwd(ctypes.byref(a), stream), f"tb block {i}")
+            src, dst = dst, src
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(dev))
+        # head: the last out_len frames of skip, back in the frames layout of wn_head_fwd
+        sk_frames = torch.empty(B, out_len, S, device=dev, dtype=torch.float32)
+        native.check(lib.wn_frames_from_chunks4(skip.data_ptr(), sk_frames.data_ptr(), B, plan.t_final, S,
+                                                plan.t_final - out_len, out_len, stream), "skip to frames")
+        logits = torch.empty(B * out_len, Cc, device=dev, dtype=torch.float32)
+        hd = native.HeadArgs()
+        hd.d_skip, hd.d_logits = sk_frames.data_ptr(), logits.data_ptr()
+        (w1, b1), (w2, b2) = W["end1"], W["end2"]
+        hd.d_w1_t, hd.d_b1, hd.d_w2_t, hd.d_b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+        hd.B, hd.L, hd.S, hd.E, hd.classes, hd.skip_start, hd.out_len, hd.mode = B, L, S, E, Cc, L - out_len, out_len, 0
+        native.check(lib.wn_head_fwd(ctypes.byref(hd), stream), "head")
+        self.last_block_mode = "tb"
+        self.last_h_pair = src                       # output of the last block (debug / tests)
+        self.launches_last_forward = (1 if index_input else 2) + len(dil) + 2
         return logits
 
     # ------------------------------------------------------------------ training-path backward

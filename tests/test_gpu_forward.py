@@ -113,7 +113,7 @@ def test_full_size_properties_cfg3():
 
 def test_cfg3_full_size_vs_oracle():
     """The benchmarked shape itself against the CPU oracle: cfg-3 net (10x5 layers, 256 ch), one L=16000 sequence,
-    output_length = 10885, default (tensor-core) blocks; then B=8 where every row must equal its B=1 run bit for bit."""
+    output_length = 10885, default (fused tensor-core) blocks; then B=8 where every row must equal its B=1 run bit for bit."""
     import wavenet_model as wmod
     kw = dict(layers=10, blocks=5, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
               classes=256, output_length=16000 - 5116 + 1, kernel_size=2, bias=False)
@@ -128,7 +128,7 @@ def test_cfg3_full_size_vs_oracle():
     rt = m._runtime()
     with torch.no_grad():
         y1 = m.forward_indices(idx[3:4].cuda())
-        assert rt.last_block_mode == "tc"
+        assert rt.last_block_mode == "tb"                      # the fused tcgen05 block kernel is the default here
         err = rel_err(y1.cpu().numpy(), want)
         assert err < TOL, f"cfg3 full size vs oracle: {err:.3e}"
         y8 = m.forward_indices(idx.cuda()).view(8, -1, 256)

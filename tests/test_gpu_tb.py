@@ -1,0 +1,118 @@
+"""The fused tensor-core block (csrc/tc_block.cu: tcgen05 cta_group::2, chunked bf16-pair activations, one launch per
+residual block) against the CPU oracle, the golden outputs of the unmodified reference and the exact-fp32 SIMT blocks."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from helpers import build_model, one_hot_cuda, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _pair_emulation(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def test_pair_layout_converters():
+    """fp32 frames (B, L, C) <-> chunked pair [b][plane][c/8][t][c%8]: element placement, the split itself, the origin."""
+    import native
+    lib = native.lib()
+    B, L, C, t_begin = 2, 333, 256, 17
+    x = (torch.randn(B, L, C, generator=torch.Generator().manual_seed(1)) * 3).cuda()
+    pair = torch.zeros(B, 2, C // 8, L, 8, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    native.check(lib.wn_pair_from_frames(x.data_ptr(), pair.data_ptr(), B, L, C, t_begin, st), "to pair")
+    hi, lo = _pair_emulation(x)
+    want_hi = hi.view(B, L, C // 8, 8).permute(0, 2, 1, 3)
+    want_lo = lo.view(B, L, C // 8, 8).permute(0, 2, 1, 3)
+    assert torch.equal(pair[:, 0, :, t_begin:], want_hi[:, :, t_begin:]) and torch.equal(pair[:, 1, :, t_begin:], want_lo[:, :, t_begin:])
+    assert float(pair[:, :, :, :t_begin].abs().max()) == 0                 # frames left of t_begin are not touched
+    back = torch.full((B, L, C), 7.0, device="cuda")
+    native.check(lib.wn_frames_from_pair(pair.data_ptr(), back.data_ptr(), B, L, C, t_begin, st), "from pair")
+    assert torch.equal(back[:, t_begin:], (hi.float() + lo.float())[:, t_begin:]) and bool((back[:, :t_begin] == 7.0).all())
+    assert rel_err(back[:, t_begin:].cpu().numpy(), x[:, t_begin:].cpu().numpy()) < 2.0 ** -16
+    # chunked fp32 (B, C/4, T, 4) -> frames
+    sk = torch.randn(B, C // 4, L, 4, device="cuda")
+    out = torch.empty(B, 50, C, device="cuda")
+    native.check(lib.wn_frames_from_chunks4(sk.data_ptr(), out.data_ptr(), B, L, C, L - 50, 50, st), "chunks4")
+    assert torch.equal(out, sk[:, :, L - 50:].permute(0, 2, 1, 3).reshape(B, 50, C))
+
+
+@pytest.mark.parametrize("B,L,layers,blocks,bias,out_len", [
+    (1, 300, 3, 1, False, 64),        # a single 256-frame item and a 44-frame tail
+    (2, 700, 4, 2, True, 300),        # several items per sequence, skip starts inside an item
+    (3, 1203, 6, 2, True, 40),        # dilation 32 > tile overlap cases; most items lie left of skip_start
+    (2, 515, 2, 3, False, 500),
+])
+def test_fused_blocks_match_oracle_and_simt(B, L, layers, blocks, bias, out_len):
+    import wavenet_model as wmod
+    kw = dict(layers=layers, blocks=blocks, dilation_channels=256, residual_channels=256, skip_channels=256,
+              end_channels=256, classes=256, output_length=out_len, kernel_size=2, bias=bias)
+    torch.manual_seed(5)
+    m = wmod.WaveNetModel(**kw)
+    spec = O.NetSpec(**kw)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    idx = torch.randint(0, 256, (B, L), generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = O.forward(p, spec, O.one_hot(idx, 256)).numpy()
+        want_full = O.stack_folded(p, spec, O.one_hot(idx, 256), lambda h, d, i0, i: O.fold_time(h, d, i0)).numpy()
+    m = m.cuda()
+    rt = m._runtime()
+    with torch.no_grad():
+        y = m.forward_indices(idx.cuda())
+        assert rt.last_block_mode == "tb"
+        yu = m.forward_indices(idx.to(torch.uint8).cuda())
+        yd = m(one_hot_cuda(idx.numpy()))                               # dense (one-hot float) input path
+        full = m.wavenet(one_hot_cuda(idx.numpy()), m.wavenet_dilate)
+        rt.block_mode = "ffma"
+        y0 = m.forward_indices(idx.cuda())
+        rt.block_mode = "auto"
+        rows = [m.forward_indices(idx[b:b + 1].cuda()) for b in range(B)]
+    assert torch.equal(y, yu) and torch.equal(y, yd)
+    e = rel_err(y.cpu().numpy(), want)
+    assert e < TOL, f"fused blocks vs oracle {e:.3e}"
+    assert rel_err(y.cpu().numpy(), y0.cpu().numpy()) < 3e-5
+    assert rel_err(full.cpu().numpy(), want_full) < TOL                  # all T_final columns incl. the zero-history region
+    yb = y.view(B, out_len, 256)
+    for b in range(B):
+        assert torch.equal(yb[b], rows[b].view(out_len, 256))            # batch rows are independent, bit for bit
+
+
+def test_fused_blocks_dense_non_one_hot_input():
+    import wavenet_model as wmod
+    kw = dict(layers=3, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=100, kernel_size=2, bias=True)
+    torch.manual_seed(2)
+    m = wmod.WaveNetModel(**kw)
+    spec = O.NetSpec(**kw)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 256, 400, generator=g) * (torch.rand(2, 256, 400, generator=g) < 0.05)
+    with torch.no_grad():
+        want = O.forward(p, spec, x).numpy()
+        got = m.cuda()(x.cuda())
+    assert m._runtime().last_block_mode == "tb"
+    assert rel_err(got.cpu().numpy(), want) < TOL
+
+
+def test_fused_blocks_cfg2_golden(golden):
+    g = golden("net_cfg2.npz")
+    m = build_model(g)
+    with torch.no_grad():
+        y = m(one_hot_cuda(g["idx"]))
+    assert m._runtime().last_block_mode == "tb"
+    e = rel_err(y.cpu().numpy(), g["fwd"])
+    assert e < TOL, e
+
+
+def test_tb_mode_requires_supported_shape(golden):
+    small = build_model(golden("net_deep.npz"))
+    small._runtime().block_mode = "tb"
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        small(one_hot_cuda(golden("net_deep.npz")["idx"]))

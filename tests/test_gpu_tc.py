@@ -49,7 +49,7 @@ def test_tc_cfg2_golden_and_auto_mode(golden):
     assert rt.block_mode == "auto"
     with torch.no_grad():
         y = m(one_hot_cuda(g["idx"]))
-    assert rt.last_block_mode == "tc"                           # 256-channel nets take the tensor-core path by default
+    assert rt.last_block_mode == "tb"                           # 256-channel nets take the fused tensor-core path by default
     assert rel_err(y.cpu().numpy(), g["fwd"]) < 1e-4
     small = build_model(golden("net_deep.npz"))
     with torch.no_grad():
