@@ -37,6 +37,8 @@ GEN_KW = dict(layers=10, blocks=5, dilation_channels=256, residual_channels=256,
 GEN_SAMPLES = 16000
 TRAIN_B, TRAIN_L = 8, 16000
 TEMPERATURE = 1.0
+GEN_WORKLOAD = ("cfg2 generate_fast: layers=10 blocks=5 ch=256 classes=256, 16000 samples, single stream, temperature=1.0, "
+                "seeded random-init weights")
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -49,6 +51,18 @@ def measured_peaks(what="hbm"):
             return float(d["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return (1400.0 if what == "tensor" else 6650.0), "fallback (B200_PROFILING.md)"
+
+
+def captured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py traffic ...); None when there is no capture of it."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        d = json.load(f)
+    e = d.get(kernel)
+    return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
 
 
 class ClockSampler:
@@ -231,20 +245,22 @@ def bench_generate(args, world, rank):
     g, b, bars = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     native.lib().wn_gen_launch_info(s["handle"], ctypes.byref(g), ctypes.byref(b), ctypes.byref(bars))
     weight_bytes = 4 * sum(p.numel() for p in model.parameters())
-    ring_cols = sum(q.max_length for q in model.dilated_queues)
     per_launch_ms = ms / args.steps
     peak, peak_src = measured_peaks()
-    # algorithmic bytes per launch: every sample touches all weights once (they do not fit on chip: 79.4 MB fp32)
-    # plus k ring columns read and one written per layer
+    # algorithmic bytes per launch: every sample touches all weights once (79.4 MB fp32: they do not fit on chip) plus
+    # k ring columns read and one written per layer
     alg_bytes = n * (weight_bytes + 50 * 3 * 256 * 4)
-    roof = {"kernel": "gen_kernel_fast (persistent cooperative sampler: flag-in-data exchange, TMA weight prefetch)", "bound": "hbm",
-            "achieved": alg_bytes / (per_launch_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": alg_bytes / (per_launch_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-            "note": "latency-bound path: the 79.4 MB of fp32 weights are re-read per sample from L2 (ncu: 0.63 MB of DRAM "
-                    "traffic per sample), so this is L2->SM streaming expressed against the HBM peak; the governing "
-                    "figure is microseconds per dependent exchange stage (2 per layer + 2 for the head)",
+    traffic, tsrc = captured_traffic("gen_kernel_fast")
+    sm_mhz = clk.get("sm_mhz") or 1965.0
+    macs = sum(p.numel() for p in model.parameters()) - 256 * 256      # start conv is a gather
+    issue_peak = 148 * 128 * sm_mhz * 1e6                               # FMA lanes per second at the clock seen
+    roof = {"kernel": "gen_kernel_fast", "bound": "hbm", "achieved": alg_bytes / (per_launch_ms / 1e3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": alg_bytes / (per_launch_ms / 1e3) / 1e9 / peak,
+            "traffic": None if traffic is None else traffic, "traffic_source": tsrc, "peak_source": peak_src,
             "us_per_sample": per_launch_ms * 1e3 / n, "exchange_stages_per_sample": bars.value,
-            "us_per_exchange_stage": per_launch_ms * 1e3 / n / bars.value, "grid": g.value, "block": b.value}
+            "us_per_exchange_stage": per_launch_ms * 1e3 / n / bars.value, "grid": g.value, "block": b.value,
+            "issue": {"fma_per_sample": macs, "achieved_gfma_s": macs * n / (per_launch_ms / 1e3) / 1e9,
+                      "peak_gfma_s": issue_peak / 1e9, "frac": macs * n / (per_launch_ms / 1e3) / issue_peak}}
     return dict(value=value, ms_per_step=ms / args.steps, clocks=clk, e2e=e2e, roofline=roof,
                 argmax_samples_per_s=n / (min(t_arg) / 1e3), wall_s=t_wall, launches=args.steps, batched=batched)
 
@@ -296,6 +312,7 @@ def bench_train(args, world, rank):
         rt.block_events = None
         barrier_sync(world)
         clk = clocks.stop()
+        fwd_mode = getattr(rt, "last_block_mode", "ffma")
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), world)
         block_ms = sum(a.elapsed_time(b) for a, b in bevs) / args.steps
         value = world * B * L * args.steps / (ms / 1e3)
@@ -327,7 +344,7 @@ def bench_train(args, world, rank):
         e2e_idx_s = max_over_ranks(time.perf_counter() - t0, world)
     # opt-in single-pass TF32 blocks (outside the 1e-4 parity bar; reported for the HBM-bound regime only)
     fast = None
-    if getattr(rt, "last_block_mode", "") == "tc":
+    if getattr(rt, "last_block_mode", "") == "tc" and args.variants:
         with torch.no_grad():
             y_exact = model.forward_indices(d_idx)
             rt.fast_tf32 = True
@@ -394,21 +411,68 @@ def bench_train(args, world, rank):
                   "grad_allreduce_bytes_per_step": red.bytes_reduced // max(1, 1 + len(step_ms)) if world > 1 else 0,
                   "grad_buckets_per_step": red.buckets // max(1, 1 + len(step_ms)) if world > 1 else 0,
                   "forward_blocks": getattr(rt, "last_block_mode", "ffma"), "backward_data": getattr(rt, "last_bwd_mode", "ffma"),
-                  "weight_gradients": {"cublas": "cuBLAS fp32 einsum", "native": "wn_wgrad (split-frames fp32 FMA kernel)",
-                                       "tc": f"wn_tc_wgrad (tcgen05, bf16 pairs; {getattr(rt, 'wgrad_tc_calls', 0)} of the calls) else wn_wgrad"
-                                       }[getattr(rt, "wgrad_mode", "tc")],
-                  "note": "forward with activations saved + backward data kernels + weight-gradient kernels + NCCL all-reduce "
-                          "per block overlapped with the backward (the optimizer step is not part of this figure)"}
-    model._runtime().grad_reducer = None
+                  "scaling": "weak (B=8 per GPU)"}
     del loss
     model.zero_grad(set_to_none=True)
+    if world > 1 and B % world == 0:
+        # strong scaling: the SAME global batch of 8 sequences split over the ranks
+        sidx = torch.randint(0, 256, (B, L), generator=torch.Generator().manual_seed(777))
+        stgt = torch.randint(0, 256, (B, model.output_length), generator=torch.Generator().manual_seed(778))
+        mine = dp.shard_batch(sidx, rank, world).to(torch.uint8).cuda()
+        mine_t = dp.shard_batch(stgt, rank, world).reshape(-1).cuda()
+        sms = []
+        for i in range(3):
+            model.zero_grad(set_to_none=True)
+            barrier_sync(world)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            F.cross_entropy(model.forward_indices(mine), mine_t).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                sms.append(e0.elapsed_time(e1))
+        st = max_over_ranks(sum(sms) / len(sms), world)
+        train_step["strong"] = {"global_batch": B, "ms_per_step": st, "frames_per_s": B * L / (st / 1e3)}
+        model.zero_grad(set_to_none=True)
+        # correctness of the data-parallel step, visible to the driver: rank-averaged gradients of a small 256-channel net
+        # on a sharded batch vs the single-process gradients of the whole batch
+        import wavenet_model as wmod
+        kw = dict(layers=3, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+                  classes=256, output_length=64, kernel_size=2, bias=True)
+        torch.manual_seed(5)
+        small = wmod.WaveNetModel(**kw).cuda()
+        gi = torch.randint(0, 256, (2 * world, 300), generator=torch.Generator().manual_seed(31))
+        gt = torch.randint(0, 256, (2 * world, 64), generator=torch.Generator().manual_seed(32))
+        F.cross_entropy(small.forward_indices(gi.cuda()), gt.reshape(-1).cuda()).backward()
+        whole = {k: v.grad.detach().clone() for k, v in small.named_parameters()}
+        small.zero_grad(set_to_none=True)
+        dp.make_data_parallel(small)
+        F.cross_entropy(small.forward_indices(dp.shard_batch(gi, rank, world).cuda()),
+                        dp.shard_batch(gt, rank, world).reshape(-1).cuda()).backward()
+        err = max(float((v.grad - whole[k]).abs().max() / whole[k].abs().max().clamp_min(1e-30))
+                  for k, v in small.named_parameters())
+        train_step["ddp_grad_max_rel_err"] = max_over_ranks(err, world)
+        small._runtime().grad_reducer = None
+        del small, whole
+    model._runtime().grad_reducer = None
     per_layer, start_b, head_b, flops = train_alg_bytes(model, B, L, dense_input=False)
     n_layers = len(per_layer)
     peak, peak_src = measured_peaks()
     ach = (sum(per_layer) / n_layers) / (block_ms / n_layers / 1e3) / 1e9
     tflops = flops / (block_ms / 1e3) / 1e12
-    mode = getattr(rt, "last_block_mode", "ffma")
-    if mode == "tc":
+    mode = fwd_mode
+    if mode == "tb":
+        tpeak, tsrc = measured_peaks("tensor")
+        traffic, trsrc = captured_traffic("block_fused_kernel")
+        roof = {"kernel": "block_fused_kernel (tcgen05 cta_group::2, bf16 hi/lo pairs, one launch per block)",
+                "bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                "traffic": traffic, "traffic_source": trsrc, "peak_source": tsrc, "launches_per_step": n_layers,
+                "avg_block_ms": block_ms / n_layers, "operand_split": "bf16x2",
+                "mma_per_product": 3, "tensor_pipe_equiv_frac": 3 * tflops / tpeak,
+                "hbm_achieved_gbs": ach, "hbm_peak_gbs": peak, "hbm_frac": ach / peak,
+                "alg_bytes_per_block": sum(per_layer) / n_layers,
+                "alg_bytes_per_frame": (sum(per_layer) + start_b + head_b) / (B * L)}
+    elif mode == "tc":
         tpeak, tsrc = measured_peaks("tensor")
         prec = getattr(rt, "tc_precision", "tf32x3")
         mma_per_flop = 3 if prec == "bf16x2" else 6          # bf16-rate MMA equivalents per algorithmic FLOP
@@ -444,6 +508,7 @@ def bench_train(args, world, rank):
                 roofline=roof, train_step=train_step, fast_tf32=fast, dtype="f32", scaling="weak",
                 config={"workload": "cfg3 forward: layers=10 blocks=5 ch=256, B=8 per GPU, L=16000, output_length=10885, "
                                     "uint8 index input resident in HBM", "block_kernels": mode, "global_batch": world * B, "seq_len": L,
+                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                         "parallelism": f"dp{world} (batch shards, no collective in forward)"},
                 launches=args.steps * rt.launches_last_forward)
 
@@ -524,7 +589,8 @@ def run_reference(args):
         "impl": "reference", "metric": "generate_fast samples/sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_per_step / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 generate_fast: layers=10 blocks=5 ch=256 classes=256, single stream, temperature=1.0"},
+        "config": {"workload": GEN_WORKLOAD, "parallelism": "1 CPU process (rank 0); per-sample cost is position independent, so each "
+                   f"step times ~{n_per_step} samples instead of 16000"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -540,6 +606,7 @@ def main():
     ap.add_argument("--workload", default="all", choices=["all", "generate", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the 64-stream (cfg4) generation figure")
+    ap.add_argument("--variants", action="store_true", help="also time the other operand splits of the two-launch blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -575,8 +642,7 @@ def main():
             "value": primary["value"], "unit": "samples/s" if gen is not None else "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": ({"workload": "cfg2 generate_fast: layers=10 blocks=5 ch=256 classes=256, 16000 samples, single "
-                                    "stream per GPU, temperature=1.0, seeded random-init weights",
+            "config": ({"workload": GEN_WORKLOAD,
                         "parallelism": f"{world} independent replicas (the sampling loop does not shard)",
                         "l2": "256 MiB buffer written between timed iterations (L2 flush)"}
                        if gen is not None else train["config"]),
@@ -593,6 +659,24 @@ def main():
                 line["train"] = train
         else:
             line.update({k: train[k] for k in ("train_step", "fast_tf32", "e2e_index_api", "cpu_baseline") if k in train})
+        summ = {}
+        if gen is not None:
+            summ.update(gen_samples_per_s=gen["value"], gen_us_per_sample=gen["roofline"]["us_per_sample"],
+                        gen_us_per_stage=gen["roofline"]["us_per_exchange_stage"])
+            if gen.get("batched") is not None:
+                summ["cfg4_64_streams_samples_per_s"] = gen["batched"]["value"]
+        if train is not None:
+            r = train["roofline"]
+            summ.update(train_fwd_frames_per_s=train["value"], train_fwd_ms=train["ms_per_step"],
+                        train_fwd_e2e_frames_per_s=train["e2e"]["value"], train_avg_block_ms=r.get("avg_block_ms", r.get("avg_launch_ms")),
+                        train_tensor_pipe_equiv_frac=r.get("tensor_pipe_equiv_frac"), train_hbm_frac=r.get("hbm_frac", r.get("frac")),
+                        train_step_ms=train["train_step"]["ms_per_step"],
+                        train_step_frames_per_s=train["train_step"]["frames_per_s"])
+            if "strong" in train["train_step"]:
+                summ["train_step_strong_ms"] = train["train_step"]["strong"]["ms_per_step"]
+            if "ddp_grad_max_rel_err" in train["train_step"]:
+                summ["ddp_grad_max_rel_err"] = train["train_step"]["ddp_grad_max_rel_err"]
+        line["summary"] = summ
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -52,6 +52,123 @@ class StackPlan:
         self.skip_start = L - T
 
 
+class _Packs:
+    """Lazily built packed weight groups of one model state (see _Runtime.packed_weights):
+      layers              K-outer fp32 copies for the SIMT block kernels
+      tc_layers[_bf16]    K-major pre-split pairs for the two-launch tensor-core blocks (fp32 tf32-split / bf16)
+      tc_bwd_layers[_bf16] the same for the tensor-core data-gradient GEMMs
+      tb                  all layers' slot images + biases for the fused tensor-core block (wn_tb_block_fwd)
+      start / end1 / end2 K-outer 1x1 weights
+    """
+
+    def __init__(self, rt):
+        self.rt, self.groups = rt, {}
+
+    def __getitem__(self, name):
+        if name not in self.groups:
+            rt = self.rt
+            stream = torch.cuda.current_stream(rt.device()).cuda_stream
+            self.groups[name] = getattr(self, "_build_" + name)(stream)
+        return self.groups[name]
+
+    def _dims(self):
+        m = self.rt.model
+        return (m.residual_channels, m.dilation_channels, m.skip_channels, m.end_conv_1.out_channels, m.classes,
+                m.kernel_size, m.layers * m.blocks)
+
+    def _build_layers(self, stream):
+        rt, lib = self.rt, native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = rt._params()
+        f32 = dict(device=rt.device(), dtype=torch.float32)
+        n1p, n2p = lib.wn_n1p(D), lib.wn_n2p(R + S)
+        out = []
+        for i in range(nl):
+            wfg, bfg = torch.empty(k * R, n1p, **f32), torch.empty(n1p, **f32)
+            wrs, brs = torch.empty(D, n2p, **f32), torch.empty(n2p, **f32)
+            (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
+            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+            native.check(lib.wn_pack_gate_weights(wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg),
+                                                  R, D, k, wfg.data_ptr(), bfg.data_ptr(), stream), "pack gate")
+            native.check(lib.wn_pack_res_skip_weights(wr.data_ptr(), wsk.data_ptr(), native.ptr(br), native.ptr(bs),
+                                                      R, D, S, wrs.data_ptr(), brs.data_ptr(), stream), "pack res/skip")
+            out.append((wfg, bfg, wrs, brs))
+        return out
+
+    def _build_tc_layers(self, stream):
+        rt, lib = self.rt, native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = rt._params()
+        f32 = dict(device=rt.device(), dtype=torch.float32)
+        out = []
+        for i in range(nl):
+            (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
+            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+            wa, ba = torch.empty(2, 2 * D, k * R, **f32), torch.empty(2 * D, **f32)
+            wb, bb = torch.empty(2, R + S, D, **f32), torch.empty(R + S, **f32)
+            native.check(lib.wn_tc_pack_block_weights(
+                wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
+                native.ptr(br), native.ptr(bs), R, D, S, k, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
+                bb.data_ptr(), stream), "pack tc")
+            out.append((wa, ba, wb, bb))
+        return out
+
+    def _build_tc_layers_bf16(self, stream):
+        return [(self.rt._bf16_pairs(wa, stream), ba, self.rt._bf16_pairs(wb, stream), bb) for wa, ba, wb, bb in self["tc_layers"]]
+
+    def _build_tc_bwd_layers(self, stream):
+        rt, lib = self.rt, native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = rt._params()
+        f32 = dict(device=rt.device(), dtype=torch.float32)
+        out = []
+        for i in range(nl):
+            wf, wg, wr, wsk = P["filt"][i][0], P["gate"][i][0], P["res"][i][0], P["skip"][i][0]
+            wdz, wdh = torch.empty(2, D, R + S, **f32), torch.empty(2, R, k * 2 * D, **f32)
+            native.check(lib.wn_tc_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
+                                                          R, D, S, k, wdz.data_ptr(), wdh.data_ptr(), stream), "pack tc bwd")
+            out.append((wdz, wdh))
+        return out
+
+    def _build_tc_bwd_layers_bf16(self, stream):
+        return [(self.rt._bf16_pairs(a, stream), self.rt._bf16_pairs(b, stream)) for a, b in self["tc_bwd_layers"]]
+
+    def _build_tb(self, stream):
+        rt, lib = self.rt, native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = rt._params()
+        dev = rt.device()
+        tb_w = torch.empty(nl, lib.wn_tb_weight_bytes_per_layer(), device=dev, dtype=torch.uint8)
+        tb_b = torch.empty(nl, 4 * 256, device=dev, dtype=torch.float32)
+        for i in range(nl):
+            (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
+            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+            native.check(lib.wn_tb_pack_block_weights(
+                wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
+                native.ptr(br), native.ptr(bs), tb_w[i].data_ptr(), tb_b[i].data_ptr(), stream), "pack tb")
+        return tb_w, tb_b
+
+    def _pack1x1(self, wb, N, K, stream):
+        lib = native.lib()
+        f32 = dict(device=self.rt.device(), dtype=torch.float32)
+        w, b = wb
+        wt, bp = torch.empty(K, lib.wn_n2p(N), **f32), torch.empty(lib.wn_n2p(N), **f32)
+        native.check(lib.wn_pack_1x1_weights(w.data_ptr(), native.ptr(b), N, K, wt.data_ptr(), bp.data_ptr(), stream), "pack 1x1")
+        return wt, bp
+
+    def _build_start(self, stream):
+        R, D, S, E, Cc, k, nl = self._dims()
+        return self._pack1x1(self.rt._params()["start"], R, Cc, stream)
+
+    def _build_end1(self, stream):
+        R, D, S, E, Cc, k, nl = self._dims()
+        return self._pack1x1(self.rt._params()["end1"], E, S, stream)
+
+    def _build_end2(self, stream):
+        R, D, S, E, Cc, k, nl = self._dims()
+        return self._pack1x1(self.rt._params()["end2"], Cc, E, stream)
+
+
 class _Runtime:
     """Device-side state bound to one model: packed weights, workspaces, sampler handles."""
 
@@ -98,78 +215,18 @@ class _Runtime:
         return out
 
     def packed_weights(self, stream):
-        """Pack (or re-pack after an optimizer step / load_state_dict) the K-outer weight copies."""
-        m, lib = self.model, native.lib()
+        """The packed weight copies, built per group on first use (a path packs only what it reads) and forgotten when a
+        parameter's (data_ptr, version) changes or after invalidate()."""
+        m = self.model
         key = tuple((p.data_ptr(), p._version) for p in m.parameters())
-        if key == self.pack_key:
-            return self.packed
-        dev = self.device()
-        for name, p in m.named_parameters():
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError(f"wavenet_b200: parameter {name} must be a contiguous float32 tensor "
-                                   f"(got {p.dtype}, contiguous={p.is_contiguous()}); the kernels read raw fp32 memory")
-        P = self._params()
-        R, D, S = m.residual_channels, m.dilation_channels, m.skip_channels
-        E, Cc, k = m.end_conv_1.out_channels, m.classes, m.kernel_size
-        n1p, n2p = lib.wn_n1p(D), lib.wn_n2p(R + S)
-        f32 = dict(device=dev, dtype=torch.float32)
-        out = dict(layers=[])
-        for i in range(m.layers * m.blocks):
-            wfg = torch.empty(k * R, n1p, **f32)
-            bfg = torch.empty(n1p, **f32)
-            wrs = torch.empty(D, n2p, **f32)
-            brs = torch.empty(n2p, **f32)
-            (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
-            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
-            native.check(lib.wn_pack_gate_weights(wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg),
-                                                  R, D, k, wfg.data_ptr(), bfg.data_ptr(), stream), "pack gate")
-            native.check(lib.wn_pack_res_skip_weights(wr.data_ptr(), wsk.data_ptr(), native.ptr(br), native.ptr(bs),
-                                                      R, D, S, wrs.data_ptr(), brs.data_ptr(), stream), "pack res/skip")
-            out["layers"].append((wfg, bfg, wrs, brs))
-            if lib.wn_tc_supported(R, D, S, k):
-                wa = torch.empty(2, 2 * D, k * R, **f32)
-                ba = torch.empty(2 * D, **f32)
-                wb = torch.empty(2, R + S, D, **f32)
-                bb = torch.empty(R + S, **f32)
-                native.check(lib.wn_tc_pack_block_weights(
-                    wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
-                    native.ptr(br), native.ptr(bs), R, D, S, k, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
-                    bb.data_ptr(), stream), "pack tc")
-                out.setdefault("tc_layers", []).append((wa, ba, wb, bb))
-                out.setdefault("tc_layers_bf16", []).append((self._bf16_pairs(wa, stream), ba, self._bf16_pairs(wb, stream), bb))
-            if lib.wn_tc_bwd_supported(R, D, S, k):
-                wdz = torch.empty(2, D, R + S, **f32)
-                wdh = torch.empty(2, R, k * 2 * D, **f32)
-                native.check(lib.wn_tc_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
-                                                              R, D, S, k, wdz.data_ptr(), wdh.data_ptr(), stream), "pack tc bwd")
-                out.setdefault("tc_bwd_layers", []).append((wdz, wdh))
-                out.setdefault("tc_bwd_layers_bf16", []).append((self._bf16_pairs(wdz, stream), self._bf16_pairs(wdh, stream)))
-
-        if lib.wn_tb_supported(R, D, S, k):
-            nl = m.layers * m.blocks
-            per = lib.wn_tb_weight_bytes_per_layer()
-            tb_w = torch.empty(nl, per, device=dev, dtype=torch.uint8)
-            tb_b = torch.empty(nl, 4 * 256, **f32)
-            for i in range(nl):
-                (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
-                (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
-                native.check(lib.wn_tb_pack_block_weights(
-                    wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
-                    native.ptr(br), native.ptr(bs), tb_w[i].data_ptr(), tb_b[i].data_ptr(), stream), "pack tb")
-            out["tb"] = (tb_w, tb_b)
-
-        def pack1x1(w, b, N, K):
-            wt = torch.empty(K, lib.wn_n2p(N), **f32)
-            bp = torch.empty(lib.wn_n2p(N), **f32)
-            native.check(lib.wn_pack_1x1_weights(w.data_ptr(), native.ptr(b), N, K, wt.data_ptr(), bp.data_ptr(),
-                                                 stream), "pack 1x1")
-            return wt, bp
-
-        out["start"] = pack1x1(*P["start"], R, Cc)
-        out["end1"] = pack1x1(*P["end1"], E, S)
-        out["end2"] = pack1x1(*P["end2"], Cc, E)
-        self.packed, self.pack_key = out, key
-        return out
+        if key != self.pack_key or self.packed is None:
+            self.device()
+            for name, p in m.named_parameters():
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError(f"wavenet_b200: parameter {name} must be a contiguous float32 tensor "
+                                       f"(got {p.dtype}, contiguous={p.is_contiguous()}); the kernels read raw fp32 memory")
+            self.packed, self.pack_key = _Packs(self), key
+        return self.packed
 
     # ------------------------------------------------------------------ training-path forward
     def stack_forward(self, x, out_len, index_input=False, save=None):

@@ -63,5 +63,33 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, kernel_substring=None, key=None):
+    """Average dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels whose name contains
+    `kernel_substring` in an `ncu --set full` report -> entry `key` of profiles/traffic.json (read by bench.py)."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik, it = (hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name"),
+                      hdr.index("gpu__time_duration.sum"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals, times = [], []
+    for r in rows[2:]:
+        if kernel_substring and kernel_substring not in r[ik]:
+            continue
+        vals.append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+        times.append(float(r[it]))
+    d = json.load(open(dst)) if os.path.exists(dst) else {}
+    d[key or kernel_substring] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals),
+                                  "avg_duration_in_capture": sum(times) / len(times), "duration_unit": units[it],
+                                  "source": f"ncu --set full --clock-control none, {os.path.basename(src)}"}
+    json.dump(d, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps(d[key or kernel_substring]))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
