@@ -161,6 +161,37 @@ typedef struct wn_tb_block_args {
 } wn_tb_block_args;
 int    wn_tb_block_fwd(const wn_tb_block_args* a, void* stream);
 
+/* Backward of the same block on the same layout (tcgen05 cta_group::2, bf16 pairs), replacing autograd's backward through
+ * wavenet_model.py:142-165.  Frame-range arguments are those of wn_block_bwd_args.  Buffers: d_dh_out (B,2,32,L,8) pair or
+ * NULL (last layer), d_dskip (B,2,32,L-ds_start,8) pair on its own frame axis, d_fg the forward's d_fg_save, outputs d_dfg
+ * (B,2,64,L,8) pair [dF chunks 0..31 | dG chunks 32..63], d_z (B,2,32,L,8) pair (recomputed tanh*sigmoid), d_dh_in pair.
+ * d_wb_all: [n_layers][wn_tb_bwd_weight_bytes_per_layer()] images written by wn_tb_pack_block_bwd_weights. */
+size_t wn_tb_bwd_weight_bytes_per_layer(void);
+int    wn_tb_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws,
+                                    void* d_w_layer, void* stream);
+typedef struct wn_tb_bwd_args {
+    const void* d_dh_out; const void* d_dskip; const float* d_fg;
+    void* d_dfg; void* d_z; void* d_dh_in;
+    const void* d_wb_all;
+    int layer, n_layers;
+    int B, L, dilation;
+    int in_start, out_start;
+    int gs_out, ds_start, gz, gs_in;
+} wn_tb_bwd_args;
+int    wn_tb_block_bwd_data(const wn_tb_bwd_args* a, void* stream);
+/* All weight gradients of one block in one launch (+ a deterministic reduction): the contraction over frames reads the
+ * chunked tiles as MN-major tcgen05 operands.  Outputs are the parameter-shaped tensors: d_gws (S,D,1), d_gwr (R,D,1),
+ * d_gwf / d_gwg (D,R,2).  id_start: first frame where dh_out flows straight into dh_in (= max(out_start, gs_out)).
+ * d_work: wn_tb_wgrad_workspace_bytes() bytes. */
+size_t wn_tb_wgrad_workspace_bytes(void);
+typedef struct wn_tb_wgrad_args {
+    const void* d_dskip; const void* d_dh_out; const void* d_dfg; const void* d_z; const void* d_h_in;
+    float* d_gws; float* d_gwr; float* d_gwf; float* d_gwg; float* d_work;
+    int B, L, dilation;
+    int in_start, ds_start, id_start, gz;
+} wn_tb_wgrad_args;
+int    wn_tb_wgrad(const wn_tb_wgrad_args* a, void* stream);
+
 /* ---------------------------------------------------------------- (T) head
  * replaces relu -> end_conv_1 -> relu -> end_conv_2 (wavenet_model.py:167-169) and forward()'s
  * slice/transpose/view (:191-196): logits (B*out_len, classes) for the LAST out_len frames only.

@@ -64,6 +64,22 @@ class TbBlockArgs(C.Structure):
                 ("d_fg_save", C.c_void_p), ("d_z_save", C.c_void_p)]
 
 
+class TbBwdArgs(C.Structure):
+    _fields_ = [("d_dh_out", C.c_void_p), ("d_dskip", C.c_void_p), ("d_fg", C.c_void_p),
+                ("d_dfg", C.c_void_p), ("d_z", C.c_void_p), ("d_dh_in", C.c_void_p), ("d_wb_all", C.c_void_p),
+                ("layer", C.c_int), ("n_layers", C.c_int), ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
+                ("in_start", C.c_int), ("out_start", C.c_int),
+                ("gs_out", C.c_int), ("ds_start", C.c_int), ("gz", C.c_int), ("gs_in", C.c_int)]
+
+
+class TbWgradArgs(C.Structure):
+    _fields_ = [("d_dskip", C.c_void_p), ("d_dh_out", C.c_void_p), ("d_dfg", C.c_void_p), ("d_z", C.c_void_p),
+                ("d_h_in", C.c_void_p), ("d_gws", C.c_void_p), ("d_gwr", C.c_void_p), ("d_gwf", C.c_void_p),
+                ("d_gwg", C.c_void_p), ("d_work", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
+                ("in_start", C.c_int), ("ds_start", C.c_int), ("id_start", C.c_int), ("gz", C.c_int)]
+
+
 class HeadArgs(C.Structure):
     _fields_ = [("d_skip", C.c_void_p), ("d_logits", C.c_void_p),
                 ("d_w1_t", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2_t", C.c_void_p), ("d_b2", C.c_void_p),
@@ -119,6 +135,11 @@ SIGNATURES = {
     "wn_frames_from_pair": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_frames_from_chunks4": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "wn_tb_block_fwd": (C.c_int, [C.POINTER(TbBlockArgs), C.c_void_p]),
+    "wn_tb_bwd_weight_bytes_per_layer": (C.c_size_t, []),
+    "wn_tb_pack_block_bwd_weights": (C.c_int, [C.c_void_p] * 5 + [C.c_void_p]),
+    "wn_tb_block_bwd_data": (C.c_int, [C.POINTER(TbBwdArgs), C.c_void_p]),
+    "wn_tb_wgrad_workspace_bytes": (C.c_size_t, []),
+    "wn_tb_wgrad": (C.c_int, [C.POINTER(TbWgradArgs), C.c_void_p]),
     "wn_block_bwd_data": (C.c_int, [C.POINTER(BlockBwdArgs), C.c_void_p]),
     "wn_head_bwd_data": (C.c_int, [C.POINTER(HeadBwdArgs), C.c_void_p]),
     "wn_wgrad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -148,6 +148,17 @@ class _Packs:
                 native.ptr(br), native.ptr(bs), tb_w[i].data_ptr(), tb_b[i].data_ptr(), stream), "pack tb")
         return tb_w, tb_b
 
+    def _build_tb_bwd(self, stream):
+        rt, lib = self.rt, native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = rt._params()
+        wb = torch.empty(nl, lib.wn_tb_bwd_weight_bytes_per_layer(), device=rt.device(), dtype=torch.uint8)
+        for i in range(nl):
+            wf, wg, wr, wsk = P["filt"][i][0], P["gate"][i][0], P["res"][i][0], P["skip"][i][0]
+            native.check(lib.wn_tb_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
+                                                          wb[i].data_ptr(), stream), "pack tb bwd")
+        return wb
+
     def _pack1x1(self, wb, N, K, stream):
         lib = native.lib()
         f32 = dict(device=self.rt.device(), dtype=torch.float32)
@@ -261,15 +272,16 @@ class _Runtime:
         n_layers = len(dil)
         if os.environ.get("WN_CHECK_INDICES") and index_input and (int(x.min()) < 0 or int(x.max()) >= Cc):
             raise RuntimeError(f"wavenet_b200: class index outside [0, {Cc}) (the reference's one-hot scatter raises here)")
+        if self.tc_precision not in ("tf32x3", "bf16x2"):
+            raise ValueError(f"tc_precision must be 'tf32x3' or 'bf16x2', not {self.tc_precision!r}")
         if self.block_mode not in ("auto", "tb", "tc", "ffma"):
             raise ValueError(f"block_mode must be 'auto', 'tb', 'tc' or 'ffma', not {self.block_mode!r}")
-        use_tb = (self.block_mode in ("auto", "tb") and save is None and not self.fast_tf32 and
-                  bool(lib.wn_tb_supported(R, D, S, k)))
+        use_tb = (self.block_mode in ("auto", "tb") and not self.fast_tf32 and bool(lib.wn_tb_supported(R, D, S, k)))
         if self.block_mode == "tb" and not use_tb:
             raise RuntimeError("wavenet_b200: the fused tensor-core block needs R = D = S = 256, kernel_size = 2 "
-                               f"(got {R},{D},{S},{k}) and, for now, a no-grad forward")
+                               f"(got {R},{D},{S},{k})")
         if use_tb:
-            return self._forward_tb(x, index_input, B, L, plan, out_len, W, stream)
+            return self._forward_tb(x, index_input, B, L, plan, out_len, W, stream, save)
         if save is not None:
             h_all = torch.empty(n_layers + 1, B, L, R, **f32)      # h_all[i] = input of layer i
             fg_all = torch.empty(n_layers, B, L, 2 * D, **f32)     # tanh / sigmoid outputs
@@ -344,21 +356,29 @@ class _Runtime:
                         index_input=index_input, B=B, L=L)
         return logits
 
-    def _forward_tb(self, x, index_input, B, L, plan, out_len, W, stream):
-        """No-grad forward on the fused tensor-core blocks (wn_tb_block_fwd): chunked bf16-pair activations, one launch per
-        residual block, z resident on the SM (csrc/tc_block.cu)."""
+    def _forward_tb(self, x, index_input, B, L, plan, out_len, W, stream, save=None):
+        """Forward on the fused tensor-core blocks (wn_tb_block_fwd): chunked bf16-pair activations, one launch per residual
+        block, z resident on the SM (csrc/tc_block.cu).  With ``save`` every layer's input pair and tanh/sigmoid outputs are
+        kept for _backward_tb."""
         m, lib = self.model, native.lib()
         dev = self.device()
         R, S, Cc = m.residual_channels, m.skip_channels, m.classes
         E = m.end_conv_1.out_channels
         dil = [d for d, _ in m.dilations]
-        key = ("tb", B, L)
-        if key not in self.ws:
-            self.ws.clear()
-            bf16 = dict(device=dev, dtype=torch.bfloat16)
-            self.ws[key] = (torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16),
-                            torch.empty(B, S // 4, plan.t_final, 4, device=dev, dtype=torch.float32))
-        h0, h1, skip = self.ws[key]
+        n_layers = len(dil)
+        bf16 = dict(device=dev, dtype=torch.bfloat16)
+        if save is not None:
+            h_all = torch.empty(n_layers + 1, B, 2, R // 8, L, 8, **bf16)       # h_all[i] = input of layer i
+            fg_all = torch.empty(n_layers, B, 2 * R // 4, L, 4, device=dev, dtype=torch.float32)
+            skip = torch.empty(B, S // 4, plan.t_final, 4, device=dev, dtype=torch.float32)
+            h0 = h_all[0]
+        else:
+            key = ("tb", B, L)
+            if key not in self.ws:
+                self.ws.clear()
+                self.ws[key] = (torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16),
+                                torch.empty(B, S // 4, plan.t_final, 4, device=dev, dtype=torch.float32))
+            h0, h1, skip = self.ws[key]
         ws_t, bs_p = W["start"]
         if index_input:
             fn = lib.wn_tb_start_index_u8 if x.dtype == torch.uint8 else lib.wn_tb_start_index_i64
@@ -371,18 +391,23 @@ class _Runtime:
             del frames
         tb_w, tb_b = W["tb"]
         a = native.TbBlockArgs()
-        a.B, a.L, a.n_layers = B, L, len(dil)
+        a.B, a.L, a.n_layers = B, L, n_layers
         a.d_skip, a.skip_start, a.d_w_all = skip.data_ptr(), plan.skip_start, tb_w.data_ptr()
         a.d_fg_save = a.d_z_save = None
-        src, dst = h0, h1
+        src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
         ev = getattr(self, "block_events", None)
         if ev is not None:
             ev[0].record(torch.cuda.current_stream(dev))
         for i, d in enumerate(dil):
             a.d_h_in, a.d_h_out, a.layer, a.d_bias4 = src.data_ptr(), dst.data_ptr(), i, tb_b[i].data_ptr()
             a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
+            if save is not None:
+                a.d_fg_save = fg_all[i].data_ptr()
             native.check(lib.wn_tb_block_fwd(ctypes.byref(a), stream), f"tb block {i}")
-            src, dst = dst, src
+            if save is None:
+                src, dst = dst, src
+            elif i + 1 < n_layers:
+                src, dst = h_all[i + 1], h_all[i + 2]
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(dev))
         # head: the last out_len frames of skip, back in the frames layout of wn_head_fwd
@@ -397,9 +422,140 @@ class _Runtime:
         hd.B, hd.L, hd.S, hd.E, hd.classes, hd.skip_start, hd.out_len, hd.mode = B, L, S, E, Cc, L - out_len, out_len, 0
         native.check(lib.wn_head_fwd(ctypes.byref(hd), stream), "head")
         self.last_block_mode = "tb"
-        self.last_h_pair = src                       # output of the last block (debug / tests)
-        self.launches_last_forward = (1 if index_input else 2) + len(dil) + 2
+        self.launches_last_forward = (1 if index_input else 2) + n_layers + 2
+        if save is not None:
+            save.update(mode="tb", h_all=h_all, fg_all=fg_all, sk_frames=sk_frames, plan=plan, out_len=out_len, x=x,
+                        index_input=index_input, B=B, L=L)
         return logits
+
+    def _backward_tb(self, saved, dlogits):
+        """Backward on the chunked pair layout: head (SIMT kernels on the frames layout), then per block two tcgen05 data-
+        gradient launches (wn_tb_block_bwd_data) and one weight-gradient launch (wn_tb_wgrad).  Same frame-range logic as
+        stack_backward."""
+        m, lib = self.model, native.lib()
+        dev = self.device()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        W = self.packed_weights(stream)
+        P = self._params()
+        plan, B, L, OL = saved["plan"], saved["B"], saved["L"], saved["out_len"]
+        h_all, fg_all, sk_frames = saved["h_all"], saved["fg_all"], saved["sk_frames"]
+        R, D, S = m.residual_channels, m.dilation_channels, m.skip_channels
+        E, Cc, k = m.end_conv_1.out_channels, m.classes, m.kernel_size
+        dil = [d for d, _ in m.dilations]
+        n_layers = len(dil)
+        f32 = dict(device=dev, dtype=torch.float32)
+        bf16 = dict(device=dev, dtype=torch.bfloat16)
+        pad_cols = lambda w2d, n: torch.nn.functional.pad(w2d, (0, n - w2d.shape[1])).contiguous()
+        grads = {}
+        dlogits = dlogits.contiguous().view(B, OL, Cc)
+        # ---------------- head (frames layout; its skip input is the (B, OL, S) slice the forward made)
+        w1, b1 = P["end1"]
+        w2, b2 = P["end2"]
+        y1, dy1, dskip = torch.empty(B, OL, E, **f32), torch.empty(B, OL, E, **f32), torch.empty(B, OL, S, **f32)
+        w2_rows = pad_cols(w2.detach()[:, :, 0], lib.wn_n2p(E))
+        w1_rows = pad_cols(w1.detach()[:, :, 0], lib.wn_n2p(S))
+        hb = native.HeadBwdArgs()
+        hb.d_dlogits, hb.d_skip = dlogits.data_ptr(), sk_frames.data_ptr()
+        hb.d_y1, hb.d_dy1, hb.d_dskip = y1.data_ptr(), dy1.data_ptr(), dskip.data_ptr()
+        hb.d_w1_t, hb.d_b1 = W["end1"][0].data_ptr(), W["end1"][1].data_ptr()
+        hb.d_w2_rows, hb.d_w1_rows = w2_rows.data_ptr(), w1_rows.data_ptr()
+        hb.B, hb.L, hb.S, hb.E, hb.classes, hb.skip_start, hb.out_len = B, L, S, E, Cc, L - OL, OL
+        native.check(lib.wn_head_bwd_data(ctypes.byref(hb), stream), "head bwd")
+        ds_start = L - OL
+        rskip = torch.relu(sk_frames)
+        wg_work = torch.empty(max(lib.wn_wgrad_workspace_bytes(n_, c_) for n_, c_ in ((Cc, E), (E, S))) // 4, **f32)
+        wa = native.WgradArgs()
+        wa.d_work, wa.B = wg_work.data_ptr(), B
+        self.wgrad_tc_calls = 0
+
+        def head_wgrad(out, g, ldg, x, ldx, N, C):
+            wa.d_g, wa.d_x, wa.d_dw = g.data_ptr(), x.data_ptr(), out.data_ptr()
+            wa.ldg, wa.ldx, wa.g_seq_stride, wa.x_seq_stride = ldg, ldx, OL * ldg, OL * ldx
+            wa.rows, wa.N, wa.C, wa.dw_n_stride, wa.dw_c_stride = OL, N, C, C, 1
+            if OL >= 64 and lib.wn_tc_wgrad_supported(N, C):
+                native.check(lib.wn_tc_wgrad(ctypes.byref(wa), stream), "tc wgrad")
+                self.wgrad_tc_calls += 1
+            else:
+                native.check(lib.wn_wgrad(ctypes.byref(wa), stream), "wgrad")
+
+        gw2, gw1 = torch.empty(Cc, E, 1, **f32), torch.empty(E, S, 1, **f32)
+        head_wgrad(gw2, dlogits, Cc, y1, E, Cc, E)
+        head_wgrad(gw1, dy1, E, rskip, S, E, S)
+        grads["end_conv_2.weight"], grads["end_conv_1.weight"] = gw2, gw1
+        grads["end_conv_2.bias"] = dlogits.sum((0, 1))
+        grads["end_conv_1.bias"] = dy1.sum((0, 1))
+        reducer = getattr(self, "grad_reducer", None)
+        if reducer is not None:
+            reducer.reduce_async([grads[n] for n in ("end_conv_2.weight", "end_conv_2.bias", "end_conv_1.weight",
+                                                     "end_conv_1.bias")])
+        # ---------------- residual blocks, last to first
+        dskip_pair = torch.empty(B, 2, S // 8, OL, 8, **bf16)
+        native.check(lib.wn_pair_from_frames(dskip.data_ptr(), dskip_pair.data_ptr(), B, OL, S, 0, stream), "dskip pair")
+        dskip_bias = dskip.sum((0, 1)) if P["skip"][0][1] is not None else None
+        dfg = torch.empty(B, 2, 2 * D // 8, L, 8, **bf16)
+        zbuf = torch.empty(B, 2, D // 8, L, 8, **bf16)
+        dh_a, dh_b = torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16)
+        work = torch.empty(lib.wn_tb_wgrad_workspace_bytes() // 4, **f32)
+        wb_all = W["tb_bwd"]
+        a = native.TbBwdArgs()
+        a.B, a.L, a.n_layers, a.ds_start = B, L, n_layers, ds_start
+        a.d_dskip, a.d_dfg, a.d_z, a.d_wb_all = dskip_pair.data_ptr(), dfg.data_ptr(), zbuf.data_ptr(), wb_all.data_ptr()
+        g = native.TbWgradArgs()
+        g.B, g.L, g.ds_start = B, L, ds_start
+        g.d_dskip, g.d_dfg, g.d_z, g.d_work = dskip_pair.data_ptr(), dfg.data_ptr(), zbuf.data_ptr(), work.data_ptr()
+        dh_out, gs_out = None, L
+        self.last_bwd_mode = "tb"
+        for i in range(n_layers - 1, -1, -1):
+            d = dil[i]
+            in_s, out_s = plan.in_start[i], plan.out_start[i]
+            (wf, bf), (wgt, bg) = P["filt"][i], P["gate"][i]
+            (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
+            gz = max(out_s, min(gs_out, ds_start))
+            id_start = max(out_s, gs_out)
+            gs_in = max(in_s, min(id_start, gz - (k - 1) * d))
+            dh_in = dh_a if dh_out is not dh_a else dh_b
+            a.d_dh_out = None if dh_out is None else dh_out.data_ptr()
+            a.d_fg, a.d_dh_in, a.layer = fg_all[i].data_ptr(), dh_in.data_ptr(), i
+            a.dilation, a.in_start, a.out_start = d, in_s, out_s
+            a.gs_out, a.gz, a.gs_in = gs_out, gz, gs_in
+            native.check(lib.wn_tb_block_bwd_data(ctypes.byref(a), stream), f"tb block bwd {i}")
+            gws, gwr = torch.empty(S, D, 1, **f32), torch.empty(R, D, 1, **f32)
+            gwf, gwg = torch.empty(D, R, k, **f32), torch.empty(D, R, k, **f32)
+            g.d_dh_out, g.d_h_in = a.d_dh_out, h_all[i].data_ptr()
+            g.d_gws, g.d_gwr, g.d_gwf, g.d_gwg = gws.data_ptr(), gwr.data_ptr(), gwf.data_ptr(), gwg.data_ptr()
+            g.dilation, g.in_start, g.id_start, g.gz = d, in_s, id_start, gz
+            native.check(lib.wn_tb_wgrad(ctypes.byref(g), stream), f"tb wgrad {i}")
+            grads[f"skip_convs.{i}.weight"], grads[f"residual_convs.{i}.weight"] = gws, gwr
+            grads[f"filter_convs.{i}.weight"], grads[f"gate_convs.{i}.weight"] = gwf, gwg
+            if bs is not None:
+                grads[f"skip_convs.{i}.bias"] = dskip_bias.clone()
+            if br is not None:
+                grads[f"residual_convs.{i}.bias"] = (dh_out[:, :, :, id_start:, :].float().sum((0, 1, 3)).reshape(R)
+                                                     if dh_out is not None and id_start < L else torch.zeros_like(br))
+            if bf is not None:
+                bsum = dfg[:, :, :, gz:, :].float().sum((0, 1, 3)).reshape(2 * D)
+                grads[f"filter_convs.{i}.bias"], grads[f"gate_convs.{i}.bias"] = bsum[:D].clone(), bsum[D:].clone()
+            if reducer is not None:
+                reducer.reduce_async([grads.get(f"{n}.{i}.{wb}") for n in ("filter_convs", "gate_convs", "residual_convs",
+                                                                         "skip_convs") for wb in ("weight", "bias")])
+            dh_out, gs_out = dh_in, gs_in
+        # ---------------- start conv
+        dh0_frames = torch.empty(B, L, R, **f32)
+        native.check(lib.wn_frames_from_pair(dh_out.data_ptr(), dh0_frames.data_ptr(), B, L, R, gs_out, stream), "dh0 frames")
+        dh0 = dh0_frames[:, gs_out:, :]
+        x = saved["x"]
+        if saved["index_input"]:
+            table = torch.zeros(Cc, R, **f32)
+            table.index_add_(0, x[:, gs_out:].reshape(-1).long(), dh0.reshape(-1, R))
+            grads["start_conv.weight"] = table.t().contiguous().unsqueeze(-1)
+        else:
+            grads["start_conv.weight"] = torch.einsum("btr,bct->rc", dh0, x[:, :, gs_out:]).unsqueeze(-1)
+        if P["start"][1] is not None:
+            grads["start_conv.bias"] = dh0.sum((0, 1))
+        if reducer is not None:
+            reducer.reduce_async([grads["start_conv.weight"], grads.get("start_conv.bias")])
+            reducer.wait_all()
+        return grads
 
     # ------------------------------------------------------------------ training-path backward
     def stack_backward(self, saved, dlogits):
@@ -407,6 +563,8 @@ class _Runtime:
         wn_*_bwd_data kernels, the weight gradients on wn_tc_wgrad / wn_wgrad over the buffers those kernels produce
         (bias gradients are row sums; the start-conv gradient is a scatter-add of dh over the input indices).
         Returns a dict name -> gradient tensor shaped like the parameter."""
+        if saved.get("mode") == "tb":
+            return self._backward_tb(saved, dlogits)
         m, lib = self.model, native.lib()
         dev = self.device()
         stream = torch.cuda.current_stream(dev).cuda_stream
