@@ -87,7 +87,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * EPI_WARPS); }
-        for (int i = 0; i < 8; ++i) mbar_init(z_ready + i, 2 * (EPI_WARPS / 2));
+        for (int i = 0; i < 8; ++i) mbar_init(z_ready + i, 2 * EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -219,9 +219,11 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 tc_fence_after();
                 const unsigned ta = lane_addr + j * 256;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-                    for (int c = grp * 64 + half * 32; c < grp * 64 + half * 32 + 32; c += 16) {
+                for (int sb = 0; sb < 4; ++sb) {
+                    // slab sb of this n-tile = 32 dilation channels; the two column groups take 16 each, so the slabs become
+                    // ready in the order pass B consumes them
+                    {
+                        const int c = sb * 32 + grp * 16;
                         float f[16], g[16];
                         tmem_ld16(ta + c, f);
                         tmem_ld16(ta + 128 + c, g);
@@ -261,10 +263,10 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                             zs[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                         }
                     }
-                    // z slab (32 channels) 4j + 2*grp + half of this CTA is complete for this warp's 32 rows
+                    // this warp's 32 rows x 16 channels of z slab 4j + sb are in shared memory
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(z_ready_addr + 8u * (unsigned)(4 * j + 2 * grp + half));
+                    if (lane == 0) mbar_arrive_cluster(z_ready_addr + 8u * (unsigned)(4 * j + sb));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -278,16 +280,21 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 const unsigned ta = lane_addr;
                 const uint4* hin = p.h_in + (size_t)b * 2 * plane_stride + t;
                 uint4* hout = p.h_out + (size_t)b * 2 * plane_stride + t;
+                uint4 nx[4];
+                auto load_res = [&](int c) {
+                    nx[0] = nx[1] = nx[2] = nx[3] = make_uint4(0, 0, 0, 0);
+                    if (live) {
+                        const uint4* s = hin + (size_t)(c / 8) * p.L;
+                        nx[0] = __ldg(s); nx[1] = __ldg(s + p.L); nx[2] = __ldg(s + plane_stride); nx[3] = __ldg(s + plane_stride + p.L);
+                    }
+                };
+                load_res(grp * 128);
 #pragma unroll 1
                 for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
                     float v[16];
                     tmem_ld16(ta + c, v);
-                    uint4 xh0, xh1, xl0, xl1;
-                    xh0 = xh1 = xl0 = xl1 = make_uint4(0, 0, 0, 0);
-                    if (live) {
-                        const uint4* s = hin + (size_t)(c / 8) * p.L;
-                        xh0 = __ldg(s); xh1 = __ldg(s + p.L); xl0 = __ldg(s + plane_stride); xl1 = __ldg(s + plane_stride + p.L);
-                    }
+                    const uint4 xh0 = nx[0], xh1 = nx[1], xl0 = nx[2], xl1 = nx[3];
+                    if (c + 16 < grp * 128 + 128) load_res(c + 16);        // next chunk's loads fly under this chunk's math
                     tmem_ld_wait();
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + 2 * CH + c);
                     const unsigned xh[8] = {xh0.x, xh0.y, xh0.z, xh0.w, xh1.x, xh1.y, xh1.z, xh1.w};
@@ -321,16 +328,22 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 const unsigned ta = lane_addr + 256;
                 const bool on = live && t >= p.skip_start;
                 float4* sk = p.skip + (size_t)b * (CH / 4) * Tsk + (t - p.skip_start);
+                float4 nx[4];
+                const bool rmw = on && !p.skip_init;
+                auto load_skip = [&](int c) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        nx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rmw) nx[i] = sk[(size_t)(c / 4 + i) * Tsk];
+                    }
+                };
+                load_skip(grp * 128);
 #pragma unroll 1
                 for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
                     float v[16];
                     tmem_ld16(ta + c, v);
-                    float4 x[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (on && !p.skip_init) x[i] = sk[(size_t)(c / 4 + i) * Tsk];
-                    }
+                    const float4 x[4] = {nx[0], nx[1], nx[2], nx[3]};
+                    if (c + 16 < grp * 128 + 128) load_skip(c + 16);
                     tmem_ld_wait();
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + 3 * CH + c);
                     if (on) {

@@ -995,9 +995,33 @@ class WaveNetModel(nn.Module):
 
     # ------------------------------------------------------------------ generation
     def generate(self, num_samples, first_samples=None, temperature=1.):
-        """The reference's slow generate() is dead code there (it raises AttributeError on ``self.scope``,
-        wavenet_model.py:209); kept as a stub that points to generate_fast."""
-        raise NotImplementedError("generate() is broken in the reference (wavenet_model.py:209); use generate_fast()")
+        """The slow sampler (reference wavenet_model.py:198-235): every new sample re-evaluates the whole stack on a window
+        of the last ``receptive_field`` samples.  The reference's own body cannot run (``self.scope`` at :209 does not exist
+        and :230-235 concatenates Long and Float tensors); this restates its evident intent with the same schedule: the
+        given samples are left-padded with zeros (class 0) to one receptive field, each step takes the last column of the
+        training-path forward on the window, draws with numpy's global RNG (or the argmax for ``temperature == 0``) and
+        appends.  Returns the mu-law expanded float64 waveform of the WHOLE sequence (padding + given + generated), as the
+        reference's closing lines do.  One device->host sync per sample: use generate_fast for anything but cross-checks."""
+        self.eval()
+        first = np.zeros(1, dtype=np.int64) if first_samples is None else self._first_array(first_samples)
+        rf = self.receptive_field
+        if first.shape[0] < rf:
+            first = np.concatenate([np.zeros(rf - first.shape[0], dtype=np.int64), first])
+        seq = list(first.tolist())
+        rt = self._runtime()
+        dev = rt.device()
+        with torch.no_grad(), torch.cuda.device(dev):
+            for _ in range(num_samples):
+                window = torch.tensor(seq[-rf:], dtype=torch.int64, device=dev).view(1, rf)
+                x = rt.stack_forward(window, 1, index_input=True)[0]
+                if temperature > 0:
+                    prob = torch.softmax(x / temperature, dim=0).cpu().numpy()
+                    seq.append(int(np.random.choice(self.classes, p=prob)))
+                else:
+                    seq.append(int(torch.argmax(x)))
+        self.train()
+        generated = (np.asarray(seq, dtype=np.float64) / self.classes) * 2. - 1
+        return mu_law_expansion(generated, self.classes)
 
     def _first_array(self, first_samples):
         if first_samples is None:

@@ -51,6 +51,8 @@ def separate_head_relu_ties(params, spec, x, out_len, margin=2e-5, step=1e-4):
     sk = taps["skip"][..., -out_len:].clone()                           # (B, S, out_len)
     for name, pre_of in ((f"skip_convs.{last}.bias", lambda: sk),
                          ("end_conv_1.bias", lambda: F_conv1d(torch.relu(sk), p["end_conv_1.weight"], p["end_conv_1.bias"]))):
+        if name not in p:              # bias=False nets have no skip bias to nudge: see tie_free_indices
+            continue
         pre = pre_of()
         for c in range(pre.shape[1]):
             v, off = pre[:, c, :], 0.0
@@ -59,6 +61,19 @@ def separate_head_relu_ties(params, spec, x, out_len, margin=2e-5, step=1e-4):
             p[name][c] += off
             pre[:, c, :] += off
     return {k: v.float() for k, v in p.items()}
+
+
+def tie_free_indices(params, spec, B, L, out_len, margin=5e-6, seed0=2, tries=30):
+    """(B, L) class indices for which no relu(skip) input of the oracle lies within `margin` of zero: the alternative to a
+    bias nudge for nets without skip biases.  Feasible only for small B * out_len (the chance of a miss grows with it)."""
+    p = {k: v.detach().double() for k, v in params.items()}
+    for s in range(seed0, seed0 + tries):
+        idx = torch.randint(0, spec.classes, (B, L), generator=torch.Generator().manual_seed(s))
+        taps = {}
+        O.stack_direct(p, spec, O.one_hot(idx, spec.classes).double(), taps)
+        if float(taps["skip"][..., -out_len:].abs().min()) > margin:
+            return idx
+    raise RuntimeError("no tie-free input found")
 
 
 def F_conv1d(x, w, b):

@@ -288,3 +288,22 @@ def test_generate_fast_from_cpu_model(golden):
     b = build_model(g).generate_fast(24, first_samples=g["first"], temperature=0.0)
     assert np.array_equal(a, b) and m_cpu.start_conv.weight.device.type == "cpu"
     assert m_cpu.dilated_queues[0].data.shape[0] == m_cpu.residual_channels
+
+
+def test_slow_generate_equals_generate_fast(golden):
+    """generate() (the repaired slow path, reference wavenet_model.py:198-235) and generate_fast() are two evaluations of the
+    same network: with a full receptive field of given samples their argmax continuations coincide (up to a near-tie)."""
+    g = golden("net_odd_bias.npz")
+    m = build_model(g)
+    rf = m.receptive_field
+    first = g["first"][:rf]
+    slow = m.generate(12, first_samples=first, temperature=0.0)
+    assert slow.dtype == np.float64 and slow.shape == (rf + 12,) and m.training
+    fast = m.generate_fast(12, first_samples=first, temperature=0.0)
+    idx_slow = np.rint((O.mu_law_encoding(slow[rf:], 256) + 1) * 128).astype(np.int64)
+    idx_fast = np.rint((O.mu_law_encoding(fast, 256) + 1) * 128).astype(np.int64)
+    _, lg = m.generate_fast_batch(12, first[None, :], temperature=0.0, forced=idx_fast[None, :], return_logits=True)
+    assert_stream_parity(idx_slow, idx_fast, lg[0])
+    # fewer given samples than the receptive field: zero (class 0) padding on the left, as the reference intends
+    short = m.generate(3, first_samples=first[:4], temperature=0.0)
+    assert short.shape == (rf + 3,) and np.array_equal(short[:rf - 4], np.full(rf - 4, audio_of([0])[0]))

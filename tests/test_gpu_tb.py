@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import wavenet_oracle as O
-from helpers import build_model, one_hot_cuda, rel_err, separate_head_relu_ties
+from helpers import build_model, one_hot_cuda, rel_err, separate_head_relu_ties, tie_free_indices
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -120,8 +120,8 @@ def test_tb_mode_requires_supported_shape(golden):
 
 @pytest.mark.parametrize("B,L,layers,blocks,bias,out_len", [
     (2, 420, 3, 2, True, 150),
-    (3, 700, 4, 2, False, 300),        # several 256-frame items, gradients start inside an item
-    (1, 1100, 6, 1, True, 37),         # most frames lie outside the receptive cone of the outputs (structurally zero)
+    (3, 700, 4, 2, True, 300),         # several 256-frame items, gradients start inside an item
+    (1, 1100, 6, 1, False, 37),        # no biases; most frames lie outside the receptive cone of the outputs
 ])
 def test_fused_backward_matches_oracle_and_simt(B, L, layers, blocks, bias, out_len):
     """Training step through the chunked-pair kernels (forward with saved activations, tcgen05 data gradients, MN-major
@@ -135,9 +135,12 @@ def test_fused_backward_matches_oracle_and_simt(B, L, layers, blocks, bias, out_
     spec = O.NetSpec(**kw)
     idx = torch.randint(0, 256, (B, L), generator=torch.Generator().manual_seed(2))
     tgt = torch.randint(0, 256, (B * out_len,), generator=torch.Generator().manual_seed(3))
-    # keep head ReLU inputs away from zero: a mask flipped by rounding noise is a discontinuity of the gradient itself
-    if bias:
-        m.load_state_dict(separate_head_relu_ties(m.state_dict(), spec, O.one_hot(idx, 256), out_len), strict=True)
+    # keep head ReLU inputs away from zero: a mask flipped by rounding noise is a discontinuity of the gradient itself (one
+    # flipped element perturbs EVERY gradient by ~1e-3 through dskip).  Biases are nudged where they exist; a net without
+    # skip biases gets an input whose relu(skip) arguments all stay clear of zero.
+    if not bias:
+        idx = tie_free_indices(m.state_dict(), spec, B, L, out_len)
+    m.load_state_dict(separate_head_relu_ties(m.state_dict(), spec, O.one_hot(idx, 256), out_len), strict=True)
     p = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     F.cross_entropy(O.forward(p, spec, O.one_hot(idx, 256)), tgt).backward()
     m = m.cuda()
@@ -159,13 +162,7 @@ def test_fused_backward_matches_oracle_and_simt(B, L, layers, blocks, bias, out_
         if scale == 0:
             assert np.abs(grads["auto"][k]).max() == 0, k
             continue
-        d_t, d_f = np.abs(grads["auto"][k] - want) / scale, np.abs(grads["ffma"][k] - want) / scale
-        if bias:
-            ok = d_t.max() < 1e-4 and d_f.max() < 1e-4
-        else:
-            # no skip biases to nudge: a relu(skip) input within rounding noise of zero may take the other branch in one
-            # implementation, which moves the few gradient entries it feeds by up to percent -- allow 0.1 % such entries
-            ok = (np.quantile(d_t, 0.999) < 1e-4 and d_t.max() < 5e-2 and np.quantile(d_f, 0.999) < 1e-4 and d_f.max() < 5e-2)
-        if not ok:
-            bad.append((k, float(scale), float(d_t.max()), float(d_f.max())))
+        e_t, e_f = np.abs(grads["auto"][k] - want).max() / scale, np.abs(grads["ffma"][k] - want).max() / scale
+        if not (e_t < 1e-4 and e_f < 1e-4):
+            bad.append((k, float(scale), float(e_t), float(e_f)))
     assert not bad, bad[:10]

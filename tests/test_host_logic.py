@@ -144,3 +144,42 @@ def test_shape_predicates_and_workspace_sizes_are_host_side():
     assert lib.wn_tc_wgrad(ctypes.byref(a), None) < 0 and b"C == 256" in lib.wn_last_error_string()
     assert lib.wn_tc_block_bwd_data_prec(None, None, None, 0, None) < 0
     assert lib.wn_tc_convert_weights_bf16(None, None, 0, None) < 0
+
+
+def test_dataset_matches_reference_items(golden):
+    """WavenetDataset (reference audio_data.py:12-131): same lengths, same item -> sample-window map (incl. windows that
+    cross array boundaries and the train / test split), and the index mode (one_hot=False)
+    returns exactly the indices whose one-hot matrix the reference builds."""
+    import os
+    from conftest import GOLDEN
+    import audio_data
+    g = golden("dataset_items.npz")
+    tiny = os.path.join(GOLDEN, "tiny_dataset.npz")
+    keys = sorted(k[:-4] for k in g.files if k.endswith("_cfg"))
+    assert len(keys) == 8
+    for key in keys:
+        item_length, target_length, stride, train, n = [int(v) for v in g[key + "_cfg"]]
+        for one_hot in (True, False):
+            ds = audio_data.WavenetDataset(dataset_file=tiny, item_length=item_length, target_length=target_length,
+                                           test_stride=stride, train=bool(train), one_hot=one_hot)
+            assert len(ds) == n, key
+            for j, i in enumerate(g[key + "_picks"]):
+                x, t = ds[int(i)]
+                assert np.array_equal(t.numpy(), g[key + "_t"][j])
+                if one_hot:
+                    assert x.shape == (256, item_length) and x.dtype == torch.float32 and float(x.sum()) == item_length
+                    assert np.array_equal(x.argmax(0).numpy(), g[key + "_x"][j])
+                else:
+                    assert x.dtype == torch.uint8 and np.array_equal(x.numpy(), g[key + "_x"][j])
+
+
+def test_write_wav_roundtrip(tmp_path):
+    import wave
+    import audio_data
+    audio = np.sin(np.linspace(0, 40, 1600)) * 0.5
+    path = str(tmp_path / "clip.wav")
+    audio_data.write_wav(path, audio, sr=16000)
+    with wave.open(path, "rb") as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, 1600)
+        pcm = np.frombuffer(f.readframes(1600), dtype="<i2")
+    assert np.abs(pcm / 32767.0 - audio).max() < 1e-4
