@@ -269,6 +269,28 @@ int wn_wgrad(const wn_wgrad_args* a, void* stream);
 int wn_tc_wgrad_supported(int N, int C);
 int wn_tc_wgrad(const wn_wgrad_args* a, void* stream);
 
+/* ---------------------------------------------------------------- (T) the rest of a training step
+ * What WavenetTrainer.train does around model(x) (reference wavenet_training.py:64-76), as native launches:
+ * wn_ce_fwd_bwd: F.cross_entropy(output, target) (:69) AND its gradient in one pass: *d_loss = mean_i(logsumexp(x_i) -
+ *   x_i[target_i]), d_dlogits = (softmax(x_i) - onehot(target_i)) / N (may not alias d_logits); deterministic; *d_err
+ *   (optional) is set when a target is outside [0, C).  d_work: wn_ce_workspace_bytes().  C <= 1024.
+ * wn_adam_step: torch.optim.Adam's update (the reference's default optimizer, :24) of every tensor in one launch.  d_segs
+ *   is a DEVICE array of segments, d_chunks a DEVICE array of (segment, chunk-of-4096) int pairs covering them.
+ * wn_scatter_rows: start_conv gradient for index input: table (classes, R) = sum over frames t >= t_begin of dh[b][t][:]
+ *   into row idx[b][t] (idx uint8 or int64, (B, L)); wn_colsum: out[c] = sum_r x[r][c] (bias gradients), d_work
+ *   wn_colsum_workspace_bytes(rows, C); wn_relu_copy: y = max(x, 0) (the head's relu(skip) operand of a weight gradient). */
+size_t wn_ce_workspace_bytes(void);
+int    wn_ce_fwd_bwd(const float* d_logits, const int64_t* d_target, float* d_dlogits, float* d_loss, float* d_work, int* d_err,
+                     int N, int C, void* stream);
+typedef struct wn_adam_seg { float* p; const float* g; float* m; float* v; long long n; } wn_adam_seg;
+int    wn_adam_step(const wn_adam_seg* d_segs, const int* d_chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream);
+int    wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, float* d_table, int B, int L, int R, int classes,
+                       int t_begin, void* stream);
+size_t wn_colsum_workspace_bytes(long long rows, int C);
+int    wn_colsum(const float* d_x, float* d_out, float* d_work, long long rows, int C, int ld, void* stream);
+int    wn_relu_copy(const float* d_x, float* d_y, long long n, void* stream);
+
 /* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
  * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with
  * DilatedQueue.enqueue/dequeue/reset (wavenet_modules.py:55-77): ONE persistent cooperative kernel runs

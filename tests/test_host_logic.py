@@ -118,7 +118,7 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 256, 16))
     with pytest.raises(RuntimeError, match="CUDA"):
         m.generate_fast(4)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         m.generate(4)
 
 
