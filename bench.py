@@ -392,6 +392,7 @@ def bench_train(args, world, rank):
     # full training step on the same shapes: forward (saving activations) + backward + per-block gradient all-reduce
     import torch.nn.functional as F
     import data_parallel as dp
+    import wavenet_training as wt
     red = dp.make_data_parallel(model)
     target = torch.randint(0, 256, (B * model.output_length,), generator=torch.Generator().manual_seed(99 + rank)).cuda()
     step_ms = []
@@ -400,7 +401,7 @@ def bench_train(args, world, rank):
         barrier_sync(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loss = F.cross_entropy(model.forward_indices(d_idx), target)
+        loss = wt.fused_cross_entropy(model.forward_indices(d_idx), target)
         loss.backward()
         e1.record()
         torch.cuda.synchronize()
@@ -426,7 +427,7 @@ def bench_train(args, world, rank):
             barrier_sync(world)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            F.cross_entropy(model.forward_indices(mine), mine_t).backward()
+            wt.fused_cross_entropy(model.forward_indices(mine), mine_t).backward()
             e1.record()
             torch.cuda.synchronize()
             if i > 0:

@@ -145,6 +145,9 @@ int    wn_tb_start_index_u8(const uint8_t* d_idx, const float* d_w_t, const floa
                             int B, int classes, int L, int R, int* d_err, void* stream);
 int    wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair,
                              int B, int classes, int L, int R, int* d_err, void* stream);
+/* all layers in one launch each: d_ptrs is a DEVICE table [n_layers][8] of {wf, wg, bf, bg, wr, ws, br, bs} (biases may be 0) */
+int    wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, void* d_w_all, float* d_bias_all, void* stream);
+int    wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, void* d_wb_all, void* stream);
 int    wn_pair_from_frames(const float* d_frames, void* d_pair, int B, int L, int C, int t_begin, void* stream);
 int    wn_frames_from_pair(const void* d_pair, float* d_frames, int B, int L, int C, int t_begin, void* stream);
 /* frames [t_first, t_first + n) of a chunked fp32 tensor (B, C/4, T, 4) -> (B, n, C) */
@@ -277,7 +280,8 @@ int wn_tc_wgrad(const wn_wgrad_args* a, void* stream);
  * wn_adam_step: torch.optim.Adam's update (the reference's default optimizer, :24) of every tensor in one launch.  d_segs
  *   is a DEVICE array of segments, d_chunks a DEVICE array of (segment, chunk-of-4096) int pairs covering them.
  * wn_scatter_rows: start_conv gradient for index input: table (classes, R) = sum over frames t >= t_begin of dh[b][t][:]
- *   into row idx[b][t] (idx uint8 or int64, (B, L)); wn_colsum: out[c] = sum_r x[r][c] (bias gradients), d_work
+ *   into row idx[b][t] (idx uint8 or int64, (B, L)), optionally also transposed into d_out_t (R, classes) = the layout of
+ *   start_conv.weight; wn_colsum: out[c] = sum_r x[r][c] (bias gradients), d_work
  *   wn_colsum_workspace_bytes(rows, C); wn_relu_copy: y = max(x, 0) (the head's relu(skip) operand of a weight gradient). */
 size_t wn_ce_workspace_bytes(void);
 int    wn_ce_fwd_bwd(const float* d_logits, const int64_t* d_target, float* d_dlogits, float* d_loss, float* d_work, int* d_err,
@@ -285,8 +289,8 @@ int    wn_ce_fwd_bwd(const float* d_logits, const int64_t* d_target, float* d_dl
 typedef struct wn_adam_seg { float* p; const float* g; float* m; float* v; long long n; } wn_adam_seg;
 int    wn_adam_step(const wn_adam_seg* d_segs, const int* d_chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream);
-int    wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, float* d_table, int B, int L, int R, int classes,
-                       int t_begin, void* stream);
+int    wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, float* d_table, float* d_out_t, int B, int L, int R,
+                       int classes, int t_begin, void* stream);
 size_t wn_colsum_workspace_bytes(long long rows, int C);
 int    wn_colsum(const float* d_x, float* d_out, float* d_work, long long rows, int C, int ld, void* stream);
 int    wn_relu_copy(const float* d_x, float* d_y, long long n, void* stream);

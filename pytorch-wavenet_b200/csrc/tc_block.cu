@@ -395,6 +395,37 @@ __global__ void pack_block_kernel(const float* __restrict__ wf, const float* __r
         o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
+// all layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs}; blockIdx.y = layer
+__global__ void pack_block_all_kernel(const float* const* __restrict__ ptrs, __nv_bfloat16* __restrict__ out_all, float* __restrict__ bias_all) {
+    const float* const* q = ptrs + (size_t)blockIdx.y * 8;
+    const float* wf = q[0]; const float* wg = q[1]; const float* wr = q[4]; const float* ws = q[5];
+    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (W_LAYER_BYTES / 2);
+    const int n_a = 2 * SLABS_A * 2, n_blocks = n_a + 2 * SLABS_B * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
+         i += (long long)gridDim.x * blockDim.x) {
+        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));
+        const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
+        float v;
+        if (blk < n_a) {
+            const int j = blk / (SLABS_A * 2), sl = (blk / 2) % SLABS_A, r = blk % 2;
+            const int kk = sl * KS + ck * 8 + e, tap = kk / CH, cin = kk % CH, cout = j * 128 + row;
+            v = (r == 0 ? wf : wg)[((size_t)cout * CH + cin) * 2 + tap];
+        } else {
+            const int bb = blk - n_a, j = bb / (SLABS_B * 2), s8 = (bb / 2) % SLABS_B, r = bb % 2;
+            const int cin = s8 * KS + ck * 8 + e, cout = r * 128 + row;
+            v = (j == 0 ? wr : ws)[(size_t)cout * CH + cin];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
+        o[0] = h;
+        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 4 * CH; i += blockDim.x) {
+            const float* src = i < CH ? q[2] : (i < 2 * CH ? q[3] : (i < 3 * CH ? q[6] : q[7]));
+            bias_all[(size_t)blockIdx.y * 4 * CH + i] = src ? src[i % CH] : 0.f;
+        }
+}
 __global__ void pack_bias_kernel(const float* bf, const float* bg, const float* br, const float* bs, float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4 * CH) return;
@@ -530,6 +561,13 @@ extern "C" int wn_tb_pack_block_weights(const float* d_wf, const float* d_wg, co
     cudaStream_t st = (cudaStream_t)stream;
     tb::pack_block_kernel<<<296, 256, 0, st>>>(d_wf, d_wg, d_wr, d_ws, (__nv_bfloat16*)d_w_layer);
     tb::pack_bias_kernel<<<4, 256, 0, st>>>(d_bf, d_bg, d_br, d_bs, d_bias4);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, void* d_w_all, float* d_bias_all, void* stream) {
+    WN_REQUIRE(d_ptrs && d_w_all && d_bias_all && n_layers > 0, WN_E_BADARG, "wn_tb_pack_all_weights: bad arguments");
+    tb::pack_block_all_kernel<<<dim3(74, n_layers), 256, 0, (cudaStream_t)stream>>>(d_ptrs, (__nv_bfloat16*)d_w_all, d_bias_all);
     WN_CUDA(cudaGetLastError());
     return 0;
 }

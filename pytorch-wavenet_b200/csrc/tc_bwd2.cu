@@ -267,6 +267,32 @@ __global__ void pack_bwd_kernel(const float* __restrict__ wf, const float* __res
     }
 }
 
+// all layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs} (the table of wn_tb_pack_all_weights)
+__global__ void pack_bwd_all_kernel(const float* const* __restrict__ ptrs, __nv_bfloat16* __restrict__ out_all) {
+    const float* const* q = ptrs + (size_t)blockIdx.y * 8;
+    const float* wf = q[0]; const float* wg = q[1]; const float* wr = q[4]; const float* ws = q[5];
+    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (WB_LAYER_BYTES / 2);
+    const int n_dz = SLABS_DZ * 2, n_blocks = n_dz + SLABS_DH * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
+         i += (long long)gridDim.x * blockDim.x) {
+        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));
+        const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
+        float v;
+        if (blk < n_dz) {
+            const int sl = blk / 2, r = blk % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
+            v = kk < CH ? wr[(size_t)kk * CH + n] : ws[(size_t)(kk - CH) * CH + n];
+        } else {
+            const int bb = blk - n_dz, sl = bb / 2, r = bb % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
+            const int tap = kk / (2 * CH), m = kk % (2 * CH);
+            v = m < CH ? wf[((size_t)m * CH + n) * 2 + tap] : wg[((size_t)(m - CH) * CH + n) * 2 + tap];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
+        o[0] = h;
+        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 // ============================================================================================== weight gradients
 constexpr int WG_KF = 32;                         // frames per k-slab: slot image [plane 2][chunk 16][frame 32][16 B]
 constexpr int WG_NSLOT = 8;
@@ -418,6 +444,13 @@ extern "C" int wn_tb_pack_block_bwd_weights(const float* d_wf, const float* d_wg
                                             void* d_w_layer, void* stream) {
     WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_w_layer, WN_E_BADARG, "wn_tb_pack_block_bwd_weights: null pointer");
     tb2::pack_bwd_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d_wf, d_wg, d_wr, d_ws, (__nv_bfloat16*)d_w_layer);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, void* d_wb_all, void* stream) {
+    WN_REQUIRE(d_ptrs && d_wb_all && n_layers > 0, WN_E_BADARG, "wn_tb_pack_all_bwd_weights: bad arguments");
+    tb2::pack_bwd_all_kernel<<<dim3(74, n_layers), 256, 0, (cudaStream_t)stream>>>(d_ptrs, (__nv_bfloat16*)d_wb_all);
     WN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -119,6 +119,20 @@ __global__ void scatter_rows_kernel(const IDX* __restrict__ idx, const float* __
     }
 }
 
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {      // out[c][r] = in[r][c]
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
 // column sums of rows [0, rows) of x (rows, ld) -> out[C]; stage 1: per block partials, stage 2: fixed-order sum
 constexpr int CS_ROWS = 256;
 __global__ void colsum_part_kernel(const float* __restrict__ x, float* __restrict__ part, long long rows, int C, int ld) {
@@ -174,15 +188,18 @@ extern "C" int wn_adam_step(const wn_adam_seg* d_segs, const int* d_chunks, int 
     return 0;
 }
 
-extern "C" int wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, float* d_table, int B, int L, int R, int classes,
-                               int t_begin, void* stream) {
+extern "C" int wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, float* d_table, float* d_out_t, int B, int L, int R,
+                               int classes, int t_begin, void* stream) {
     WN_REQUIRE(d_idx && d_dh && d_table && B > 0 && L > 0 && R > 0 && classes > 0 && t_begin >= 0 && t_begin <= L, WN_E_BADARG,
                "wn_scatter_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     WN_CUDA(cudaMemsetAsync(d_table, 0, sizeof(float) * (size_t)classes * R, st));
-    if (t_begin == L) return 0;
-    if (idx_is_u8) misc::scatter_rows_kernel<uint8_t><<<592, 256, 0, st>>>((const uint8_t*)d_idx, d_dh, d_table, B, L, R, classes, t_begin);
-    else misc::scatter_rows_kernel<long long><<<592, 256, 0, st>>>((const long long*)d_idx, d_dh, d_table, B, L, R, classes, t_begin);
+    if (t_begin < L) {
+        if (idx_is_u8) misc::scatter_rows_kernel<uint8_t><<<592, 256, 0, st>>>((const uint8_t*)d_idx, d_dh, d_table, B, L, R, classes, t_begin);
+        else misc::scatter_rows_kernel<long long><<<592, 256, 0, st>>>((const long long*)d_idx, d_dh, d_table, B, L, R, classes, t_begin);
+    }
+    if (d_out_t)      // (R, classes): the layout of start_conv.weight
+        misc::transpose_kernel<<<dim3((R + 31) / 32, (classes + 31) / 32), dim3(32, 8), 0, st>>>(d_table, d_out_t, classes, R);
     WN_CUDA(cudaGetLastError());
     return 0;
 }

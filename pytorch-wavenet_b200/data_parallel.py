@@ -35,9 +35,26 @@ class GradientAverager:
         self.bytes_reduced += flat.numel() * flat.element_size()
         self.buckets += 1
 
+    def reduce_flat_async(self, flat):
+        """All-reduce (average) ONE contiguous bucket in place: the gradient tensors are views of it, so there is no
+        flatten pass before and no copy back after (NCCL averages inside the collective; other backends sum, and wait_all
+        divides once)."""
+        if self.world == 1:
+            return
+        avg = dist.get_backend(self.group) == "nccl"
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((work, flat, None if avg else "div"))
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        self.buckets += 1
+
     def wait_all(self):
         for work, flat, tensors in self.pending:
             work.wait()
+            if tensors is None:
+                continue
+            if isinstance(tensors, str):
+                flat.div_(self.world)
+                continue
             off = 0
             for t in tensors:
                 n = t.numel()

@@ -154,7 +154,9 @@ SIGNATURES = {
     "wn_ce_workspace_bytes": (C.c_size_t, []),
     "wn_ce_fwd_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 2 + [C.c_void_p]),
     "wn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 5 + [C.c_int, C.c_void_p]),
-    "wn_scatter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "wn_scatter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "wn_tb_pack_all_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wn_tb_pack_all_bwd_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wn_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
     "wn_colsum": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "wn_relu_copy": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p]),

@@ -133,31 +133,48 @@ class _Packs:
     def _build_tc_bwd_layers_bf16(self, stream):
         return [(self.rt._bf16_pairs(a, stream), self.rt._bf16_pairs(b, stream)) for a, b in self["tc_bwd_layers"]]
 
-    def _build_tb(self, stream):
-        rt, lib = self.rt, native.lib()
-        R, D, S, E, Cc, k, nl = self._dims()
+    def _ptr_table(self):
+        """DEVICE table [n_layers][8] of parameter pointers {wf, wg, bf, bg, wr, ws, br, bs} (0 = no bias), cached on the
+        runtime while the parameters stay where they are."""
+        rt = self.rt
         P = rt._params()
-        dev = rt.device()
-        tb_w = torch.empty(nl, lib.wn_tb_weight_bytes_per_layer(), device=dev, dtype=torch.uint8)
-        tb_b = torch.empty(nl, 4 * 256, device=dev, dtype=torch.float32)
+        nl = self._dims()[6]
+        rows = []
         for i in range(nl):
             (wf, bf), (wg, bg) = P["filt"][i], P["gate"][i]
             (wr, br), (wsk, bs) = P["res"][i], P["skip"][i]
-            native.check(lib.wn_tb_pack_block_weights(
-                wf.data_ptr(), wg.data_ptr(), native.ptr(bf), native.ptr(bg), wr.data_ptr(), wsk.data_ptr(),
-                native.ptr(br), native.ptr(bs), tb_w[i].data_ptr(), tb_b[i].data_ptr(), stream), "pack tb")
+            rows.append([native.ptr(t) or 0 for t in (wf, wg, bf, bg, wr, wsk, br, bs)])
+        key = tuple(map(tuple, rows))
+        cached = rt.__dict__.get("_ptr_table_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, torch.tensor(rows, dtype=torch.int64, device=rt.device()))
+            rt._ptr_table_cache = cached
+        return cached[1]
+
+    def _build_tb(self, stream):
+        rt, lib = self.rt, native.lib()
+        nl = self._dims()[6]
+        dev = rt.device()
+        tb_w = torch.empty(nl, lib.wn_tb_weight_bytes_per_layer(), device=dev, dtype=torch.uint8)
+        tb_b = torch.empty(nl, 4 * 256, device=dev, dtype=torch.float32)
+        native.check(lib.wn_tb_pack_all_weights(self._ptr_table().data_ptr(), nl, tb_w.data_ptr(), tb_b.data_ptr(), stream),
+                     "pack tb")
         return tb_w, tb_b
 
     def _build_tb_bwd(self, stream):
         rt, lib = self.rt, native.lib()
-        R, D, S, E, Cc, k, nl = self._dims()
-        P = rt._params()
+        nl = self._dims()[6]
         wb = torch.empty(nl, lib.wn_tb_bwd_weight_bytes_per_layer(), device=rt.device(), dtype=torch.uint8)
-        for i in range(nl):
-            wf, wg, wr, wsk = P["filt"][i][0], P["gate"][i][0], P["res"][i][0], P["skip"][i][0]
-            native.check(lib.wn_tb_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), wsk.data_ptr(),
-                                                          wb[i].data_ptr(), stream), "pack tb bwd")
+        native.check(lib.wn_tb_pack_all_bwd_weights(self._ptr_table().data_ptr(), nl, wb.data_ptr(), stream), "pack tb bwd")
         return wb
+
+    def _build_head_rows(self, stream):
+        """end_conv_2 / end_conv_1 weight rows zero-padded to the SIMT kernels' column pitch (wn_head_bwd_data)."""
+        lib = native.lib()
+        R, D, S, E, Cc, k, nl = self._dims()
+        P = self.rt._params()
+        pad = lambda w2d, n: torch.nn.functional.pad(w2d, (0, n - w2d.shape[1])).contiguous()
+        return (pad(P["end2"][0].detach()[:, :, 0], lib.wn_n2p(E)), pad(P["end1"][0].detach()[:, :, 0], lib.wn_n2p(S)))
 
     def _pack1x1(self, wb, N, K, stream):
         lib = native.lib()
@@ -445,15 +462,11 @@ class _Runtime:
         n_layers = len(dil)
         f32 = dict(device=dev, dtype=torch.float32)
         bf16 = dict(device=dev, dtype=torch.bfloat16)
-        pad_cols = lambda w2d, n: torch.nn.functional.pad(w2d, (0, n - w2d.shape[1])).contiguous()
         grads = {}
         dlogits = dlogits.contiguous().view(B, OL, Cc)
         # ---------------- head (frames layout; its skip input is the (B, OL, S) slice the forward made)
-        w1, b1 = P["end1"]
-        w2, b2 = P["end2"]
         y1, dy1, dskip = torch.empty(B, OL, E, **f32), torch.empty(B, OL, E, **f32), torch.empty(B, OL, S, **f32)
-        w2_rows = pad_cols(w2.detach()[:, :, 0], lib.wn_n2p(E))
-        w1_rows = pad_cols(w1.detach()[:, :, 0], lib.wn_n2p(S))
+        w2_rows, w1_rows = W["head_rows"]
         hb = native.HeadBwdArgs()
         hb.d_dlogits, hb.d_skip = dlogits.data_ptr(), sk_frames.data_ptr()
         hb.d_y1, hb.d_dy1, hb.d_dskip = y1.data_ptr(), dy1.data_ptr(), dskip.data_ptr()
@@ -462,7 +475,15 @@ class _Runtime:
         hb.B, hb.L, hb.S, hb.E, hb.classes, hb.skip_start, hb.out_len = B, L, S, E, Cc, L - OL, OL
         native.check(lib.wn_head_bwd_data(ctypes.byref(hb), stream), "head bwd")
         ds_start = L - OL
-        rskip = torch.relu(sk_frames)
+        rskip = torch.empty_like(sk_frames)
+        native.check(lib.wn_relu_copy(sk_frames.data_ptr(), rskip.data_ptr(), sk_frames.numel(), stream), "relu(skip)")
+        cs_work = torch.empty(lib.wn_colsum_workspace_bytes(B * OL, max(Cc, E, S)) // 4 + 4, **f32)
+
+        def colsum(x2d, C):
+            out = torch.empty(C, **f32)
+            native.check(lib.wn_colsum(x2d.data_ptr(), out.data_ptr(), cs_work.data_ptr(), B * OL, C, C, stream), "column sums")
+            return out
+
         wg_work = torch.empty(max(lib.wn_wgrad_workspace_bytes(n_, c_) for n_, c_ in ((Cc, E), (E, S))) // 4, **f32)
         wa = native.WgradArgs()
         wa.d_work, wa.B = wg_work.data_ptr(), B
@@ -482,8 +503,8 @@ class _Runtime:
         head_wgrad(gw2, dlogits, Cc, y1, E, Cc, E)
         head_wgrad(gw1, dy1, E, rskip, S, E, S)
         grads["end_conv_2.weight"], grads["end_conv_1.weight"] = gw2, gw1
-        grads["end_conv_2.bias"] = dlogits.sum((0, 1))
-        grads["end_conv_1.bias"] = dy1.sum((0, 1))
+        grads["end_conv_2.bias"] = colsum(dlogits, Cc)
+        grads["end_conv_1.bias"] = colsum(dy1, E)
         reducer = getattr(self, "grad_reducer", None)
         if reducer is not None:
             reducer.reduce_async([grads[n] for n in ("end_conv_2.weight", "end_conv_2.bias", "end_conv_1.weight",
@@ -491,7 +512,7 @@ class _Runtime:
         # ---------------- residual blocks, last to first
         dskip_pair = torch.empty(B, 2, S // 8, OL, 8, **bf16)
         native.check(lib.wn_pair_from_frames(dskip.data_ptr(), dskip_pair.data_ptr(), B, OL, S, 0, stream), "dskip pair")
-        dskip_bias = dskip.sum((0, 1)) if P["skip"][0][1] is not None else None
+        dskip_bias = colsum(dskip, S) if P["skip"][0][1] is not None else None
         dfg = torch.empty(B, 2, 2 * D // 8, L, 8, **bf16)
         zbuf = torch.empty(B, 2, D // 8, L, 8, **bf16)
         dh_a, dh_b = torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16)
@@ -519,8 +540,11 @@ class _Runtime:
             a.dilation, a.in_start, a.out_start = d, in_s, out_s
             a.gs_out, a.gz, a.gs_in = gs_out, gz, gs_in
             native.check(lib.wn_tb_block_bwd_data(ctypes.byref(a), stream), f"tb block bwd {i}")
-            gws, gwr = torch.empty(S, D, 1, **f32), torch.empty(R, D, 1, **f32)
-            gwf, gwg = torch.empty(D, R, k, **f32), torch.empty(D, R, k, **f32)
+            # the block's four weight gradients are views of ONE bucket: the all-reduce runs in place on it
+            bucket = torch.empty(S * D + R * D + 2 * D * R * k, **f32)
+            gws, gwr = bucket[:S * D].view(S, D, 1), bucket[S * D:S * D + R * D].view(R, D, 1)
+            gwf = bucket[S * D + R * D:S * D + R * D + D * R * k].view(D, R, k)
+            gwg = bucket[S * D + R * D + D * R * k:].view(D, R, k)
             g.d_dh_out, g.d_h_in = a.d_dh_out, h_all[i].data_ptr()
             g.d_gws, g.d_gwr, g.d_gwf, g.d_gwg = gws.data_ptr(), gwr.data_ptr(), gwf.data_ptr(), gwg.data_ptr()
             g.dilation, g.in_start, g.id_start, g.gz = d, in_s, id_start, gz
@@ -536,8 +560,10 @@ class _Runtime:
                 bsum = dfg[:, :, :, gz:, :].float().sum((0, 1, 3)).reshape(2 * D)
                 grads[f"filter_convs.{i}.bias"], grads[f"gate_convs.{i}.bias"] = bsum[:D].clone(), bsum[D:].clone()
             if reducer is not None:
-                reducer.reduce_async([grads.get(f"{n}.{i}.{wb}") for n in ("filter_convs", "gate_convs", "residual_convs",
-                                                                         "skip_convs") for wb in ("weight", "bias")])
+                reducer.reduce_flat_async(bucket)
+                if bf is not None or br is not None or bs is not None:
+                    reducer.reduce_async([grads.get(f"{n}.{i}.bias") for n in ("filter_convs", "gate_convs", "residual_convs",
+                                                                              "skip_convs")])
             dh_out, gs_out = dh_in, gs_in
         # ---------------- start conv
         dh0_frames = torch.empty(B, L, R, **f32)
@@ -545,9 +571,10 @@ class _Runtime:
         dh0 = dh0_frames[:, gs_out:, :]
         x = saved["x"]
         if saved["index_input"]:
-            table = torch.zeros(Cc, R, **f32)
-            table.index_add_(0, x[:, gs_out:].reshape(-1).long(), dh0.reshape(-1, R))
-            grads["start_conv.weight"] = table.t().contiguous().unsqueeze(-1)
+            table, gw = torch.empty(Cc, R, **f32), torch.empty(R, Cc, 1, **f32)
+            native.check(lib.wn_scatter_rows(x.data_ptr(), int(x.dtype == torch.uint8), dh0_frames.data_ptr(), table.data_ptr(),
+                                             gw.data_ptr(), B, L, R, Cc, gs_out, stream), "start conv gradient")
+            grads["start_conv.weight"] = gw
         else:
             grads["start_conv.weight"] = torch.einsum("btr,bct->rc", dh0, x[:, :, gs_out:]).unsqueeze(-1)
         if P["start"][1] is not None:

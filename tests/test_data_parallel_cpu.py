@@ -37,6 +37,13 @@ def _worker(rank, world, port, q):
         for l, (a, b, _) in enumerate(layers):
             ok &= bool(torch.allclose(a, torch.full((3, 4), (1 + l + 2 + l) / 2.0)))
             ok &= bool(torch.allclose(b, torch.arange(5.) * 1.5))
+        # ---- in-place averaging of one contiguous bucket whose views are the gradient tensors
+        flat = torch.arange(10.) * (rank + 1)
+        va, vb = flat[:4].view(2, 2), flat[4:]
+        avg.reduce_flat_async(flat)
+        avg.wait_all()
+        ok &= bool(torch.allclose(flat, torch.arange(10.) * 1.5)) and bool(torch.allclose(va, (torch.arange(4.) * 1.5).view(2, 2)))
+        ok &= bool(torch.allclose(vb, torch.arange(4., 10.) * 1.5)) and avg.buckets == 5
         # ---- make_data_parallel broadcasts rank 0's weights and installs the reducer
         torch.manual_seed(100 + rank)                       # different init per rank on purpose
         m = wmod.WaveNetModel(layers=2, blocks=1, dilation_channels=4, residual_channels=4, skip_channels=4, end_channels=4)

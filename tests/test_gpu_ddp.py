@@ -80,7 +80,8 @@ def test_two_rank_gradients_equal_single_process():
         d = float((g0[k] - g1[k]).abs().max())
         assert d <= 1e-6 * max(float(g0[k].abs().max()), 1e-30), (k, d)     # all-reduce leaves the same averaged gradients
     n_params = sum(v.numel() for v in w0.values())
-    assert buckets == KW["layers"] * KW["blocks"] + 2 and nbytes == 4 * n_params   # one bucket per block + head + start
+    # per block one in-place weight bucket + one small bias bucket, plus head and start
+    assert buckets == 2 * KW["layers"] * KW["blocks"] + 2 and nbytes == 4 * n_params
     # single process, whole batch, rank-0 weights
     import wavenet_model as wmod
     m = wmod.WaveNetModel(**KW)
