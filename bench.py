@@ -514,6 +514,75 @@ def bench_train(args, world, rank):
                 launches=args.steps * rt.launches_last_forward)
 
 
+# ------------------------------------------------------------------------------------------------ cfg 5: deep 512-channel stack, bf16
+CFG5_KW = dict(layers=10, blocks=8, dilation_channels=512, residual_channels=512, skip_channels=512, end_channels=512,
+               classes=256, output_length=32000 - 8185 + 1, kernel_size=2, bias=False)
+CFG5_L = 32000
+
+
+def bench_train_cfg5(args, world, rank):
+    """BASELINE.json configs[4]: layers=10, blocks=8, 512 channels, seq 32000, bf16 training; B = 1 sequence per GPU (the
+    config names no batch).  Single-pass bf16 tensor-core operands, fp32 accumulation, fp32-class residual / skip streams."""
+    import data_parallel as dp
+    import wavenet_training as wt
+    model = build_model(CFG5_KW).cuda()
+    rt = model._runtime()
+    rt.tc_precision = "bf16"
+    L = CFG5_L
+    idx = torch.randint(0, 256, (1, L), generator=torch.Generator().manual_seed(4321 + rank)).to(torch.uint8).cuda()
+    target = torch.randint(0, 256, (model.output_length,), generator=torch.Generator().manual_seed(55 + rank)).cuda()
+    flush = L2Flush()
+    n = max(1, min(args.steps, 3))
+    with torch.no_grad():
+        for _ in range(2):
+            model.forward_indices(idx)
+        barrier_sync(world)
+        evs, bevs = [], []
+        for _ in range(n):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rt.block_events = (b0, b1)
+            e0.record()
+            model.forward_indices(idx)
+            e1.record()
+            evs.append((e0, e1)); bevs.append((b0, b1))
+        rt.block_events = None
+        barrier_sync(world)
+        fwd_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / n, world)
+        block_ms = sum(a.elapsed_time(b) for a, b in bevs) / n
+    red = dp.make_data_parallel(model)
+    step_ms = []
+    for i in range(1 + n):
+        model.zero_grad(set_to_none=True)
+        barrier_sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = wt.fused_cross_entropy(model.forward_indices(idx), target)
+        loss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            step_ms.append(e0.elapsed_time(e1))
+    step_t = max_over_ranks(sum(step_ms) / len(step_ms), world)
+    per_layer, start_b, head_b, flops = train_alg_bytes(model, 1, L, dense_input=False)
+    tpeak, tsrc = measured_peaks("tensor")
+    hpeak, _ = measured_peaks()
+    tflops = flops / (block_ms / 1e3) / 1e12
+    model._runtime().grad_reducer = None
+    out = {"workload": "cfg5: layers=10 blocks=8 ch=512 (skip/end 512), B=1 per GPU, L=32000, output_length=23816, uint8 index input",
+           "dtype": "bf16 operands / fp32 accumulate / fp32-class residual+skip", "metric": "training-forward mu-law frames/sec",
+           "value": world * L / (fwd_ms / 1e3), "unit": "frames/s", "ms_per_step": fwd_ms,
+           "train_step": {"ms_per_step": step_t, "frames_per_s": world * L / (step_t / 1e3), "loss": float(loss.detach()),
+                          "grad_allreduce_bytes_per_step": red.bytes_reduced // (1 + n) if world > 1 else 0},
+           "roofline": {"kernel": "block_fused_kernel<512, single-pass bf16>", "bound": "tensor", "achieved": tflops, "peak": tpeak,
+                        "unit": "TFLOP/s", "frac": tflops / tpeak, "peak_source": tsrc, "avg_block_ms": block_ms / len(per_layer),
+                        "hbm_frac": (sum(per_layer) / (block_ms / 1e3) / 1e9) / hpeak, "traffic": None},
+           "parameters": model.parameter_count(), "scaling": "weak"}
+    del loss
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_generate(budget_s, temperature, threads):
     """samples/s of the CPU port at `threads` torch threads, on a sample sized to ~budget_s seconds."""
@@ -607,6 +676,7 @@ def main():
     ap.add_argument("--workload", default="all", choices=["all", "generate", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the 64-stream (cfg4) generation figure")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 512-channel bf16 deep-stack figures (cfg 5)")
     ap.add_argument("--variants", action="store_true", help="also time the other operand splits of the two-launch blocks")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -616,6 +686,11 @@ def main():
     world, rank, _ = dist_setup(args.gpus)
     gen = bench_generate(args, world, rank) if args.workload in ("all", "generate") else None
     train = bench_train(args, world, rank) if args.workload in ("all", "train") else None
+    cfg5 = None
+    if train is not None and not args.no_cfg5:
+        torch.cuda.empty_cache()
+        cfg5 = bench_train_cfg5(args, world, rank)
+        train["cfg5"] = cfg5
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, note = cpu_generate_best(8.0, TEMPERATURE)
@@ -677,6 +752,9 @@ def main():
                 summ["train_step_strong_ms"] = train["train_step"]["strong"]["ms_per_step"]
             if "ddp_grad_max_rel_err" in train["train_step"]:
                 summ["ddp_grad_max_rel_err"] = train["train_step"]["ddp_grad_max_rel_err"]
+            if train.get("cfg5") is not None:
+                summ.update(cfg5_fwd_ms=train["cfg5"]["ms_per_step"], cfg5_step_ms=train["cfg5"]["train_step"]["ms_per_step"],
+                            cfg5_tensor_frac=train["cfg5"]["roofline"]["frac"])
         line["summary"] = summ
         print(json.dumps(line))
     if world > 1:

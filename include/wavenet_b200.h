@@ -29,7 +29,12 @@
 extern "C" {
 #endif
 
-#define WN_ABI_VERSION 1
+#define WN_ABI_VERSION 2
+
+/* operand precision of the tensor-core training kernels (wn_tb_*): what the MATRIX PRODUCTS see; the residual stream and
+ * skip stay fp32-class and accumulation is fp32 in both */
+#define WN_PREC_BF16       1   /* single-pass bf16 operands (BASELINE.json configs[4], "bf16 training")             */
+#define WN_PREC_BF16_PAIRS 2   /* bf16 (hi, lo) pairs, three MMAs per product: fp32-class, the 1e-4 parity path       */
 
 #define WN_E_BADARG   (-1)   /* null pointer / non-positive size / inconsistent shapes        */
 #define WN_E_UNSUPP   (-2)   /* shape outside what the kernels cover (message says which)     */
@@ -132,35 +137,34 @@ int wn_tc_read_trace(long long* host_out, int n);
  *     bf16 [b][plane: 0 = hi, 1 = lo][c / 8][t][c % 8]         x = hi + lo, hi = bf16(x), lo = bf16(x - hi)
  * (the same number of bytes as fp32 frames), and skip as fp32 [b][c / 4][t - skip_start][c % 4].  wn_pair_from_frames /
  * wn_frames_from_pair / wn_frames_from_chunks4 convert to and from the frames layout of the other entry points.
- * Weights: wn_tb_pack_block_weights writes one layer's pre-split, pre-tiled image (wn_tb_weight_bytes_per_layer() bytes) and
- * its four bias vectors [bf | bg | br | bs] (4*256 floats); all layers live in ONE array d_w_all [n_layers][bytes_per_layer].
+ * Weights: wn_tb_pack_all_weights writes every layer's pre-split, pre-tiled image (wn_tb_weight_bytes_per_layer(channels,
+ * precision) bytes each) into ONE array d_w_all [n_layers][bytes_per_layer] and the bias vectors [bf | bg | br | bs].
  * wn_tb_start_index_* is start_conv on class indices (wavenet_model.py:65-68,127) writing that layout; *d_err (optional) is
  * set to 1 when an index is outside [0, classes) -- the reference's one-hot scatter would raise there. */
-int    wn_tb_supported(int R, int D, int S, int k);
-size_t wn_tb_weight_bytes_per_layer(void);
-int    wn_tb_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
-                                const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
-                                void* d_w_layer, float* d_bias4, void* stream);
+int    wn_tb_supported(int R, int D, int S, int k);                  /* R = D = S in {256, 512}, k = 2                        */
+int    wn_tb_precision_supported(int channels, int precision);       /* pairs: 256 channels; single-pass bf16: 256 or 512   */
+size_t wn_tb_weight_bytes_per_layer(int channels, int precision);
+/* all layers in one launch: d_ptrs is a DEVICE table [n_layers][8] of {wf, wg, bf, bg, wr, ws, br, bs} (biases may be 0);
+ * d_bias_all receives [n_layers][4 * channels] = [bf | bg | br | bs] */
+int    wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, int channels, int precision, void* d_w_all,
+                              float* d_bias_all, void* stream);
 int    wn_tb_start_index_u8(const uint8_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair,
                             int B, int classes, int L, int R, int* d_err, void* stream);
 int    wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, const float* d_b_p, void* d_h_pair,
                              int B, int classes, int L, int R, int* d_err, void* stream);
-/* all layers in one launch each: d_ptrs is a DEVICE table [n_layers][8] of {wf, wg, bf, bg, wr, ws, br, bs} (biases may be 0) */
-int    wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, void* d_w_all, float* d_bias_all, void* stream);
-int    wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, void* d_wb_all, void* stream);
 int    wn_pair_from_frames(const float* d_frames, void* d_pair, int B, int L, int C, int t_begin, void* stream);
 int    wn_frames_from_pair(const void* d_pair, float* d_frames, int B, int L, int C, int t_begin, void* stream);
 /* frames [t_first, t_first + n) of a chunked fp32 tensor (B, C/4, T, 4) -> (B, n, C) */
 int    wn_frames_from_chunks4(const float* d_chunked, float* d_frames, int B, int T, int C, int t_first, int n, void* stream);
 typedef struct wn_tb_block_args {
-    const void* d_h_in; void* d_h_out;     /* chunked pairs (B, 2, 32, L, 8) bf16                                   */
-    float* d_skip;                         /* chunked (B, 64, L - skip_start, 4) fp32                               */
-    const void* d_w_all; const float* d_bias4;   /* all layers' packed weights; THIS layer's biases               */
+    const void* d_h_in; void* d_h_out;     /* chunked pairs (B, 2, channels/8, L, 8) bf16                           */
+    float* d_skip;                         /* chunked (B, channels/4, L - skip_start, 4) fp32                       */
+    const void* d_w_all; const float* d_bias4;   /* all layers' packed weights; THIS layer's biases [4 * channels] */
     int layer, n_layers;
+    int channels, precision;               /* 256 / 512; WN_PREC_*                                                  */
     int B, L, dilation;
     int in_start, out_start, skip_start, skip_init;
-    float* d_fg_save;                      /* optional chunked (B, 128, L, 4) fp32: tanh | sigmoid outputs (for the backward) */
-    void* d_z_save;                        /* optional chunked pair (B, 2, 32, L, 8): z = tanh * sigmoid             */
+    float* d_fg_save;                      /* optional chunked (B, 2*channels/4, L, 4) fp32: tanh | sigmoid outputs (for the backward) */
 } wn_tb_block_args;
 int    wn_tb_block_fwd(const wn_tb_block_args* a, void* stream);
 
@@ -168,15 +172,16 @@ int    wn_tb_block_fwd(const wn_tb_block_args* a, void* stream);
  * wavenet_model.py:142-165.  Frame-range arguments are those of wn_block_bwd_args.  Buffers: d_dh_out (B,2,32,L,8) pair or
  * NULL (last layer), d_dskip (B,2,32,L-ds_start,8) pair on its own frame axis, d_fg the forward's d_fg_save, outputs d_dfg
  * (B,2,64,L,8) pair [dF chunks 0..31 | dG chunks 32..63], d_z (B,2,32,L,8) pair (recomputed tanh*sigmoid), d_dh_in pair.
- * d_wb_all: [n_layers][wn_tb_bwd_weight_bytes_per_layer()] images written by wn_tb_pack_block_bwd_weights. */
-size_t wn_tb_bwd_weight_bytes_per_layer(void);
-int    wn_tb_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws,
-                                    void* d_w_layer, void* stream);
+ * d_wb_all: [n_layers][wn_tb_bwd_weight_bytes_per_layer(channels, precision)] images written by wn_tb_pack_all_bwd_weights. */
+size_t wn_tb_bwd_weight_bytes_per_layer(int channels, int precision);
+int    wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, int channels, int precision, void* d_wb_all,
+                                  void* stream);
 typedef struct wn_tb_bwd_args {
     const void* d_dh_out; const void* d_dskip; const float* d_fg;
     void* d_dfg; void* d_z; void* d_dh_in;
     const void* d_wb_all;
     int layer, n_layers;
+    int channels, precision;
     int B, L, dilation;
     int in_start, out_start;
     int gs_out, ds_start, gz, gs_in;
@@ -190,6 +195,7 @@ size_t wn_tb_wgrad_workspace_bytes(void);
 typedef struct wn_tb_wgrad_args {
     const void* d_dskip; const void* d_dh_out; const void* d_dfg; const void* d_z; const void* d_h_in;
     float* d_gws; float* d_gwr; float* d_gwf; float* d_gwg; float* d_work;
+    int channels, precision;
     int B, L, dilation;
     int in_start, ds_start, id_start, gz;
 } wn_tb_wgrad_args;

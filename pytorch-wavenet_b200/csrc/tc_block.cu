@@ -37,41 +37,60 @@ namespace wn {
 namespace tb {
 using namespace px;
 
-constexpr int CH = 256;                   // residual = dilation = skip channels
 constexpr int BM = 128;                   // frames per CTA
 constexpr int PM = 256;                   // frames per item (CTA pair)
-constexpr int KS = 32;                    // channels per k-slab
-constexpr int SLOT = 16384;               // one ring slot: [plane 2][chunk 4][row 128][16 B]
+constexpr int SLOT = 16384;               // one ring slot
 constexpr int NSLOT = 6;
-constexpr int ZPLANE = 65536;             // z image: [plane 2][chunk 32][row 128][16 B]
 constexpr int NTHREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr unsigned LBO = BM * 16, SBO = 128;
-constexpr int SLABS_A = 2 * CH / KS;      // 16 k-slabs per pass-A n-tile (2 taps)
-constexpr int SLABS_B = CH / KS;          // 8 k-slabs per pass-B n-tile
-constexpr int WROWS_A = 2 * SLABS_A * 2 * 8;      // 2 KB rows of the packed pass-A weights of one layer (512)
-constexpr int WROWS_LAYER = WROWS_A + 2 * SLABS_B * 2 * 8;      // 768
-constexpr size_t W_LAYER_BYTES = (size_t)WROWS_LAYER * 2048;    // 1.5 MB
-constexpr size_t SMEM_BYTES = 128 + 2 * ZPLANE + NSLOT * SLOT + 256;
+
+// Shapes and operand precision.  PAIR: every MMA operand is a bf16 (hi, lo) pair and a product costs three MMAs
+// (fp32-class: the parity path).  !PAIR: single-pass bf16 operands (the hi planes only) with fp32 accumulation -- the
+// "bf16 training" mode of BASELINE.json configs[4]; the residual stream h and skip stay fp32-class (h is still stored and
+// updated as a pair, skip as fp32), only the matrix products see bf16.
+template <int CH_, bool PAIR_>
+struct Cfg {
+    static constexpr int CH = CH_;
+    static constexpr bool PAIR = PAIR_;
+    static constexpr int PLANES = PAIR ? 2 : 1;              // planes of an MMA operand image
+    static constexpr int KC = PAIR ? 4 : 8;                  // 8-channel chunks per k-slab slot: [plane][chunk][row 128][16 B] = 16 KB
+    static constexpr int KS = KC * 8;                        // channels per k-slab
+    static constexpr int SLABS_A = 2 * CH / KS;              // k-slabs per pass-A n-tile (2 taps)
+    static constexpr int SLABS_B = CH / KS;
+    static constexpr int NT_A = 2 * CH / 256;                // pass-A n-tiles: [tanh | sigmoid] pre-activations of 128 channels each
+    static constexpr int NT_R = CH / 256;                    // pass-B n-tiles: residual, then as many skip tiles
+    static constexpr int NT_B = 2 * CH / 256;
+    static constexpr int ZPLANE = (CH / 8) * BM * 16;        // one plane of the resident z image
+    static constexpr int ZBYTES = PLANES * ZPLANE;
+    static constexpr int NZ = CH / KS;                       // z slabs = z_ready barriers
+    static constexpr int WROWS_A = NT_A * SLABS_A * 2 * 8;   // 2 KB rows of one layer's packed pass-A weights
+    static constexpr int WROWS_LAYER = WROWS_A + NT_B * SLABS_B * 2 * 8;
+    static constexpr size_t W_LAYER_BYTES = (size_t)WROWS_LAYER * 2048;
+    static constexpr size_t SMEM_BYTES = 128 + ZBYTES + NSLOT * SLOT + 256;
+    static_assert(ZBYTES <= 131072, "the z image must fit beside the ring");
+    static_assert(NZ <= 8, "z_ready barriers");
+};
 
 struct BlockParams {
     int B, L, t_begin, in_start, skip_start, skip_init, dil;
     int tiles_per_seq, n_items;
     int w_row0;                    // first 2 KB row of this layer in the packed weight array
-    const float* bias;             // [bf 256 | bg 256 | br 256 | bs 256]
-    const uint4* h_in;             // chunked pair (B, 2, 32, L, 8) bf16, viewed as 16-byte pieces
+    const float* bias;             // [bf CH | bg CH | br CH | bs CH]
+    const uint4* h_in;             // chunked pair (B, 2, CH/8, L, 8) bf16, viewed as 16-byte pieces
     uint4* h_out;
-    float4* skip;                  // chunked (B, 64, L - skip_start, 4) fp32
-    float4* fg_save;               // optional chunked (B, 128, L, 4) fp32: tanh outputs in chunks [0,64), sigmoid in [64,128)
-    uint4* z_save;                 // optional chunked pair (B, 2, 32, L, 8) bf16
+    float4* skip;                  // chunked (B, CH/4, L - skip_start, 4) fp32
+    float4* fg_save;               // optional chunked (B, 2CH/4, L, 4) fp32: tanh outputs in chunks [0,CH/4), sigmoid after
 };
 
+template <typename C>
 __global__ void __launch_bounds__(NTHREADS, 1)
 block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW, const BlockParams p) {
+    constexpr int CH = C::CH;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     unsigned char* zbuf = base;
-    unsigned char* ring = base + 2 * ZPLANE;
+    unsigned char* ring = base + C::ZBYTES;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + NSLOT * SLOT);
     unsigned long long* full = bars;                   // [NSLOT]  leader: both CTAs' bytes of the slot have landed
     unsigned long long* empty = bars + NSLOT;          // [NSLOT]  per CTA: the MMAs reading the slot have retired
@@ -115,20 +134,20 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
                 const bool need_skip = t0 + PM > p.skip_start;
                 const int tc = t0 + (int)rank * BM - p.in_start;           // this CTA's first frame, relative to the map origin
-                for (int j = 0; j < 2; ++j)
-                    for (int sl = 0; sl < SLABS_A; ++sl) {
+                for (int j = 0; j < C::NT_A; ++j)
+                    for (int sl = 0; sl < C::SLABS_A; ++sl) {
                         unsigned bar;
                         unsigned char* dst = acquire(bar);
-                        const int tap = sl >> 3;                            // tap 0 reads h[t - d], tap 1 reads h[t]
-                        tma2_load_4d(dst, &mapH, 2 * (tc - (1 - tap) * p.dil), (sl & 7) * 4, 0, b, bar);
+                        const int tap = sl / (C::SLABS_A / 2);              // tap 0 reads h[t - d], tap 1 reads h[t]
+                        tma2_load_4d(dst, &mapH, 2 * (tc - (1 - tap) * p.dil), (sl % (C::SLABS_A / 2)) * C::KC, 0, b, bar);
                         dst = acquire(bar);
-                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + ((j * SLABS_A + sl) * 2 + (int)rank) * 8, bar);
+                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + ((j * C::SLABS_A + sl) * 2 + (int)rank) * 8, bar);
                     }
-                for (int j = 0; j < (need_skip ? 2 : 1); ++j)
-                    for (int s8 = 0; s8 < SLABS_B; ++s8) {
+                for (int j = 0; j < (need_skip ? C::NT_B : C::NT_R); ++j)
+                    for (int s8 = 0; s8 < C::SLABS_B; ++s8) {
                         unsigned bar;
                         unsigned char* dst = acquire(bar);
-                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + WROWS_A + ((j * SLABS_B + s8) * 2 + (int)rank) * 8, bar);
+                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + C::WROWS_A + ((j * C::SLABS_B + s8) * 2 + (int)rank) * 8, bar);
                     }
             }
         }
@@ -136,26 +155,31 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         // ===================================================================== MMA issuer (leader CTA)
         if (rank == 0) {
             constexpr unsigned idesc = make_idesc_bf16(PM, 256);
-            unsigned it = 0, use[2] = {0, 0}, n_item = 0;
-            // the three products of one k-step (16 channels = 2 chunks): a/b = byte addresses of the hi planes, lo planes
-            // a_lo / b_lo bytes further
-            auto mma3 = [&](unsigned d, unsigned a, unsigned a_lo, unsigned bw, unsigned accumulate) {
-                const unsigned long long ah = smem_desc(a, LBO, SBO), al = smem_desc(a + a_lo, LBO, SBO);
-                const unsigned long long bh = smem_desc(bw, LBO, SBO), bl = smem_desc(bw + SLOT / 2, LBO, SBO);
+            unsigned it = 0, q = 0, n_item = 0;                  // slot counter, n-tile counter (accumulator = q & 1), item counter
+            // the products of one k-step (16 channels = 2 chunks): a / bw = byte addresses of the hi planes; the lo planes sit
+            // a_lo / SLOT/2 bytes further (pairs only)
+            auto mma_step = [&](unsigned d, unsigned a, unsigned a_lo, unsigned bw, unsigned accumulate) {
+                const unsigned long long ah = smem_desc(a, LBO, SBO), bh = smem_desc(bw, LBO, SBO);
                 umma2_f16(d, ah, bh, idesc, accumulate);
-                umma2_f16(d, al, bh, idesc, 1);
-                umma2_f16(d, ah, bl, idesc, 1);
+                if constexpr (C::PAIR) {
+                    umma2_f16(d, smem_desc(a + a_lo, LBO, SBO), bh, idesc, 1);
+                    umma2_f16(d, ah, smem_desc(bw + SLOT / 2, LBO, SBO), idesc, 1);
+                }
+            };
+            auto next_acc = [&]() -> unsigned {                  // claim the next accumulator buffer (waits for its epilogue)
+                const unsigned ab = q & 1, u = q >> 1;
+                ++q;
+                if (u > 0) mbar_wait_cluster(acc_empty + ab, (u - 1) & 1);
+                tc_fence_after();
+                return ab;
             };
             for (int item = cluster_id; item < p.n_items; item += n_clusters, ++n_item) {
                 const int t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
                 const bool need_skip = t0 + PM > p.skip_start;
-                // ---------------- pass A: two n-tiles of [tanh | sigmoid] pre-activations
-                for (int j = 0; j < 2; ++j) {
-                    const unsigned u = use[j]++;
-                    if (u > 0) mbar_wait_cluster(acc_empty + j, (u - 1) & 1);
-                    tc_fence_after();
-                    const unsigned d = tmem_base + j * 256;
-                    for (int sl = 0; sl < SLABS_A; ++sl) {
+                // ---------------- pass A: n-tiles of [tanh | sigmoid] pre-activations, K = 2 taps x CH
+                for (int j = 0; j < C::NT_A; ++j) {
+                    const unsigned ab = next_acc(), d = tmem_base + ab * 256;
+                    for (int sl = 0; sl < C::SLABS_A; ++sl) {
                         const unsigned sa = it % NSLOT, pa = (it / NSLOT) & 1; ++it;
                         const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
                         mbar_wait_cluster(full + sa, pa);
@@ -164,33 +188,30 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                         if (elect_one()) {
                             const unsigned a = s32(ring + sa * SLOT), w = s32(ring + sw * SLOT);
 #pragma unroll
-                            for (int ks = 0; ks < KS / 16; ++ks)
-                                mma3(d, a + ks * 2 * LBO, SLOT / 2, w + ks * 2 * LBO, (sl | ks) != 0);
+                            for (int ks = 0; ks < C::KS / 16; ++ks)
+                                mma_step(d, a + ks * 2 * LBO, SLOT / 2, w + ks * 2 * LBO, (sl | ks) != 0);
                             umma2_commit(empty + sa);
                             umma2_commit(empty + sw);
-                            if (sl == SLABS_A - 1) umma2_commit(acc_full + j);
+                            if (sl == C::SLABS_A - 1) umma2_commit(acc_full + ab);
                         }
                         __syncwarp();
                     }
                 }
-                // ---------------- pass B: residual (acc0) and skip (acc1) from the resident z image
-                for (int j = 0; j < (need_skip ? 2 : 1); ++j) {
-                    const unsigned u = use[j]++;
-                    mbar_wait_cluster(acc_empty + j, (u - 1) & 1);
-                    tc_fence_after();
-                    const unsigned d = tmem_base + j * 256;
-                    for (int s8 = 0; s8 < SLABS_B; ++s8) {
+                // ---------------- pass B: residual tiles, then skip tiles, from the resident z image
+                for (int j = 0; j < (need_skip ? C::NT_B : C::NT_R); ++j) {
+                    const unsigned ab = next_acc(), d = tmem_base + ab * 256;
+                    for (int s8 = 0; s8 < C::SLABS_B; ++s8) {
                         const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
                         mbar_wait_cluster(z_ready + s8, n_item & 1);
                         mbar_wait_cluster(full + sw, pw);
                         tc_fence_after();
                         if (elect_one()) {
-                            const unsigned a = s32(zbuf) + (unsigned)s8 * 4 * LBO, w = s32(ring + sw * SLOT);
+                            const unsigned a = s32(zbuf) + (unsigned)s8 * C::KC * LBO, w = s32(ring + sw * SLOT);
 #pragma unroll
-                            for (int ks = 0; ks < KS / 16; ++ks)
-                                mma3(d, a + ks * 2 * LBO, ZPLANE, w + ks * 2 * LBO, (s8 | ks) != 0);
+                            for (int ks = 0; ks < C::KS / 16; ++ks)
+                                mma_step(d, a + ks * 2 * LBO, C::ZPLANE, w + ks * 2 * LBO, (s8 | ks) != 0);
                             umma2_commit(empty + sw);
-                            if (s8 == SLABS_B - 1) umma2_commit(acc_full + j);
+                            if (s8 == C::SLABS_B - 1) umma2_commit(acc_full + ab);
                         }
                         __syncwarp();
                     }
@@ -199,31 +220,32 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         }
     } else {
         // ===================================================================== epilogue: warps 2..9
-        const int q = warp & 3, grp = (warp - 2) >> 2;                // TMEM lane quadrant (= warp id mod 4), column group
-        const int row = q * 32 + lane;
-        const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
+        const int qd = warp & 3, grp = (warp - 2) >> 2;               // TMEM lane quadrant (= warp id mod 4), column group
+        const int row = qd * 32 + lane;
+        const unsigned lane_addr = tmem_base + ((unsigned)(qd * 32) << 16);
         const unsigned acc_empty_addr[2] = {mapa(s32(acc_empty), 0), mapa(s32(acc_empty + 1), 0)};
         const unsigned z_ready_addr = mapa(s32(z_ready), 0);
         const size_t plane_stride = (size_t)(CH / 8) * p.L;            // 16-byte pieces per plane of a pair tensor
         const int Tsk = p.L - p.skip_start;
-        unsigned use[2] = {0, 0};
+        unsigned q = 0;
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
             const bool need_skip = t0 + PM > p.skip_start;
             const int t = t0 + (int)rank * BM + row;                   // this thread's frame
             const bool live = t < p.L;
-            // ---------------- gate: z = tanh(F + bf) * sigmoid(G + bg) -> shared-memory pair image (+ optional saves)
-            for (int j = 0; j < 2; ++j) {
-                const unsigned u = use[j]++;
-                mbar_wait(acc_full + j, u & 1);
+            // ---------------- gate: z = tanh(F + bf) * sigmoid(G + bg) -> shared-memory operand image (+ optional saves)
+            for (int j = 0; j < C::NT_A; ++j) {
+                const unsigned ab = q & 1, u = q >> 1;
+                ++q;
+                mbar_wait(acc_full + ab, u & 1);
                 tc_fence_after();
-                const unsigned ta = lane_addr + j * 256;
+                const unsigned ta = lane_addr + ab * 256;
 #pragma unroll 1
-                for (int sb = 0; sb < 4; ++sb) {
-                    // slab sb of this n-tile = 32 dilation channels; the two column groups take 16 each, so the slabs become
+                for (int sb = 0; sb < 128 / C::KS; ++sb) {
+                    // slab sb of this n-tile = KS dilation channels; the two column groups take half each, so the slabs become
                     // ready in the order pass B consumes them
-                    {
-                        const int c = sb * 32 + grp * 16;
+#pragma unroll 1
+                    for (int c = sb * C::KS + grp * (C::KS / 2); c < sb * C::KS + (grp + 1) * (C::KS / 2); c += 16) {
                         float f[16], g[16];
                         tmem_ld16(ta + c, f);
                         tmem_ld16(ta + 128 + c, g);
@@ -253,111 +275,102 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                         unsigned char* zr = zbuf + (ch / 8) * (BM * 16) + row * 16;
                         *reinterpret_cast<uint4*>(zr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(zr + BM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                        *reinterpret_cast<uint4*>(zr + ZPLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(zr + ZPLANE + BM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                        if (p.z_save != nullptr && live) {
-                            uint4* zs = p.z_save + ((size_t)b * 2 * (CH / 8) + ch / 8) * p.L + t;
-                            zs[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            zs[p.L] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                            zs[plane_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                            zs[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        if constexpr (C::PAIR) {
+                            *reinterpret_cast<uint4*>(zr + C::ZPLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            *reinterpret_cast<uint4*>(zr + C::ZPLANE + BM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                         }
                     }
-                    // this warp's 32 rows x 16 channels of z slab 4j + sb are in shared memory
+                    // this warp's 32 rows of its half of z slab (128j / KS + sb) are in shared memory
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(z_ready_addr + 8u * (unsigned)(4 * j + sb));
+                    if (lane == 0) mbar_arrive_cluster(z_ready_addr + 8u * (unsigned)(j * (128 / C::KS) + sb));
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[j]);
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[ab]);
             }
-            // ---------------- residual: h_out = acc0 + br + h_in  -> pair
-            {
-                const unsigned u = use[0]++;
-                mbar_wait(acc_full + 0, u & 1);
+            // ---------------- pass B tiles: residual h_out = acc + br + h_in -> pair; then skip (+)= acc + bs
+            for (int j = 0; j < (need_skip ? C::NT_B : C::NT_R); ++j) {
+                const unsigned ab = q & 1, u = q >> 1;
+                ++q;
+                mbar_wait(acc_full + ab, u & 1);
                 tc_fence_after();
-                const unsigned ta = lane_addr;
-                const uint4* hin = p.h_in + (size_t)b * 2 * plane_stride + t;
-                uint4* hout = p.h_out + (size_t)b * 2 * plane_stride + t;
-                uint4 nx[4];
-                auto load_res = [&](int c) {
-                    nx[0] = nx[1] = nx[2] = nx[3] = make_uint4(0, 0, 0, 0);
-                    if (live) {
-                        const uint4* s = hin + (size_t)(c / 8) * p.L;
-                        nx[0] = __ldg(s); nx[1] = __ldg(s + p.L); nx[2] = __ldg(s + plane_stride); nx[3] = __ldg(s + plane_stride + p.L);
-                    }
-                };
-                load_res(grp * 128);
+                const unsigned ta = lane_addr + ab * 256;
+                if (j < C::NT_R) {
+                    const int n0 = j * 256;                                // first residual channel of this tile
+                    const uint4* hin = p.h_in + (size_t)b * 2 * plane_stride + t;
+                    uint4* hout = p.h_out + (size_t)b * 2 * plane_stride + t;
+                    uint4 nx[4];
+                    auto load_res = [&](int c) {
+                        nx[0] = nx[1] = nx[2] = nx[3] = make_uint4(0, 0, 0, 0);
+                        if (live) {
+                            const uint4* s = hin + (size_t)((n0 + c) / 8) * p.L;
+                            nx[0] = __ldg(s); nx[1] = __ldg(s + p.L); nx[2] = __ldg(s + plane_stride); nx[3] = __ldg(s + plane_stride + p.L);
+                        }
+                    };
+                    load_res(grp * 128);
 #pragma unroll 1
-                for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
-                    float v[16];
-                    tmem_ld16(ta + c, v);
-                    const uint4 xh0 = nx[0], xh1 = nx[1], xl0 = nx[2], xl1 = nx[3];
-                    if (c + 16 < grp * 128 + 128) load_res(c + 16);        // next chunk's loads fly under this chunk's math
-                    tmem_ld_wait();
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + 2 * CH + c);
-                    const unsigned xh[8] = {xh0.x, xh0.y, xh0.z, xh0.w, xh1.x, xh1.y, xh1.z, xh1.w};
-                    const unsigned xl[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
-                    unsigned hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 bb = __ldg(b4 + i);
-                        const float2 h0 = unpack_bf16x2(xh[2 * i]), l0 = unpack_bf16x2(xl[2 * i]);
-                        const float2 h1 = unpack_bf16x2(xh[2 * i + 1]), l1 = unpack_bf16x2(xl[2 * i + 1]);
-                        split2(v[4 * i] + bb.x + (h0.x + l0.x), v[4 * i + 1] + bb.y + (h0.y + l0.y), hi[2 * i], lo[2 * i]);
-                        split2(v[4 * i + 2] + bb.z + (h1.x + l1.x), v[4 * i + 3] + bb.w + (h1.y + l1.y), hi[2 * i + 1], lo[2 * i + 1]);
-                    }
-                    if (live) {
-                        uint4* o = hout + (size_t)(c / 8) * p.L;
-                        o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        o[p.L] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                        o[plane_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        o[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[0]);
-            }
-            // ---------------- skip: skip (+)= acc1 + bs
-            if (need_skip) {
-                const unsigned u = use[1]++;
-                mbar_wait(acc_full + 1, u & 1);
-                tc_fence_after();
-                const unsigned ta = lane_addr + 256;
-                const bool on = live && t >= p.skip_start;
-                float4* sk = p.skip + (size_t)b * (CH / 4) * Tsk + (t - p.skip_start);
-                float4 nx[4];
-                const bool rmw = on && !p.skip_init;
-                auto load_skip = [&](int c) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        nx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rmw) nx[i] = sk[(size_t)(c / 4 + i) * Tsk];
-                    }
-                };
-                load_skip(grp * 128);
-#pragma unroll 1
-                for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
-                    float v[16];
-                    tmem_ld16(ta + c, v);
-                    const float4 x[4] = {nx[0], nx[1], nx[2], nx[3]};
-                    if (c + 16 < grp * 128 + 128) load_skip(c + 16);
-                    tmem_ld_wait();
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + 3 * CH + c);
-                    if (on) {
+                    for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                        float v[16];
+                        tmem_ld16(ta + c, v);
+                        const uint4 xh0 = nx[0], xh1 = nx[1], xl0 = nx[2], xl1 = nx[3];
+                        if (c + 16 < grp * 128 + 128) load_res(c + 16);        // next chunk's loads fly under this chunk's math
+                        tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + 2 * CH + n0 + c);
+                        const unsigned xh[8] = {xh0.x, xh0.y, xh0.z, xh0.w, xh1.x, xh1.y, xh1.z, xh1.w};
+                        const unsigned xl[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
+                        unsigned hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float4 bb = __ldg(b4 + i);
-                            sk[(size_t)(c / 4 + i) * Tsk] = make_float4(v[4 * i] + bb.x + x[i].x, v[4 * i + 1] + bb.y + x[i].y,
-                                                                        v[4 * i + 2] + bb.z + x[i].z, v[4 * i + 3] + bb.w + x[i].w);
+                            const float2 h0 = unpack_bf16x2(xh[2 * i]), l0 = unpack_bf16x2(xl[2 * i]);
+                            const float2 h1 = unpack_bf16x2(xh[2 * i + 1]), l1 = unpack_bf16x2(xl[2 * i + 1]);
+                            split2(v[4 * i] + bb.x + (h0.x + l0.x), v[4 * i + 1] + bb.y + (h0.y + l0.y), hi[2 * i], lo[2 * i]);
+                            split2(v[4 * i + 2] + bb.z + (h1.x + l1.x), v[4 * i + 3] + bb.w + (h1.y + l1.y), hi[2 * i + 1], lo[2 * i + 1]);
+                        }
+                        if (live) {
+                            uint4* o = hout + (size_t)((n0 + c) / 8) * p.L;
+                            o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            o[p.L] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                            o[plane_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            o[plane_stride + p.L] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        }
+                    }
+                } else {
+                    const int n0 = (j - C::NT_R) * 256;                    // first skip channel of this tile
+                    const bool on = live && t >= p.skip_start;
+                    float4* sk = p.skip + (size_t)b * (CH / 4) * Tsk + (t - p.skip_start);
+                    float4 nx[4];
+                    const bool rmw = on && !p.skip_init;
+                    auto load_skip = [&](int c) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            nx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rmw) nx[i] = sk[(size_t)((n0 + c) / 4 + i) * Tsk];
+                        }
+                    };
+                    load_skip(grp * 128);
+#pragma unroll 1
+                    for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
+                        float v[16];
+                        tmem_ld16(ta + c, v);
+                        const float4 x[4] = {nx[0], nx[1], nx[2], nx[3]};
+                        if (c + 16 < grp * 128 + 128) load_skip(c + 16);
+                        tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + 3 * CH + n0 + c);
+                        if (on) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 bb = __ldg(b4 + i);
+                                sk[(size_t)((n0 + c) / 4 + i) * Tsk] = make_float4(v[4 * i] + bb.x + x[i].x, v[4 * i + 1] + bb.y + x[i].y,
+                                                                                   v[4 * i + 2] + bb.z + x[i].z, v[4 * i + 3] + bb.w + x[i].w);
+                            }
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[1]);
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr[ab]);
             }
         }
     }
@@ -368,69 +381,43 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
-// Packed image of one layer (bf16): pass A blocks [n-tile j 2][k-slab sl 16][half r 2], pass B blocks [j 2][s 8][r 2]; a block
-// is the 16 KB slot image [plane 2][chunk 4][row 128][8].  Pass A: N row n = r*128 + row is filter (r = 0) or gate (r = 1)
-// channel 128j + row; K index sl*32 + ck*8 + e = tap*256 + input channel (tap 0 = weight[:, :, 0], the older frame).
-// Pass B: j = 0 residual rows, j = 1 skip rows, output channel r*128 + row; K = dilation channel.
-__global__ void pack_block_kernel(const float* __restrict__ wf, const float* __restrict__ wg, const float* __restrict__ wr,
-                                  const float* __restrict__ ws, __nv_bfloat16* __restrict__ out) {
-    const int n_a = 2 * SLABS_A * 2, n_blocks = n_a + 2 * SLABS_B * 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
-         i += (long long)gridDim.x * blockDim.x) {
-        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));     // w: element index inside one plane of the block
-        const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
-        float v;
-        if (blk < n_a) {
-            const int j = blk / (SLABS_A * 2), sl = (blk / 2) % SLABS_A, r = blk % 2;
-            const int kk = sl * KS + ck * 8 + e, tap = kk / CH, cin = kk % CH, cout = j * 128 + row;
-            v = (r == 0 ? wf : wg)[((size_t)cout * CH + cin) * 2 + tap];
-        } else {
-            const int bb = blk - n_a, j = bb / (SLABS_B * 2), s8 = (bb / 2) % SLABS_B, r = bb % 2;
-            const int cin = s8 * KS + ck * 8 + e, cout = r * 128 + row;
-            v = (j == 0 ? wr : ws)[(size_t)cout * CH + cin];
-        }
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
-        o[0] = h;
-        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
-}
-// all layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs}; blockIdx.y = layer
+// Packed image of one layer (bf16): pass A blocks [n-tile j][k-slab sl][half r], pass B blocks [j][s][r]; a block is the 16 KB
+// slot image [plane][chunk KC][row 128][8].  Pass A: N row n = r*128 + row is filter (r = 0) or gate (r = 1) channel 128j + row;
+// K index sl*KS + ck*8 + e = tap*CH + input channel (tap 0 = weight[:, :, 0], the older frame).  Pass B: tiles j < NT_R are
+// residual rows, the rest skip rows, output channel 256*(j mod NT_R) + r*128 + row; K = dilation channel.
+// All layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs} (biases may be null); blockIdx.y = layer.
+template <typename C>
 __global__ void pack_block_all_kernel(const float* const* __restrict__ ptrs, __nv_bfloat16* __restrict__ out_all, float* __restrict__ bias_all) {
+    constexpr int CH = C::CH;
     const float* const* q = ptrs + (size_t)blockIdx.y * 8;
     const float* wf = q[0]; const float* wg = q[1]; const float* wr = q[4]; const float* ws = q[5];
-    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (W_LAYER_BYTES / 2);
-    const int n_a = 2 * SLABS_A * 2, n_blocks = n_a + 2 * SLABS_B * 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
+    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (C::W_LAYER_BYTES / 2);
+    constexpr int n_a = C::NT_A * C::SLABS_A * 2, n_blocks = n_a + C::NT_B * C::SLABS_B * 2;
+    constexpr int per_plane = SLOT / 2 / C::PLANES;                        // bf16 elements of one plane of a slot image
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * per_plane;
          i += (long long)gridDim.x * blockDim.x) {
-        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));
+        const int blk = (int)(i / per_plane), w = (int)(i % per_plane);   // w: element index inside one plane of the block
         const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
         float v;
         if (blk < n_a) {
-            const int j = blk / (SLABS_A * 2), sl = (blk / 2) % SLABS_A, r = blk % 2;
-            const int kk = sl * KS + ck * 8 + e, tap = kk / CH, cin = kk % CH, cout = j * 128 + row;
+            const int j = blk / (C::SLABS_A * 2), sl = (blk / 2) % C::SLABS_A, r = blk % 2;
+            const int kk = sl * C::KS + ck * 8 + e, tap = kk / CH, cin = kk % CH, cout = j * 128 + row;
             v = (r == 0 ? wf : wg)[((size_t)cout * CH + cin) * 2 + tap];
         } else {
-            const int bb = blk - n_a, j = bb / (SLABS_B * 2), s8 = (bb / 2) % SLABS_B, r = bb % 2;
-            const int cin = s8 * KS + ck * 8 + e, cout = r * 128 + row;
-            v = (j == 0 ? wr : ws)[(size_t)cout * CH + cin];
+            const int bb = blk - n_a, j = bb / (C::SLABS_B * 2), s8 = (bb / 2) % C::SLABS_B, r = bb % 2;
+            const int cin = s8 * C::KS + ck * 8 + e, cout = (j % C::NT_R) * 256 + r * 128 + row;
+            v = (j < C::NT_R ? wr : ws)[(size_t)cout * CH + cin];
         }
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
         o[0] = h;
-        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if constexpr (C::PAIR) o[per_plane] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < 4 * CH; i += blockDim.x) {
             const float* src = i < CH ? q[2] : (i < 2 * CH ? q[3] : (i < 3 * CH ? q[6] : q[7]));
             bias_all[(size_t)blockIdx.y * 4 * CH + i] = src ? src[i % CH] : 0.f;
         }
-}
-__global__ void pack_bias_kernel(const float* bf, const float* bg, const float* br, const float* bs, float* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 4 * CH) return;
-    const float* src = i < CH ? bf : (i < 2 * CH ? bg : (i < 3 * CH ? br : bs));
-    out[i] = src ? src[i % CH] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------- layout converters
@@ -482,8 +469,8 @@ __global__ void frames_from_chunks4_kernel(const float4* __restrict__ in, float*
 // h0 pair <- table[idx[b][t]] where table (classes, ldt) holds start_conv.weight^T (+ bias) as packed by wn_pack_1x1_weights
 template <typename IDX>
 __global__ void start_pair_kernel(const IDX* __restrict__ idx, const float* __restrict__ table, const float* __restrict__ bias,
-                                  uint4* __restrict__ out, int B, int L, int classes, int ldt, int* __restrict__ err) {
-    const int chunks = CH / 8;
+                                  uint4* __restrict__ out, int B, int L, int classes, int ldt, int R, int* __restrict__ err) {
+    const int chunks = R / 8;
     const long long total = (long long)B * chunks * L;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % L), ck = (int)((i / L) % chunks), b = (int)(i / ((long long)L * chunks));
@@ -515,16 +502,17 @@ static EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// chunked pair tensor (B, 2, C/8, L, 8) bf16 as 8-byte elements: dims {2(L - origin), C/8, 2, B}; box {256, box_chunks, 2, 1}:
-// 128 frames x box_chunks chunks x both planes.  Frames left of `origin` (and right of L) are out of bounds -> zeros.
-int make_pair_map(CUtensorMap* m, const void* base, int B, int L, int C, int origin, int box_frames, int box_chunks) {
+// chunked pair tensor (B, 2, C/8, L, 8) bf16 as 8-byte elements: dims {2(L - origin), C/8, 2, B}; box {2 box_frames, box_chunks,
+// box_planes, 1} (box_planes = 1: the hi plane only, for single-pass bf16 operands).  Frames left of `origin` (and right of L)
+// are out of bounds -> zeros.
+int make_pair_map(CUtensorMap* m, const void* base, int B, int L, int C, int origin, int box_frames, int box_chunks, int box_planes) {
     EncodeTiledFn fn = encode_fn();
     WN_REQUIRE(fn, WN_E_UNSUPP, "cuTensorMapEncodeTiled is not available from this driver");
     WN_REQUIRE(L - origin >= 1, WN_E_BADARG, "empty activation range");
     const cuuint64_t chunks = (cuuint64_t)(C / 8);
     cuuint64_t dims[4] = {(cuuint64_t)2 * (L - origin), chunks, 2, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)L * 16, chunks * L * 16, 2 * chunks * L * 16};
-    cuuint32_t box[4] = {(cuuint32_t)(2 * box_frames), (cuuint32_t)box_chunks, 2, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * box_frames), (cuuint32_t)box_chunks, (cuuint32_t)box_planes, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)((const unsigned char*)base + (size_t)origin * 16), dims, strides, box,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -551,23 +539,28 @@ int make_wrows_map(CUtensorMap* m, const void* base, long long rows) {
 
 using namespace wn;
 
-extern "C" int wn_tb_supported(int R, int D, int S, int k) { return R == tb::CH && D == tb::CH && S == tb::CH && k == 2; }
-extern "C" size_t wn_tb_weight_bytes_per_layer(void) { return tb::W_LAYER_BYTES; }
-
-extern "C" int wn_tb_pack_block_weights(const float* d_wf, const float* d_wg, const float* d_bf, const float* d_bg,
-                                        const float* d_wr, const float* d_ws, const float* d_br, const float* d_bs,
-                                        void* d_w_layer, float* d_bias4, void* stream) {
-    WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_w_layer && d_bias4, WN_E_BADARG, "wn_tb_pack_block_weights: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    tb::pack_block_kernel<<<296, 256, 0, st>>>(d_wf, d_wg, d_wr, d_ws, (__nv_bfloat16*)d_w_layer);
-    tb::pack_bias_kernel<<<4, 256, 0, st>>>(d_bf, d_bg, d_br, d_bs, d_bias4);
-    WN_CUDA(cudaGetLastError());
-    return 0;
+extern "C" int wn_tb_supported(int R, int D, int S, int k) { return R == D && D == S && (R == 256 || R == 512) && k == 2; }
+// precision: WN_PREC_BF16_PAIRS (fp32-class, channels == 256 only: the z image of 512 channels does not fit as a pair) or
+// WN_PREC_BF16 (single-pass bf16 operands, 256 or 512 channels)
+extern "C" int wn_tb_precision_supported(int channels, int precision) {
+    return (precision == WN_PREC_BF16_PAIRS && channels == 256) || (precision == WN_PREC_BF16 && (channels == 256 || channels == 512));
+}
+extern "C" size_t wn_tb_weight_bytes_per_layer(int channels, int precision) {
+    if (!wn_tb_precision_supported(channels, precision)) return 0;
+    if (precision == WN_PREC_BF16_PAIRS) return tb::Cfg<256, true>::W_LAYER_BYTES;
+    return channels == 256 ? tb::Cfg<256, false>::W_LAYER_BYTES : tb::Cfg<512, false>::W_LAYER_BYTES;
 }
 
-extern "C" int wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, void* d_w_all, float* d_bias_all, void* stream) {
+extern "C" int wn_tb_pack_all_weights(const float* const* d_ptrs, int n_layers, int channels, int precision, void* d_w_all,
+                                      float* d_bias_all, void* stream) {
     WN_REQUIRE(d_ptrs && d_w_all && d_bias_all && n_layers > 0, WN_E_BADARG, "wn_tb_pack_all_weights: bad arguments");
-    tb::pack_block_all_kernel<<<dim3(74, n_layers), 256, 0, (cudaStream_t)stream>>>(d_ptrs, (__nv_bfloat16*)d_w_all, d_bias_all);
+    WN_REQUIRE(wn_tb_precision_supported(channels, precision), WN_E_UNSUPP, "wn_tb_pack_all_weights: %d channels with precision %d is not supported",
+               channels, precision);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(74, n_layers);
+    if (precision == WN_PREC_BF16_PAIRS) tb::pack_block_all_kernel<tb::Cfg<256, true>><<<grid, 256, 0, st>>>(d_ptrs, (__nv_bfloat16*)d_w_all, d_bias_all);
+    else if (channels == 256) tb::pack_block_all_kernel<tb::Cfg<256, false>><<<grid, 256, 0, st>>>(d_ptrs, (__nv_bfloat16*)d_w_all, d_bias_all);
+    else tb::pack_block_all_kernel<tb::Cfg<512, false>><<<grid, 256, 0, st>>>(d_ptrs, (__nv_bfloat16*)d_w_all, d_bias_all);
     WN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -597,11 +590,11 @@ extern "C" int wn_frames_from_chunks4(const float* d_chunked, float* d_frames, i
 static int start_pair(const void* d_idx, bool u8, const float* d_w_t, const float* d_b_p, void* d_h_pair, int B, int classes, int L,
                       int R, int* d_err, void* stream) {
     WN_REQUIRE(d_idx && d_w_t && d_b_p && d_h_pair && B > 0 && L > 0 && classes > 0, WN_E_BADARG, "wn_tb_start_index: bad arguments");
-    WN_REQUIRE(R == tb::CH, WN_E_UNSUPP, "wn_tb_start_index: R must be %d", tb::CH);
+    WN_REQUIRE(R > 0 && R % 8 == 0, WN_E_UNSUPP, "wn_tb_start_index: R must be a multiple of 8");
     const int ldt = wn_n2p(R);
     cudaStream_t st = (cudaStream_t)stream;
-    if (u8) tb::start_pair_kernel<uint8_t><<<1184, 256, 0, st>>>((const uint8_t*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, d_err);
-    else tb::start_pair_kernel<long long><<<1184, 256, 0, st>>>((const long long*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, d_err);
+    if (u8) tb::start_pair_kernel<uint8_t><<<1184, 256, 0, st>>>((const uint8_t*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, R, d_err);
+    else tb::start_pair_kernel<long long><<<1184, 256, 0, st>>>((const long long*)d_idx, d_w_t, d_b_p, (uint4*)d_h_pair, B, L, classes, ldt, R, d_err);
     WN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -614,39 +607,32 @@ extern "C" int wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, c
     return start_pair(d_idx, false, d_w_t, d_b_p, d_h_pair, B, classes, L, R, d_err, stream);
 }
 
-extern "C" int wn_tb_block_fwd(const wn_tb_block_args* a, void* stream) {
-    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_block_fwd: null args");
-    WN_REQUIRE(a->d_h_in && a->d_h_out && a->d_skip && a->d_w_all && a->d_bias4, WN_E_BADARG, "wn_tb_block_fwd: null pointer");
-    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->in_start >= 0 && a->out_start >= a->in_start && a->out_start < a->L &&
-                   a->skip_start >= a->out_start && a->skip_start < a->L && a->layer >= 0 && a->layer < a->n_layers,
-               WN_E_BADARG, "wn_tb_block_fwd: bad frame ranges or layer index");
-    WN_REQUIRE(((uintptr_t)a->d_h_in | (uintptr_t)a->d_h_out | (uintptr_t)a->d_skip | (uintptr_t)a->d_w_all) % 16 == 0, WN_E_BADARG,
-               "wn_tb_block_fwd: buffers must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+template <typename C>
+static int launch_block(const wn_tb_block_args* a, cudaStream_t st) {
     int dev = 0, sms = 0;
     WN_CUDA(cudaGetDevice(&dev));
     WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CUtensorMap mH, mW;
-    if (int rc = tb::make_pair_map(&mH, a->d_h_in, a->B, a->L, tb::CH, a->in_start, tb::BM, tb::KS / 8)) return rc;
-    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)a->n_layers * tb::WROWS_LAYER)) return rc;
+    if (int rc = tb::make_pair_map(&mH, a->d_h_in, a->B, a->L, C::CH, a->in_start, tb::BM, C::KC, C::PLANES)) return rc;
+    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)a->n_layers * C::WROWS_LAYER)) return rc;
     tb::BlockParams p;
     memset(&p, 0, sizeof(p));
     p.B = a->B; p.L = a->L; p.t_begin = a->out_start; p.in_start = a->in_start; p.skip_start = a->skip_start;
     p.skip_init = a->skip_init; p.dil = a->dilation;
     p.tiles_per_seq = (a->L - a->out_start + tb::PM - 1) / tb::PM;
     p.n_items = a->B * p.tiles_per_seq;
-    p.w_row0 = a->layer * tb::WROWS_LAYER;
+    p.w_row0 = a->layer * C::WROWS_LAYER;
     p.bias = a->d_bias4;
     p.h_in = (const uint4*)a->d_h_in; p.h_out = (uint4*)a->d_h_out; p.skip = (float4*)a->d_skip;
-    p.fg_save = (float4*)a->d_fg_save; p.z_save = (uint4*)a->d_z_save;
-    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    p.fg_save = (float4*)a->d_fg_save;
+    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     int grid = 2 * p.n_items;
     const int max_grid = (sms / 2) * 2;
     if (grid > max_grid) grid = max_grid;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(tb::NTHREADS);
-    cfg.dynamicSmemBytes = tb::SMEM_BYTES;
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -655,7 +641,23 @@ extern "C" int wn_tb_block_fwd(const wn_tb_block_args* a, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel, mH, mW, p));
+    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel<C>, mH, mW, p));
     WN_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int wn_tb_block_fwd(const wn_tb_block_args* a, void* stream) {
+    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_block_fwd: null args");
+    WN_REQUIRE(a->d_h_in && a->d_h_out && a->d_skip && a->d_w_all && a->d_bias4, WN_E_BADARG, "wn_tb_block_fwd: null pointer");
+    WN_REQUIRE(wn_tb_precision_supported(a->channels, a->precision), WN_E_UNSUPP, "wn_tb_block_fwd: %d channels with precision %d is not supported",
+               a->channels, a->precision);
+    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->in_start >= 0 && a->out_start >= a->in_start && a->out_start < a->L &&
+                   a->skip_start >= a->out_start && a->skip_start < a->L && a->layer >= 0 && a->layer < a->n_layers,
+               WN_E_BADARG, "wn_tb_block_fwd: bad frame ranges or layer index");
+    WN_REQUIRE(((uintptr_t)a->d_h_in | (uintptr_t)a->d_h_out | (uintptr_t)a->d_skip | (uintptr_t)a->d_w_all) % 16 == 0, WN_E_BADARG,
+               "wn_tb_block_fwd: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->precision == WN_PREC_BF16_PAIRS) return launch_block<tb::Cfg<256, true>>(a, st);
+    if (a->channels == 256) return launch_block<tb::Cfg<256, false>>(a, st);
+    return launch_block<tb::Cfg<512, false>>(a, st);
 }

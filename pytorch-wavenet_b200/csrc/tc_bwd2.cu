@@ -22,41 +22,53 @@
 
 namespace wn {
 namespace tb {
-int make_pair_map(CUtensorMap* m, const void* base, int B, int L, int C, int origin, int box_frames, int box_chunks);
+int make_pair_map(CUtensorMap* m, const void* base, int B, int L, int C, int origin, int box_frames, int box_chunks, int box_planes);
 int make_wrows_map(CUtensorMap* m, const void* base, long long rows);
 }
 namespace tb2 {
 using namespace px;
 
-constexpr int CH = 256;
-constexpr int BM = 128, PM = 256, KS = 32;
+constexpr int BM = 128, PM = 256;
 constexpr int SLOT = 16384, NSLOT = 8;
 constexpr int NTHREADS = 320, EPI_WARPS = 8;
 constexpr unsigned LBO = BM * 16, SBO = 128;
-constexpr int SLABS_DZ = 2 * CH / KS;             // 16: [dh_out 256 | dskip 256]
-constexpr int SLABS_DH = 2 * 2 * CH / KS;         // 32: 2 taps x (dF 256 | dG 256)
-constexpr int WROWS_DZ = SLABS_DZ * 2 * 8;        // 256 rows of 2 KB
-constexpr int WROWS_BWD_LAYER = WROWS_DZ + SLABS_DH * 2 * 8;     // 768
-constexpr size_t WB_LAYER_BYTES = (size_t)WROWS_BWD_LAYER * 2048;
-constexpr size_t SMEM_PG = 128 + NSLOT * SLOT + 256;
 enum { EPI_DZ = 0, EPI_DH = 1 };
+
+// channels and operand precision, as tb::Cfg (tc_block.cu): PAIR = bf16 (hi, lo) operand pairs, three MMAs per product;
+// !PAIR = single-pass bf16 operands (hi planes only).  Gradient tensors are always STORED as pairs.
+template <int CH_, bool PAIR_>
+struct Cfg {
+    static constexpr int CH = CH_;
+    static constexpr bool PAIR = PAIR_;
+    static constexpr int PLANES = PAIR ? 2 : 1;
+    static constexpr int KC = PAIR ? 4 : 8;                  // 8-channel chunks per k-slab slot
+    static constexpr int KS = KC * 8;
+    static constexpr int NT = CH / 256;                      // 256-column n-tiles of dz (dilation channels) / dh_in (residual channels)
+    static constexpr int SLABS_DZ = 2 * CH / KS;             // K of dz: [dh_out CH | dskip CH]
+    static constexpr int SLABS_DH = 4 * CH / KS;             // K of dh: 2 taps x (dF CH | dG CH)
+    static constexpr int WROWS_DZ = NT * SLABS_DZ * 2 * 8;   // 2 KB rows
+    static constexpr int WROWS_BWD_LAYER = WROWS_DZ + NT * SLABS_DH * 2 * 8;
+    static constexpr size_t WB_LAYER_BYTES = (size_t)WROWS_BWD_LAYER * 2048;
+};
+constexpr size_t SMEM_PG = 128 + NSLOT * SLOT + 256;
 
 struct KSeg { int shift, origin, slabs, pad; };    // A rows of frame t: the segment's tensor at frame t + shift - origin
 struct PgParams {
     int B, L, t_begin, tiles_per_seq, n_items;
     int n_seg; KSeg seg[2];
-    int w_row0;
-    const float4* fg;        // DZ: chunked (B, 128, L, 4) tanh | sigmoid outputs
-    uint4* out0;             // DZ: dFG pair (B, 2, 64, L, 8)      DH: dh_in pair (B, 2, 32, L, 8)
-    uint4* out1;             // DZ: z pair (B, 2, 32, L, 8)
+    int w_row0, w_slabs_per_tile, w_slab_off;      // weight slot of (n-tile j, k-slab s): row w_row0 + ((j*w_slabs_per_tile + w_slab_off + s)*2 + rank)*8
+    const float4* fg;        // DZ: chunked (B, 2CH/4, L, 4) tanh | sigmoid outputs
+    uint4* out0;             // DZ: dFG pair (B, 2, 2CH/8, L, 8)      DH: dh_in pair (B, 2, CH/8, L, 8)
+    uint4* out1;             // DZ: z pair (B, 2, CH/8, L, 8)
     const uint4* res;        // DH: dh_out pair or null
     int id_start;            // DH: frames >= id_start carry dh_out straight through
 };
 
-template <int EPI>
+template <typename C, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapW, const PgParams p) {
+    constexpr int CH = C::CH;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + NSLOT * SLOT);
@@ -98,16 +110,18 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             };
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
                 const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM + (int)rank * BM;
-                int gsl = 0;
-                for (int sg = 0; sg < p.n_seg; ++sg) {
-                    const KSeg s = p.seg[sg];
-                    const CUtensorMap* map = sg == 0 ? &mapA0 : &mapA1;
-                    for (int sl = 0; sl < s.slabs; ++sl, ++gsl) {
-                        unsigned bar;
-                        unsigned char* dst = acquire(bar);
-                        tma2_load_4d(dst, map, 2 * (t0 + s.shift - s.origin), sl * 4, 0, b, bar);
-                        dst = acquire(bar);
-                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + (gsl * 2 + (int)rank) * 8, bar);
+                for (int j = 0; j < C::NT; ++j) {
+                    int gsl = 0;
+                    for (int sg = 0; sg < p.n_seg; ++sg) {
+                        const KSeg s = p.seg[sg];
+                        const CUtensorMap* map = sg == 0 ? &mapA0 : &mapA1;
+                        for (int sl = 0; sl < s.slabs; ++sl, ++gsl) {
+                            unsigned bar;
+                            unsigned char* dst = acquire(bar);
+                            tma2_load_4d(dst, map, 2 * (t0 + s.shift - s.origin), sl * C::KC, 0, b, bar);
+                            dst = acquire(bar);
+                            tma2_load_2d(dst, &mapW, 0, p.w_row0 + ((j * p.w_slabs_per_tile + p.w_slab_off + gsl) * 2 + (int)rank) * 8, bar);
+                        }
                     }
                 }
             }
@@ -115,55 +129,59 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     } else if (warp == 1) {
         if (rank == 0) {
             constexpr unsigned idesc = make_idesc_bf16(PM, 256);
-            unsigned it = 0, n_item = 0;
-            for (int item = cluster_id; item < p.n_items; item += n_clusters, ++n_item) {
-                const unsigned ab = n_item & 1, u = n_item >> 1;
-                if (u > 0) mbar_wait_cluster(acc_empty + ab, (u - 1) & 1);
-                tc_fence_after();
-                const unsigned d = tmem_base + ab * 256;
-                for (int sl = 0; sl < slabs; ++sl) {
-                    const unsigned sa = it % NSLOT, pa = (it / NSLOT) & 1; ++it;
-                    const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
-                    mbar_wait_cluster(full + sa, pa);
-                    mbar_wait_cluster(full + sw, pw);
+            unsigned it = 0, q = 0;
+            for (int item = cluster_id; item < p.n_items; item += n_clusters)
+                for (int j = 0; j < C::NT; ++j, ++q) {
+                    const unsigned ab = q & 1, u = q >> 1;
+                    if (u > 0) mbar_wait_cluster(acc_empty + ab, (u - 1) & 1);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const unsigned a = s32(ring + sa * SLOT), w = s32(ring + sw * SLOT);
+                    const unsigned d = tmem_base + ab * 256;
+                    for (int sl = 0; sl < slabs; ++sl) {
+                        const unsigned sa = it % NSLOT, pa = (it / NSLOT) & 1; ++it;
+                        const unsigned sw = it % NSLOT, pw = (it / NSLOT) & 1; ++it;
+                        mbar_wait_cluster(full + sa, pa);
+                        mbar_wait_cluster(full + sw, pw);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const unsigned a = s32(ring + sa * SLOT), w = s32(ring + sw * SLOT);
 #pragma unroll
-                        for (int ks = 0; ks < KS / 16; ++ks) {
-                            const unsigned long long ah = smem_desc(a + ks * 2 * LBO, LBO, SBO), al = smem_desc(a + SLOT / 2 + ks * 2 * LBO, LBO, SBO);
-                            const unsigned long long bh = smem_desc(w + ks * 2 * LBO, LBO, SBO), bl = smem_desc(w + SLOT / 2 + ks * 2 * LBO, LBO, SBO);
-                            umma2_f16(d, ah, bh, idesc, (sl | ks) != 0);
-                            umma2_f16(d, al, bh, idesc, 1);
-                            umma2_f16(d, ah, bl, idesc, 1);
+                            for (int ks = 0; ks < C::KS / 16; ++ks) {
+                                const unsigned long long ah = smem_desc(a + ks * 2 * LBO, LBO, SBO), bh = smem_desc(w + ks * 2 * LBO, LBO, SBO);
+                                umma2_f16(d, ah, bh, idesc, (sl | ks) != 0);
+                                if constexpr (C::PAIR) {
+                                    umma2_f16(d, smem_desc(a + SLOT / 2 + ks * 2 * LBO, LBO, SBO), bh, idesc, 1);
+                                    umma2_f16(d, ah, smem_desc(w + SLOT / 2 + ks * 2 * LBO, LBO, SBO), idesc, 1);
+                                }
+                            }
+                            umma2_commit(empty + sa);
+                            umma2_commit(empty + sw);
+                            if (sl == slabs - 1) umma2_commit(acc_full + ab);
                         }
-                        umma2_commit(empty + sa);
-                        umma2_commit(empty + sw);
-                        if (sl == slabs - 1) umma2_commit(acc_full + ab);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
-            }
         }
     } else {
-        const int q = warp & 3, grp = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
+        const int qd = warp & 3, grp = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;
+        const unsigned lane_addr = tmem_base + ((unsigned)(qd * 32) << 16);
         const unsigned acc_empty_addr[2] = {mapa(s32(acc_empty), 0), mapa(s32(acc_empty + 1), 0)};
         const size_t L = (size_t)p.L;
-        unsigned n_item = 0;
-        for (int item = cluster_id; item < p.n_items; item += n_clusters, ++n_item) {
-            const unsigned ab = n_item & 1, u = n_item >> 1;
+        unsigned q = 0;
+        for (int item = cluster_id; item < p.n_items; item += n_clusters)
+          for (int j = 0; j < C::NT; ++j, ++q) {
+            const unsigned ab = q & 1, u = q >> 1;
             const int b = item / p.tiles_per_seq;
             const int t = p.t_begin + (item % p.tiles_per_seq) * PM + (int)rank * BM + row;
             const bool live = t < p.L;
+            const int n0 = j * 256;                                     // first output channel of this n-tile
             mbar_wait(acc_full + ab, u & 1);
             tc_fence_after();
             const unsigned ta = lane_addr + ab * 256;
             if (EPI == EPI_DZ) {
-                const float4* fg = p.fg + (size_t)b * (2 * CH / 4) * L + t;
-                uint4* dfg = p.out0 + (size_t)b * 2 * (2 * CH / 8) * L + t;            // planes of 64 chunks
-                uint4* zo = p.out1 + (size_t)b * 2 * (CH / 8) * L + t;                 // planes of 32 chunks
+                const float4* fg = p.fg + ((size_t)b * (2 * CH / 4) + n0 / 4) * L + t;
+                uint4* dfg = p.out0 + ((size_t)b * 2 * (2 * CH / 8) + n0 / 8) * L + t;     // planes of 2CH/8 chunks
+                uint4* zo = p.out1 + ((size_t)b * 2 * (CH / 8) + n0 / 8) * L + t;          // planes of CH/8 chunks
                 const size_t pl_fg = (size_t)(2 * CH / 8) * L, pl_z = (size_t)(CH / 8) * L;
 #pragma unroll 1
                 for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
@@ -200,8 +218,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 }
             } else {
                 const size_t pl = (size_t)(CH / 8) * L;
-                const uint4* rs = p.res ? p.res + (size_t)b * 2 * pl + t : nullptr;
-                uint4* o0 = p.out0 + (size_t)b * 2 * pl + t;
+                const uint4* rs = p.res ? p.res + ((size_t)b * 2 * (CH / 8) + n0 / 8) * L + t : nullptr;
+                uint4* o0 = p.out0 + ((size_t)b * 2 * (CH / 8) + n0 / 8) * L + t;
                 const bool add = live && rs != nullptr && t >= p.id_start;
 #pragma unroll 1
                 for (int c = grp * 128; c < grp * 128 + 128; c += 16) {
@@ -241,72 +259,53 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing (backward)
-// dz blocks [k-slab 16][half r 2]: N row n = r*128 + row = dilation channel; K index kk = sl*32 + ck*8 + e: kk < 256 ->
-// residual_conv.weight[kk][n], else skip_conv.weight[kk-256][n].  dh blocks [k-slab 32][r]: N row = residual channel;
-// kk = tap*512 + m (tap 0 pairs with dFG(t + d), tap 1 with dFG(t)), m < 256 -> filter.weight[m][n][tap], else gate.
-__global__ void pack_bwd_kernel(const float* __restrict__ wf, const float* __restrict__ wg, const float* __restrict__ wr,
-                                const float* __restrict__ ws, __nv_bfloat16* __restrict__ out) {
-    const int n_dz = SLABS_DZ * 2, n_blocks = n_dz + SLABS_DH * 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
-         i += (long long)gridDim.x * blockDim.x) {
-        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));
-        const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
-        float v;
-        if (blk < n_dz) {
-            const int sl = blk / 2, r = blk % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
-            v = kk < CH ? wr[(size_t)kk * CH + n] : ws[(size_t)(kk - CH) * CH + n];
-        } else {
-            const int bb = blk - n_dz, sl = bb / 2, r = bb % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
-            const int tap = kk / (2 * CH), m = kk % (2 * CH);
-            v = m < CH ? wf[((size_t)m * CH + n) * 2 + tap] : wg[((size_t)(m - CH) * CH + n) * 2 + tap];
-        }
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
-        o[0] = h;
-        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
-}
-
-// all layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs} (the table of wn_tb_pack_all_weights)
+// dz blocks [n-tile j][k-slab][half r]: N row n = 256j + r*128 + row = dilation channel; K index kk = sl*KS + ck*8 + e: kk < CH ->
+// residual_conv.weight[kk][n], else skip_conv.weight[kk-CH][n].  dh blocks [n-tile j][k-slab][r]: N row = residual channel;
+// kk = tap*2CH + m (tap 0 pairs with dFG(t + d), tap 1 with dFG(t)), m < CH -> filter.weight[m][n][tap], else gate.
+// All layers in one launch: ptrs[layer] = {wf, wg, bf, bg, wr, ws, br, bs} (the table of wn_tb_pack_all_weights).
+template <typename C>
 __global__ void pack_bwd_all_kernel(const float* const* __restrict__ ptrs, __nv_bfloat16* __restrict__ out_all) {
+    constexpr int CH = C::CH;
     const float* const* q = ptrs + (size_t)blockIdx.y * 8;
     const float* wf = q[0]; const float* wg = q[1]; const float* wr = q[4]; const float* ws = q[5];
-    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (WB_LAYER_BYTES / 2);
-    const int n_dz = SLABS_DZ * 2, n_blocks = n_dz + SLABS_DH * 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * (SLOT / 4);
+    __nv_bfloat16* out = out_all + (size_t)blockIdx.y * (C::WB_LAYER_BYTES / 2);
+    constexpr int n_dz = C::NT * C::SLABS_DZ * 2, n_blocks = n_dz + C::NT * C::SLABS_DH * 2;
+    constexpr int per_plane = SLOT / 2 / C::PLANES;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_blocks * per_plane;
          i += (long long)gridDim.x * blockDim.x) {
-        const int blk = (int)(i / (SLOT / 4)), w = (int)(i % (SLOT / 4));
+        const int blk = (int)(i / per_plane), w = (int)(i % per_plane);
         const int ck = w / (BM * 8), row = (w / 8) % BM, e = w % 8;
         float v;
         if (blk < n_dz) {
-            const int sl = blk / 2, r = blk % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
+            const int j = blk / (C::SLABS_DZ * 2), sl = (blk / 2) % C::SLABS_DZ, r = blk % 2;
+            const int n = j * 256 + r * 128 + row, kk = sl * C::KS + ck * 8 + e;
             v = kk < CH ? wr[(size_t)kk * CH + n] : ws[(size_t)(kk - CH) * CH + n];
         } else {
-            const int bb = blk - n_dz, sl = bb / 2, r = bb % 2, n = r * 128 + row, kk = sl * KS + ck * 8 + e;
+            const int bb = blk - n_dz, j = bb / (C::SLABS_DH * 2), sl = (bb / 2) % C::SLABS_DH, r = bb % 2;
+            const int n = j * 256 + r * 128 + row, kk = sl * C::KS + ck * 8 + e;
             const int tap = kk / (2 * CH), m = kk % (2 * CH);
             v = m < CH ? wf[((size_t)m * CH + n) * 2 + tap] : wg[((size_t)(m - CH) * CH + n) * 2 + tap];
         }
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         __nv_bfloat16* o = out + (size_t)blk * (SLOT / 2) + w;
         o[0] = h;
-        o[SLOT / 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if constexpr (C::PAIR) o[per_plane] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
 
 // ============================================================================================== weight gradients
-constexpr int WG_KF = 32;                         // frames per k-slab: slot image [plane 2][chunk 16][frame 32][16 B]
+constexpr int WG_KF = 32;                         // frames per k-slab: slot image [plane][chunk 16][frame 32][16 B]
 constexpr int WG_NSLOT = 8;
 constexpr int WG_THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
 constexpr size_t SMEM_WG = 128 + WG_NSLOT * SLOT + 256;
-constexpr int WG_MAX_JOBS = 6;
+constexpr int WG_MAX_JOBS = 24;
 
 struct WgJob {
     int g_map, g_chunk0, g_origin;                // g operand: tensor map index, first chunk of the 256-channel M tile, map origin frame
-    int x_map, x_origin, x_shift;                 // x operand: frames t + x_shift
+    int x_map, x_origin, x_shift, x_chunk0;       // x operand: frames t + x_shift, first chunk of the 256-channel N tile
     int t_lo, slabs_per_seq, total_slabs;         // frames [t_lo, L) of every sequence, in slabs of 32
     int split0, n_splits, slabs_per_split;        // clusters [split0, split0 + n_splits) work on this job
     int work_slot0;                               // partial (256 x 256 fp32) index of split 0 in the workspace
-    int pad;
 };
 struct WgParams {
     int n_jobs, B;
@@ -314,6 +313,7 @@ struct WgParams {
     float* work;
 };
 
+template <bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad2_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
               const __grid_constant__ CUtensorMap m3, const __grid_constant__ CUtensorMap m4, const WgParams p) {
@@ -359,10 +359,10 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CU
                 for (int which = 0; which < 2; ++which, ++it) {
                     const unsigned sl = it % WG_NSLOT, ph = (it / WG_NSLOT) & 1;
                     mbar_wait(empty + sl, ph ^ 1);
-                    if (rank == 0) mbar_expect_tx(full + sl, 2 * SLOT);
+                    if (rank == 0) mbar_expect_tx(full + sl, PAIR ? 2 * SLOT : SLOT);          // single pass: the hi plane only
                     const unsigned bar = mapa(s32(full + sl), 0);
                     if (which == 0) tma2_load_4d(ring + sl * SLOT, gm, 2 * (t0 - jb.g_origin), jb.g_chunk0 + 16 * (int)rank, 0, b, bar);
-                    else tma2_load_4d(ring + sl * SLOT, xm, 2 * (t0 + jb.x_shift - jb.x_origin), 16 * (int)rank, 0, b, bar);
+                    else tma2_load_4d(ring + sl * SLOT, xm, 2 * (t0 + jb.x_shift - jb.x_origin), jb.x_chunk0 + 16 * (int)rank, 0, b, bar);
                 }
             }
         }
@@ -381,11 +381,12 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CU
                     const unsigned g = s32(ring + sg * SLOT), x = s32(ring + sx * SLOT);
 #pragma unroll
                     for (int ks = 0; ks < WG_KF / 16; ++ks) {
-                        const unsigned long long gh = smem_desc(g + ks * 2 * KLBO, KLBO, KSBO), gl = smem_desc(g + SLOT / 2 + ks * 2 * KLBO, KLBO, KSBO);
-                        const unsigned long long xh = smem_desc(x + ks * 2 * KLBO, KLBO, KSBO), xl = smem_desc(x + SLOT / 2 + ks * 2 * KLBO, KLBO, KSBO);
+                        const unsigned long long gh = smem_desc(g + ks * 2 * KLBO, KLBO, KSBO), xh = smem_desc(x + ks * 2 * KLBO, KLBO, KSBO);
                         umma2_f16(tmem_base, gh, xh, idesc, (i | ks) != 0);
-                        umma2_f16(tmem_base, gl, xh, idesc, 1);
-                        umma2_f16(tmem_base, gh, xl, idesc, 1);
+                        if constexpr (PAIR) {
+                            umma2_f16(tmem_base, smem_desc(g + SLOT / 2 + ks * 2 * KLBO, KLBO, KSBO), xh, idesc, 1);
+                            umma2_f16(tmem_base, gh, smem_desc(x + SLOT / 2 + ks * 2 * KLBO, KLBO, KSBO), idesc, 1);
+                        }
                     }
                     umma2_commit(empty + sg);
                     umma2_commit(empty + sx);
@@ -438,29 +439,41 @@ __global__ void wgrad2_reduce_kernel(const WgReduceParams p) {
 
 using namespace wn;
 
-extern "C" size_t wn_tb_bwd_weight_bytes_per_layer(void) { return tb2::WB_LAYER_BYTES; }
-
-extern "C" int wn_tb_pack_block_bwd_weights(const float* d_wf, const float* d_wg, const float* d_wr, const float* d_ws,
-                                            void* d_w_layer, void* stream) {
-    WN_REQUIRE(d_wf && d_wg && d_wr && d_ws && d_w_layer, WN_E_BADARG, "wn_tb_pack_block_bwd_weights: null pointer");
-    tb2::pack_bwd_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d_wf, d_wg, d_wr, d_ws, (__nv_bfloat16*)d_w_layer);
-    WN_CUDA(cudaGetLastError());
-    return 0;
+// dispatch over (channels, precision): f.template operator()<Cfg>()
+template <typename F>
+static int with_cfg(int channels, int precision, F&& f) {
+    if (precision == WN_PREC_BF16_PAIRS) return f.template operator()<tb2::Cfg<256, true>>();
+    if (channels == 256) return f.template operator()<tb2::Cfg<256, false>>();
+    return f.template operator()<tb2::Cfg<512, false>>();
 }
 
-extern "C" int wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, void* d_wb_all, void* stream) {
+extern "C" size_t wn_tb_bwd_weight_bytes_per_layer(int channels, int precision) {
+    if (!wn_tb_precision_supported(channels, precision)) return 0;
+    size_t r = 0;
+    with_cfg(channels, precision, [&]<typename C>() { r = C::WB_LAYER_BYTES; return 0; });
+    return r;
+}
+
+extern "C" int wn_tb_pack_all_bwd_weights(const float* const* d_ptrs, int n_layers, int channels, int precision, void* d_wb_all,
+                                          void* stream) {
     WN_REQUIRE(d_ptrs && d_wb_all && n_layers > 0, WN_E_BADARG, "wn_tb_pack_all_bwd_weights: bad arguments");
-    tb2::pack_bwd_all_kernel<<<dim3(74, n_layers), 256, 0, (cudaStream_t)stream>>>(d_ptrs, (__nv_bfloat16*)d_wb_all);
+    WN_REQUIRE(wn_tb_precision_supported(channels, precision), WN_E_UNSUPP, "wn_tb_pack_all_bwd_weights: %d channels with precision %d is not supported",
+               channels, precision);
+    cudaStream_t st = (cudaStream_t)stream;
+    with_cfg(channels, precision, [&]<typename C>() {
+        tb2::pack_bwd_all_kernel<C><<<dim3(74, n_layers), 256, 0, st>>>(d_ptrs, (__nv_bfloat16*)d_wb_all);
+        return 0;
+    });
     WN_CUDA(cudaGetLastError());
     return 0;
 }
 
-template <int EPI>
+template <typename C, int EPI>
 static int launch_pg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const tb2::PgParams& p, cudaStream_t st) {
     int dev = 0, sms = 0;
     WN_CUDA(cudaGetDevice(&dev));
     WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    WN_CUDA(cudaFuncSetAttribute(tb2::pair_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb2::SMEM_PG));
+    WN_CUDA(cudaFuncSetAttribute(tb2::pair_gemm_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb2::SMEM_PG));
     int grid = 2 * p.n_items;
     const int max_grid = (sms / 2) * 2;
     if (grid > max_grid) grid = max_grid;
@@ -473,26 +486,20 @@ static int launch_pg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, tb2::pair_gemm_kernel<EPI>, a0, a1, w, p));
+    WN_CUDA(cudaLaunchKernelEx(&cfg, tb2::pair_gemm_kernel<C, EPI>, a0, a1, w, p));
     WN_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int wn_tb_block_bwd_data(const wn_tb_bwd_args* a, void* stream) {
-    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_block_bwd_data: null args");
-    WN_REQUIRE(a->d_dskip && a->d_fg && a->d_dfg && a->d_z && a->d_dh_in && a->d_wb_all, WN_E_BADARG, "wn_tb_block_bwd_data: null pointer");
-    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->layer >= 0 && a->layer < a->n_layers, WN_E_BADARG, "wn_tb_block_bwd_data: bad sizes");
-    WN_REQUIRE(a->gz >= a->out_start && a->gz < a->L && a->gs_in >= a->in_start && a->gs_in <= a->gz && a->ds_start >= a->out_start &&
-                   a->ds_start < a->L,
-               WN_E_BADARG, "wn_tb_block_bwd_data: bad gradient frame ranges");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int B = a->B, L = a->L;
+template <typename C>
+static int bwd_data(const wn_tb_bwd_args* a, cudaStream_t st) {
+    const int B = a->B, L = a->L, CH = C::CH;
     const bool have_dh = a->d_dh_out != nullptr && a->gs_out < L;
     CUtensorMap mDh, mDs, mW, mDfg;
-    if (int rc = tb::make_pair_map(&mDs, a->d_dskip, B, L - a->ds_start, tb2::CH, 0, tb2::BM, tb2::KS / 8)) return rc;
-    if (have_dh) { if (int rc = tb::make_pair_map(&mDh, a->d_dh_out, B, L, tb2::CH, a->gs_out, tb2::BM, tb2::KS / 8)) return rc; }
+    if (int rc = tb::make_pair_map(&mDs, a->d_dskip, B, L - a->ds_start, CH, 0, tb2::BM, C::KC, C::PLANES)) return rc;
+    if (have_dh) { if (int rc = tb::make_pair_map(&mDh, a->d_dh_out, B, L, CH, a->gs_out, tb2::BM, C::KC, C::PLANES)) return rc; }
     else mDh = mDs;
-    if (int rc = tb::make_wrows_map(&mW, a->d_wb_all, (long long)a->n_layers * tb2::WROWS_BWD_LAYER)) return rc;
+    if (int rc = tb::make_wrows_map(&mW, a->d_wb_all, (long long)a->n_layers * C::WROWS_BWD_LAYER)) return rc;
     tb2::PgParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.L = L;
@@ -500,32 +507,46 @@ extern "C" int wn_tb_block_bwd_data(const wn_tb_bwd_args* a, void* stream) {
     p.t_begin = a->gz;
     p.tiles_per_seq = (L - a->gz + tb2::PM - 1) / tb2::PM;
     p.n_items = B * p.tiles_per_seq;
-    const int row0 = a->layer * tb2::WROWS_BWD_LAYER;
+    const int row0 = a->layer * C::WROWS_BWD_LAYER;
+    p.w_row0 = row0; p.w_slabs_per_tile = C::SLABS_DZ;
     if (have_dh) {
         p.n_seg = 2;
-        p.seg[0].shift = 0; p.seg[0].origin = a->gs_out; p.seg[0].slabs = tb2::CH / tb2::KS;
-        p.seg[1].shift = 0; p.seg[1].origin = a->ds_start; p.seg[1].slabs = tb2::CH / tb2::KS;
-        p.w_row0 = row0;
+        p.seg[0].shift = 0; p.seg[0].origin = a->gs_out; p.seg[0].slabs = CH / C::KS;
+        p.seg[1].shift = 0; p.seg[1].origin = a->ds_start; p.seg[1].slabs = CH / C::KS;
+        p.w_slab_off = 0;
     } else {
         p.n_seg = 1;
-        p.seg[0].shift = 0; p.seg[0].origin = a->ds_start; p.seg[0].slabs = tb2::CH / tb2::KS;
-        p.w_row0 = row0 + (tb2::CH / tb2::KS) * 2 * 8;          // skip rows of the packed dz weights only
+        p.seg[0].shift = 0; p.seg[0].origin = a->ds_start; p.seg[0].slabs = CH / C::KS;
+        p.w_slab_off = CH / C::KS;                               // the skip part of the packed dz weights only
     }
     p.fg = (const float4*)a->d_fg; p.out0 = (uint4*)a->d_dfg; p.out1 = (uint4*)a->d_z;
-    if (int rc = launch_pg<tb2::EPI_DZ>(have_dh ? mDh : mDs, mDs, mW, p, st)) return rc;
+    if (int rc = launch_pg<C, tb2::EPI_DZ>(have_dh ? mDh : mDs, mDs, mW, p, st)) return rc;
     // ---- dh_in = dh_out + anti-causal taps of dFG, frames [gs_in, L)
-    if (int rc = tb::make_pair_map(&mDfg, a->d_dfg, B, L, 2 * tb2::CH, a->gz, tb2::BM, tb2::KS / 8)) return rc;
+    if (int rc = tb::make_pair_map(&mDfg, a->d_dfg, B, L, 2 * CH, a->gz, tb2::BM, C::KC, C::PLANES)) return rc;
     p.t_begin = a->gs_in;
     p.tiles_per_seq = (L - a->gs_in + tb2::PM - 1) / tb2::PM;
     p.n_items = B * p.tiles_per_seq;
     p.n_seg = 2;
-    p.seg[0].shift = a->dilation; p.seg[0].origin = a->gz; p.seg[0].slabs = 2 * tb2::CH / tb2::KS;
-    p.seg[1].shift = 0; p.seg[1].origin = a->gz; p.seg[1].slabs = 2 * tb2::CH / tb2::KS;
-    p.w_row0 = row0 + tb2::WROWS_DZ;
+    p.seg[0].shift = a->dilation; p.seg[0].origin = a->gz; p.seg[0].slabs = 2 * CH / C::KS;
+    p.seg[1].shift = 0; p.seg[1].origin = a->gz; p.seg[1].slabs = 2 * CH / C::KS;
+    p.w_row0 = row0 + C::WROWS_DZ; p.w_slabs_per_tile = C::SLABS_DH; p.w_slab_off = 0;
     p.fg = nullptr; p.out0 = (uint4*)a->d_dh_in; p.out1 = nullptr;
     p.res = have_dh ? (const uint4*)a->d_dh_out : nullptr;
     p.id_start = a->gs_out > a->out_start ? a->gs_out : a->out_start;
-    return launch_pg<tb2::EPI_DH>(mDfg, mDfg, mW, p, st);
+    return launch_pg<C, tb2::EPI_DH>(mDfg, mDfg, mW, p, st);
+}
+
+extern "C" int wn_tb_block_bwd_data(const wn_tb_bwd_args* a, void* stream) {
+    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_block_bwd_data: null args");
+    WN_REQUIRE(a->d_dskip && a->d_fg && a->d_dfg && a->d_z && a->d_dh_in && a->d_wb_all, WN_E_BADARG, "wn_tb_block_bwd_data: null pointer");
+    WN_REQUIRE(wn_tb_precision_supported(a->channels, a->precision), WN_E_UNSUPP, "wn_tb_block_bwd_data: %d channels with precision %d is not supported",
+               a->channels, a->precision);
+    WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1 && a->layer >= 0 && a->layer < a->n_layers, WN_E_BADARG, "wn_tb_block_bwd_data: bad sizes");
+    WN_REQUIRE(a->gz >= a->out_start && a->gz < a->L && a->gs_in >= a->in_start && a->gs_in <= a->gz && a->ds_start >= a->out_start &&
+                   a->ds_start < a->L,
+               WN_E_BADARG, "wn_tb_block_bwd_data: bad gradient frame ranges");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_cfg(a->channels, a->precision, [&]<typename C>() { return bwd_data<C>(a, st); });
 }
 
 extern "C" size_t wn_tb_wgrad_workspace_bytes(void) { return (size_t)160 * 65536 * 4; }
@@ -534,44 +555,54 @@ extern "C" int wn_tb_wgrad(const wn_tb_wgrad_args* a, void* stream) {
     WN_REQUIRE(a, WN_E_BADARG, "wn_tb_wgrad: null args");
     WN_REQUIRE(a->d_dskip && a->d_dfg && a->d_z && a->d_h_in && a->d_gws && a->d_gwr && a->d_gwf && a->d_gwg && a->d_work, WN_E_BADARG,
                "wn_tb_wgrad: null pointer");
+    WN_REQUIRE(wn_tb_precision_supported(a->channels, a->precision), WN_E_UNSUPP, "wn_tb_wgrad: %d channels with precision %d is not supported",
+               a->channels, a->precision);
     WN_REQUIRE(a->B > 0 && a->L > 0 && a->dilation >= 1, WN_E_BADARG, "wn_tb_wgrad: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     WN_CUDA(cudaGetDevice(&dev));
     WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int B = a->B, L = a->L, d = a->dilation;
+    const int B = a->B, L = a->L, d = a->dilation, CH = a->channels;
+    const bool pair = a->precision == WN_PREC_BF16_PAIRS;
+    const int planes = pair ? 2 : 1;
     const bool have_dh = a->d_dh_out != nullptr && a->id_start < L;
-    // tensor maps with the MN-major box {32 frames, 16 chunks, 2 planes}: 0 dskip, 1 dh_out, 2 dFG, 3 z, 4 h_in
+    // tensor maps with the MN-major box {32 frames, 16 chunks, planes}: 0 dskip, 1 dh_out, 2 dFG, 3 z, 4 h_in
     CUtensorMap m[5];
-    if (int rc = tb::make_pair_map(&m[0], a->d_dskip, B, L - a->ds_start, tb2::CH, 0, tb2::WG_KF, 16)) return rc;
-    if (have_dh) { if (int rc = tb::make_pair_map(&m[1], a->d_dh_out, B, L, tb2::CH, a->id_start, tb2::WG_KF, 16)) return rc; }
+    if (int rc = tb::make_pair_map(&m[0], a->d_dskip, B, L - a->ds_start, CH, 0, tb2::WG_KF, 16, planes)) return rc;
+    if (have_dh) { if (int rc = tb::make_pair_map(&m[1], a->d_dh_out, B, L, CH, a->id_start, tb2::WG_KF, 16, planes)) return rc; }
     else m[1] = m[0];
-    if (int rc = tb::make_pair_map(&m[2], a->d_dfg, B, L, 2 * tb2::CH, a->gz, tb2::WG_KF, 16)) return rc;
-    if (int rc = tb::make_pair_map(&m[3], a->d_z, B, L, tb2::CH, a->gz, tb2::WG_KF, 16)) return rc;
-    if (int rc = tb::make_pair_map(&m[4], a->d_h_in, B, L, tb2::CH, a->in_start, tb2::WG_KF, 16)) return rc;
+    if (int rc = tb::make_pair_map(&m[2], a->d_dfg, B, L, 2 * CH, a->gz, tb2::WG_KF, 16, planes)) return rc;
+    if (int rc = tb::make_pair_map(&m[3], a->d_z, B, L, CH, a->gz, tb2::WG_KF, 16, planes)) return rc;
+    if (int rc = tb::make_pair_map(&m[4], a->d_h_in, B, L, CH, a->in_start, tb2::WG_KF, 16, planes)) return rc;
     tb2::WgParams p;
     tb2::WgReduceParams rp;
     memset(&p, 0, sizeof(p));
     memset(&rp, 0, sizeof(rp));
     p.B = B; p.work = a->d_work; rp.work = a->d_work;
     int nj = 0;
-    auto add = [&](int g_map, int g_chunk0, int g_origin, int x_map, int x_origin, int x_shift, int t_lo, float* dst, long long ns, long long cs) {
-        tb2::WgJob& j = p.job[nj];
-        j.g_map = g_map; j.g_chunk0 = g_chunk0; j.g_origin = g_origin; j.x_map = x_map; j.x_origin = x_origin; j.x_shift = x_shift;
-        j.t_lo = t_lo < L ? t_lo : L;
-        j.slabs_per_seq = (L - j.t_lo + tb2::WG_KF - 1) / tb2::WG_KF;
-        j.total_slabs = B * j.slabs_per_seq;
-        rp.o[nj].dst = dst; rp.o[nj].n_stride = ns; rp.o[nj].c_stride = cs;
-        ++nj;
+    const int T = CH / 256;                                   // 256-channel tiles per side
+    // out[(n0 + n) * ns + (c0 + c) * cs]: one job per (256 g-channels, 256 x-channels) tile
+    auto add = [&](int g_map, int g_chunk_base, int g_origin, int x_map, int x_origin, int x_shift, int t_lo, float* dst, long long ns, long long cs) {
+        for (int mt = 0; mt < T; ++mt)
+            for (int nt = 0; nt < T; ++nt) {
+                tb2::WgJob& j = p.job[nj];
+                j.g_map = g_map; j.g_chunk0 = g_chunk_base + 32 * mt; j.g_origin = g_origin;
+                j.x_map = x_map; j.x_origin = x_origin; j.x_shift = x_shift; j.x_chunk0 = 32 * nt;
+                j.t_lo = t_lo < L ? t_lo : L;
+                j.slabs_per_seq = (L - j.t_lo + tb2::WG_KF - 1) / tb2::WG_KF;
+                j.total_slabs = B * j.slabs_per_seq;
+                rp.o[nj].dst = dst + (size_t)(256 * mt) * ns + (size_t)(256 * nt) * cs; rp.o[nj].n_stride = ns; rp.o[nj].c_stride = cs;
+                ++nj;
+            }
     };
-    const long long CC = tb2::CH;
+    const long long CC = CH;
     add(0, 0, a->ds_start, 3, a->gz, 0, a->ds_start, a->d_gws, CC, 1);                                   // skip_conv.weight (S, D, 1)
     if (have_dh) add(1, 0, a->id_start, 3, a->gz, 0, a->id_start, a->d_gwr, CC, 1);                      // residual_conv.weight (R, D, 1)
     for (int tap = 0; tap < 2; ++tap) {
         const int sh = (1 - tap) * d;
         const int lo = a->gz > a->in_start + sh ? a->gz : a->in_start + sh;      // frames whose tap lands on real input
-        add(2, 0, a->gz, 4, a->in_start, -sh, lo, a->d_gwf + tap, 2 * CC, 2);     // filter.weight (D, R, 2)[:, :, tap]
-        add(2, 32, a->gz, 4, a->in_start, -sh, lo, a->d_gwg + tap, 2 * CC, 2);    // gate.weight
+        add(2, 0, a->gz, 4, a->in_start, -sh, lo, a->d_gwf + tap, 2 * CC, 2);          // filter.weight (D, R, 2)[:, :, tap]
+        add(2, CH / 8, a->gz, 4, a->in_start, -sh, lo, a->d_gwg + tap, 2 * CC, 2);     // gate.weight
     }
     p.n_jobs = rp.n_jobs = nj;
     // clusters per job proportional to its slabs (at least 1), one wave of sms/2 clusters
@@ -592,7 +623,6 @@ extern "C" int wn_tb_wgrad(const wn_tb_wgrad_args* a, void* stream) {
     }
     WN_REQUIRE((size_t)slot * 65536 * 4 <= wn_tb_wgrad_workspace_bytes(), WN_E_UNSUPP, "wn_tb_wgrad: workspace too small for %d partials", slot);
     if (!have_dh) WN_CUDA(cudaMemsetAsync(a->d_gwr, 0, sizeof(float) * CC * CC, st));
-    WN_CUDA(cudaFuncSetAttribute(tb2::wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb2::SMEM_WG));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * used));
     cfg.blockDim = dim3(tb2::WG_THREADS);
@@ -602,7 +632,13 @@ extern "C" int wn_tb_wgrad(const wn_tb_wgrad_args* a, void* stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, tb2::wgrad2_kernel, m[0], m[1], m[2], m[3], m[4], p));
+    if (pair) {
+        WN_CUDA(cudaFuncSetAttribute(tb2::wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb2::SMEM_WG));
+        WN_CUDA(cudaLaunchKernelEx(&cfg, tb2::wgrad2_kernel<true>, m[0], m[1], m[2], m[3], m[4], p));
+    } else {
+        WN_CUDA(cudaFuncSetAttribute(tb2::wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb2::SMEM_WG));
+        WN_CUDA(cudaLaunchKernelEx(&cfg, tb2::wgrad2_kernel<false>, m[0], m[1], m[2], m[3], m[4], p));
+    }
     WN_CUDA(cudaGetLastError());
     tb2::wgrad2_reduce_kernel<<<dim3(256, nj), 256, 0, st>>>(rp);
     WN_CUDA(cudaGetLastError());

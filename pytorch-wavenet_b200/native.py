@@ -56,18 +56,23 @@ class TcBlockArgs(C.Structure):
                 ("skip_init", C.c_int), ("d_fg_save", C.c_void_p), ("fast_tf32", C.c_int)]
 
 
+PREC_BF16, PREC_BF16_PAIRS = 1, 2        # WN_PREC_* of include/wavenet_b200.h
+
+
 class TbBlockArgs(C.Structure):
     _fields_ = [("d_h_in", C.c_void_p), ("d_h_out", C.c_void_p), ("d_skip", C.c_void_p),
                 ("d_w_all", C.c_void_p), ("d_bias4", C.c_void_p), ("layer", C.c_int), ("n_layers", C.c_int),
+                ("channels", C.c_int), ("precision", C.c_int),
                 ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
                 ("in_start", C.c_int), ("out_start", C.c_int), ("skip_start", C.c_int), ("skip_init", C.c_int),
-                ("d_fg_save", C.c_void_p), ("d_z_save", C.c_void_p)]
+                ("d_fg_save", C.c_void_p)]
 
 
 class TbBwdArgs(C.Structure):
     _fields_ = [("d_dh_out", C.c_void_p), ("d_dskip", C.c_void_p), ("d_fg", C.c_void_p),
                 ("d_dfg", C.c_void_p), ("d_z", C.c_void_p), ("d_dh_in", C.c_void_p), ("d_wb_all", C.c_void_p),
-                ("layer", C.c_int), ("n_layers", C.c_int), ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
+                ("layer", C.c_int), ("n_layers", C.c_int), ("channels", C.c_int), ("precision", C.c_int),
+                ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
                 ("in_start", C.c_int), ("out_start", C.c_int),
                 ("gs_out", C.c_int), ("ds_start", C.c_int), ("gz", C.c_int), ("gs_in", C.c_int)]
 
@@ -75,7 +80,7 @@ class TbBwdArgs(C.Structure):
 class TbWgradArgs(C.Structure):
     _fields_ = [("d_dskip", C.c_void_p), ("d_dh_out", C.c_void_p), ("d_dfg", C.c_void_p), ("d_z", C.c_void_p),
                 ("d_h_in", C.c_void_p), ("d_gws", C.c_void_p), ("d_gwr", C.c_void_p), ("d_gwf", C.c_void_p),
-                ("d_gwg", C.c_void_p), ("d_work", C.c_void_p),
+                ("d_gwg", C.c_void_p), ("d_work", C.c_void_p), ("channels", C.c_int), ("precision", C.c_int),
                 ("B", C.c_int), ("L", C.c_int), ("dilation", C.c_int),
                 ("in_start", C.c_int), ("ds_start", C.c_int), ("id_start", C.c_int), ("gz", C.c_int)]
 
@@ -127,16 +132,17 @@ SIGNATURES = {
     "wn_tc_block_fwd": (C.c_int, [C.POINTER(TcBlockArgs), C.c_void_p]),
     "wn_tc_read_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "wn_tb_supported": (C.c_int, [C.c_int] * 4),
-    "wn_tb_weight_bytes_per_layer": (C.c_size_t, []),
-    "wn_tb_pack_block_weights": (C.c_int, [C.c_void_p] * 10 + [C.c_void_p]),
+    "wn_tb_precision_supported": (C.c_int, [C.c_int] * 2),
+    "wn_tb_weight_bytes_per_layer": (C.c_size_t, [C.c_int] * 2),
+    "wn_tb_pack_all_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wn_tb_start_index_u8": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 2),
     "wn_tb_start_index_i64": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 2),
     "wn_pair_from_frames": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_frames_from_pair": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_frames_from_chunks4": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "wn_tb_block_fwd": (C.c_int, [C.POINTER(TbBlockArgs), C.c_void_p]),
-    "wn_tb_bwd_weight_bytes_per_layer": (C.c_size_t, []),
-    "wn_tb_pack_block_bwd_weights": (C.c_int, [C.c_void_p] * 5 + [C.c_void_p]),
+    "wn_tb_bwd_weight_bytes_per_layer": (C.c_size_t, [C.c_int] * 2),
+    "wn_tb_pack_all_bwd_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wn_tb_block_bwd_data": (C.c_int, [C.POINTER(TbBwdArgs), C.c_void_p]),
     "wn_tb_wgrad_workspace_bytes": (C.c_size_t, []),
     "wn_tb_wgrad": (C.c_int, [C.POINTER(TbWgradArgs), C.c_void_p]),
@@ -155,8 +161,7 @@ SIGNATURES = {
     "wn_ce_fwd_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 2 + [C.c_void_p]),
     "wn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 5 + [C.c_int, C.c_void_p]),
     "wn_scatter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
-    "wn_tb_pack_all_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "wn_tb_pack_all_bwd_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+
     "wn_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
     "wn_colsum": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "wn_relu_copy": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p]),
@@ -187,7 +192,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError here == header and library disagree
             fn.restype, fn.argtypes = res, args
-        if handle.wn_version() != 1:
+        if handle.wn_version() != 2:
             raise RuntimeError("wavenet_b200: ABI version mismatch between native.py and libwavenet_b200.so")
         _lib = handle
     return _lib

@@ -65,6 +65,8 @@ class _Packs:
         self.rt, self.groups = rt, {}
 
     def __getitem__(self, name):
+        if name in ("tb", "tb_bwd") and name in self.groups and self.groups[name][-1] != self.rt.tb_precision():
+            del self.groups[name]                       # packed for the other operand precision
         if name not in self.groups:
             rt = self.rt
             stream = torch.cuda.current_stream(rt.device()).cuda_stream
@@ -153,20 +155,22 @@ class _Packs:
 
     def _build_tb(self, stream):
         rt, lib = self.rt, native.lib()
-        nl = self._dims()[6]
-        dev = rt.device()
-        tb_w = torch.empty(nl, lib.wn_tb_weight_bytes_per_layer(), device=dev, dtype=torch.uint8)
-        tb_b = torch.empty(nl, 4 * 256, device=dev, dtype=torch.float32)
-        native.check(lib.wn_tb_pack_all_weights(self._ptr_table().data_ptr(), nl, tb_w.data_ptr(), tb_b.data_ptr(), stream),
-                     "pack tb")
-        return tb_w, tb_b
+        R, nl = self._dims()[0], self._dims()[6]
+        prec, dev = rt.tb_precision(), rt.device()
+        tb_w = torch.empty(nl, lib.wn_tb_weight_bytes_per_layer(R, prec), device=dev, dtype=torch.uint8)
+        tb_b = torch.empty(nl, 4 * R, device=dev, dtype=torch.float32)
+        native.check(lib.wn_tb_pack_all_weights(self._ptr_table().data_ptr(), nl, R, prec, tb_w.data_ptr(), tb_b.data_ptr(),
+                                                stream), "pack tb")
+        return tb_w, tb_b, prec
 
     def _build_tb_bwd(self, stream):
         rt, lib = self.rt, native.lib()
-        nl = self._dims()[6]
-        wb = torch.empty(nl, lib.wn_tb_bwd_weight_bytes_per_layer(), device=rt.device(), dtype=torch.uint8)
-        native.check(lib.wn_tb_pack_all_bwd_weights(self._ptr_table().data_ptr(), nl, wb.data_ptr(), stream), "pack tb bwd")
-        return wb
+        R, nl = self._dims()[0], self._dims()[6]
+        prec = rt.tb_precision()
+        wb = torch.empty(nl, lib.wn_tb_bwd_weight_bytes_per_layer(R, prec), device=rt.device(), dtype=torch.uint8)
+        native.check(lib.wn_tb_pack_all_bwd_weights(self._ptr_table().data_ptr(), nl, R, prec, wb.data_ptr(), stream),
+                     "pack tb bwd")
+        return wb, prec
 
     def _build_head_rows(self, stream):
         """end_conv_2 / end_conv_1 weight rows zero-padded to the SIMT kernels' column pitch (wn_head_bwd_data)."""
@@ -219,6 +223,16 @@ class _Runtime:
         return dict(start=g(m.start_conv), filt=[g(m.filter_convs[i]) for i in range(n)],
                     gate=[g(m.gate_convs[i]) for i in range(n)], res=[g(m.residual_convs[i]) for i in range(n)],
                     skip=[g(m.skip_convs[i]) for i in range(n)], end1=g(m.end_conv_1), end2=g(m.end_conv_2))
+
+    def tb_precision(self):
+        """Operand precision of the fused tensor-core kernels for this model: ``tc_precision`` "bf16x2" -> bf16 (hi, lo)
+        pairs (fp32-class; 256 channels), "bf16" -> single-pass bf16 operands with fp32 accumulation and an fp32-class
+        residual / skip stream (256 or 512 channels).  512-channel nets always run single pass (the resident z image of a
+        512-channel pair does not fit on the SM)."""
+        R = self.model.residual_channels
+        if self.tc_precision == "bf16" or R == 512:
+            return native.PREC_BF16
+        return native.PREC_BF16_PAIRS
 
     def invalidate(self):
         """Forget the packed weight copies.  The cache is keyed on (data_ptr, tensor version); writes through ``p.data``
@@ -289,13 +303,14 @@ class _Runtime:
         n_layers = len(dil)
         if os.environ.get("WN_CHECK_INDICES") and index_input and (int(x.min()) < 0 or int(x.max()) >= Cc):
             raise RuntimeError(f"wavenet_b200: class index outside [0, {Cc}) (the reference's one-hot scatter raises here)")
-        if self.tc_precision not in ("tf32x3", "bf16x2"):
-            raise ValueError(f"tc_precision must be 'tf32x3' or 'bf16x2', not {self.tc_precision!r}")
+        if self.tc_precision not in ("tf32x3", "bf16x2", "bf16"):
+            raise ValueError(f"tc_precision must be 'bf16x2', 'bf16' or (two-launch blocks only) 'tf32x3', not {self.tc_precision!r}")
         if self.block_mode not in ("auto", "tb", "tc", "ffma"):
             raise ValueError(f"block_mode must be 'auto', 'tb', 'tc' or 'ffma', not {self.block_mode!r}")
-        use_tb = (self.block_mode in ("auto", "tb") and not self.fast_tf32 and bool(lib.wn_tb_supported(R, D, S, k)))
+        use_tb = (self.block_mode in ("auto", "tb") and not self.fast_tf32 and self.tc_precision != "tf32x3" and
+                  bool(lib.wn_tb_supported(R, D, S, k)))
         if self.block_mode == "tb" and not use_tb:
-            raise RuntimeError("wavenet_b200: the fused tensor-core block needs R = D = S = 256, kernel_size = 2 "
+            raise RuntimeError("wavenet_b200: the fused tensor-core block needs R = D = S in (256, 512), kernel_size = 2 "
                                f"(got {R},{D},{S},{k})")
         if use_tb:
             return self._forward_tb(x, index_input, B, L, plan, out_len, W, stream, save)
@@ -330,9 +345,7 @@ class _Runtime:
             a = native.TcBlockArgs()
             a.B, a.L, a.R, a.D, a.S, a.k = B, L, R, D, S, k
             a.d_z = zws.data_ptr()
-            if self.tc_precision not in ("tf32x3", "bf16x2"):
-                raise ValueError(f"tc_precision must be 'tf32x3' or 'bf16x2', not {self.tc_precision!r}")
-            a.fast_tf32 = 1 if self.fast_tf32 else (2 if self.tc_precision == "bf16x2" else 0)
+            a.fast_tf32 = 1 if self.fast_tf32 else (0 if self.tc_precision == "tf32x3" else 2)
             tc_key = "tc_layers_bf16" if a.fast_tf32 == 2 else "tc_layers"
         else:
             a = native.BlockArgs()
@@ -406,11 +419,11 @@ class _Runtime:
                                                 B, Cc, L, R, stream), "start")
             native.check(lib.wn_pair_from_frames(frames.data_ptr(), h0.data_ptr(), B, L, R, 0, stream), "pair from frames")
             del frames
-        tb_w, tb_b = W["tb"]
+        tb_w, tb_b, prec = W["tb"]
         a = native.TbBlockArgs()
-        a.B, a.L, a.n_layers = B, L, n_layers
+        a.B, a.L, a.n_layers, a.channels, a.precision = B, L, n_layers, R, prec
         a.d_skip, a.skip_start, a.d_w_all = skip.data_ptr(), plan.skip_start, tb_w.data_ptr()
-        a.d_fg_save = a.d_z_save = None
+        a.d_fg_save = None
         src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
         ev = getattr(self, "block_events", None)
         if ev is not None:
@@ -442,7 +455,8 @@ class _Runtime:
         self.launches_last_forward = (1 if index_input else 2) + n_layers + 2
         if save is not None:
             save.update(mode="tb", h_all=h_all, fg_all=fg_all, sk_frames=sk_frames, plan=plan, out_len=out_len, x=x,
-                        index_input=index_input, B=B, L=L)
+                        index_input=index_input, B=B, L=L, precision=prec)
+        self.last_precision = {native.PREC_BF16: "bf16", native.PREC_BF16_PAIRS: "bf16x2"}[prec]
         return logits
 
     def _backward_tb(self, saved, dlogits):
@@ -517,12 +531,14 @@ class _Runtime:
         zbuf = torch.empty(B, 2, D // 8, L, 8, **bf16)
         dh_a, dh_b = torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16)
         work = torch.empty(lib.wn_tb_wgrad_workspace_bytes() // 4, **f32)
-        wb_all = W["tb_bwd"]
+        wb_all, prec = W["tb_bwd"]
+        if prec != saved["precision"]:
+            raise RuntimeError("wavenet_b200: tc_precision changed between the forward and its backward")
         a = native.TbBwdArgs()
-        a.B, a.L, a.n_layers, a.ds_start = B, L, n_layers, ds_start
+        a.B, a.L, a.n_layers, a.ds_start, a.channels, a.precision = B, L, n_layers, ds_start, R, prec
         a.d_dskip, a.d_dfg, a.d_z, a.d_wb_all = dskip_pair.data_ptr(), dfg.data_ptr(), zbuf.data_ptr(), wb_all.data_ptr()
         g = native.TbWgradArgs()
-        g.B, g.L, g.ds_start = B, L, ds_start
+        g.B, g.L, g.ds_start, g.channels, g.precision = B, L, ds_start, R, prec
         g.d_dskip, g.d_dfg, g.d_z, g.d_work = dskip_pair.data_ptr(), dfg.data_ptr(), zbuf.data_ptr(), work.data_ptr()
         dh_out, gs_out = None, L
         self.last_bwd_mode = "tb"

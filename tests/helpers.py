@@ -38,12 +38,13 @@ def classify_stream(got_idx, ref_idx, ref_margins, tol=1e-4):
     return i, bool(ref_margins[i] < tol)
 
 
-def separate_head_relu_ties(params, spec, x, out_len, margin=2e-5, step=1e-4):
+def separate_head_relu_ties(params, spec, x, out_len, margin=2e-5, step=None):
     """Gradients are discontinuous where a head ReLU input is exactly zero: an fp32-class difference (3xTF32 tensor
     cores vs FFMA, or just another summation order) that flips the sign of a pre-activation of size 1e-7 switches one
     mask element and moves a weight gradient by percent.  The analogue of the argmax near-tie rule for the backward
     tests: nudge the last skip bias and the end_conv_1 bias (per channel, in float64 on the oracle) until no head ReLU
     input of this test case lies within `margin` of zero.  Returns a new fp32 parameter dict."""
+    step = 5 * margin if step is None else step
     p = {k: v.detach().clone().double() for k, v in params.items()}
     last = spec.layers * spec.blocks - 1
     taps = {}

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = native.lib()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.wn_version() == 1
+    assert lib.wn_version() == 2
     assert lib.wn_n1p(256) == 512 and lib.wn_n1p(16) == 128 and lib.wn_n2p(32 + 1024) == 1152
     # argument errors are reported through the return code + message, never by crashing
     assert lib.wn_block_fwd(None, None) == -1

@@ -49,14 +49,16 @@ for (B, L, d, in_start, out_start, gs_out, ds_start) in [(2, 420, 4, 6, 10, 60, 
     ds_pair, ds_q = to_pair(dskip)
     hin_pair, hin_q = to_pair(h_in)
     fg = torch.cat([f.view(B, L, CH // 4, 4).permute(0, 2, 1, 3), gg.view(B, L, CH // 4, 4).permute(0, 2, 1, 3)], 1).contiguous()
-    wb = torch.empty(lib.wn_tb_bwd_weight_bytes_per_layer(), device=dev, dtype=torch.uint8)
-    native.check(lib.wn_tb_pack_block_bwd_weights(wf.data_ptr(), wg.data_ptr(), wr.data_ptr(), ws.data_ptr(), wb.data_ptr(), st), "pack")
+    wb = torch.empty(lib.wn_tb_bwd_weight_bytes_per_layer(CH, 2), device=dev, dtype=torch.uint8)
+    ptrs = torch.tensor([[wf.data_ptr(), wg.data_ptr(), 0, 0, wr.data_ptr(), ws.data_ptr(), 0, 0]], dtype=torch.int64, device=dev)
+    native.check(lib.wn_tb_pack_all_bwd_weights(ptrs.data_ptr(), 1, CH, 2, wb.data_ptr(), st), "pack")
     dfg = torch.zeros(B, 2, 64, L, 8, device=dev, dtype=torch.bfloat16)
     zb = torch.zeros(B, 2, 32, L, 8, device=dev, dtype=torch.bfloat16)
     dh_in = torch.zeros(B, 2, 32, L, 8, device=dev, dtype=torch.bfloat16)
     a = native.TbBwdArgs()
     a.d_dh_out = dh_pair.data_ptr() if have_dh else None
     a.d_dskip, a.d_fg, a.d_dfg, a.d_z, a.d_dh_in, a.d_wb_all = ds_pair.data_ptr(), fg.data_ptr(), dfg.data_ptr(), zb.data_ptr(), dh_in.data_ptr(), wb.data_ptr()
+    a.channels, a.precision = CH, 2
     a.layer, a.n_layers, a.B, a.L, a.dilation, a.in_start, a.out_start = 0, 1, B, L, d, in_start, out_start
     a.gs_out, a.ds_start, a.gz, a.gs_in = gs_out, ds_start, gz, gs_in
     native.check(lib.wn_tb_block_bwd_data(ctypes.byref(a), st), "bwd data")
@@ -91,6 +93,7 @@ for (B, L, d, in_start, out_start, gs_out, ds_start) in [(2, 420, 4, 6, 10, 60, 
     w = native.TbWgradArgs()
     w.d_dskip, w.d_dh_out, w.d_dfg, w.d_z, w.d_h_in = ds_pair.data_ptr(), (dh_pair.data_ptr() if have_dh else None), dfg.data_ptr(), zb.data_ptr(), hin_pair.data_ptr()
     w.d_gws, w.d_gwr, w.d_gwf, w.d_gwg, w.d_work = gws.data_ptr(), gwr.data_ptr(), gwf.data_ptr(), gwg.data_ptr(), work.data_ptr()
+    w.channels, w.precision = CH, 2
     w.B, w.L, w.dilation, w.in_start, w.ds_start, w.id_start, w.gz = B, L, d, in_start, ds_start, id_start, gz
     native.check(lib.wn_tb_wgrad(ctypes.byref(w), st), "wgrad")
     torch.cuda.synchronize()
