@@ -168,6 +168,24 @@ typedef struct wn_tb_block_args {
 } wn_tb_block_args;
 int    wn_tb_block_fwd(const wn_tb_block_args* a, void* stream);
 
+/* ALL residual blocks of a forward in ONE persistent launch: the (layer, 256-frame item) list is dealt round-robin to the CTA
+ * pairs, an item waits for the previous layer's items that wrote the frames it reads (device-side flags), so there is no launch
+ * gap and no idle tail between layers.  h_ptrs: HOST array [n_layers + 1] of device pair tensors, layer i reads h_ptrs[i] and
+ * writes h_ptrs[i+1]; buffers may repeat with period >= 3 (never h_ptrs[i+1] == h_ptrs[i] or h_ptrs[i-1]).  d_bias_all:
+ * [n_layers][4*channels]; d_fg_all: optional (n_layers, B, 2*channels/4, L, 4); d_desc: n_layers * wn_tb_stack_desc_bytes()
+ * bytes of 128-byte aligned device scratch; d_flags: (wn_tb_stack_items(...) + n_layers) uint32 of device scratch.
+ * dilations / in_start / out_start: HOST arrays [n_layers]. */
+size_t    wn_tb_stack_desc_bytes(void);
+long long wn_tb_stack_items(int n_layers, int B, int L, const int* out_start);
+typedef struct wn_tb_stack_args {
+    const void* const* h_ptrs;
+    float* d_skip; const void* d_w_all; const float* d_bias_all; float* d_fg_all;
+    void* d_desc; unsigned* d_flags;
+    int n_layers, channels, precision, B, L, skip_start;
+    const int* dilations; const int* in_start; const int* out_start;
+} wn_tb_stack_args;
+int       wn_tb_stack_fwd(const wn_tb_stack_args* a, void* stream);
+
 /* Backward of the same block on the same layout (tcgen05 cta_group::2, bf16 pairs), replacing autograd's backward through
  * wavenet_model.py:142-165.  Frame-range arguments are those of wn_block_bwd_args.  Buffers: d_dh_out (B,2,32,L,8) pair or
  * NULL (last layer), d_dskip (B,2,32,L-ds_start,8) pair on its own frame axis, d_fg the forward's d_fg_save, outputs d_dfg

@@ -32,6 +32,7 @@
 #include "tc_ptx.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace wn {
 namespace tb {
@@ -72,21 +73,52 @@ struct Cfg {
     static_assert(NZ <= 8, "z_ready barriers");
 };
 
-struct BlockParams {
-    int B, L, t_begin, in_start, skip_start, skip_init, dil;
-    int tiles_per_seq, n_items;
-    int w_row0;                    // first 2 KB row of this layer in the packed weight array
+// One layer of a launch.  A single-layer launch carries it as a kernel parameter; the whole-stack launch reads an array of
+// them from global memory (the tensor map must then be 64-byte aligned there).
+struct alignas(128) LayerDesc {
+    CUtensorMap mapH;              // this layer's input pair tensor, origin = in_start
+    int t_begin, in_start, dil, skip_init;
+    int tiles_per_seq, n_items, item_base, w_row0;     // items of this layer are global items [item_base, item_base + n_items)
     const float* bias;             // [bf CH | bg CH | br CH | bs CH]
     const uint4* h_in;             // chunked pair (B, 2, CH/8, L, 8) bf16, viewed as 16-byte pieces
     uint4* h_out;
-    float4* skip;                  // chunked (B, CH/4, L - skip_start, 4) fp32
     float4* fg_save;               // optional chunked (B, 2CH/4, L, 4) fp32: tanh outputs in chunks [0,CH/4), sigmoid after
+    int war_layer;                 // >= 0: every item of that earlier layer must be complete before this layer writes h_out
+    int pad[7];
+};
+static_assert(sizeof(LayerDesc) % 128 == 0, "LayerDesc array elements must keep the tensor map aligned");
+
+struct BlockParams {
+    int B, L, skip_start;
+    int n_layers, total_items;
+    float4* skip;                  // chunked (B, CH/4, L - skip_start, 4) fp32
+    const LayerDesc* layers;       // whole-stack launch: [n_layers] in global memory
+    unsigned* item_done;           // whole-stack launch: [total_items] arrival counters (2 CTAs x 8 epilogue warps = 16 when complete)
+    unsigned* layer_done;          //                     [n_layers] completed items per layer
 };
 
-template <typename C>
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(p) < target) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) asm volatile("trap;");          // a dependency that never completes must not hang the GPU
+    }
+}
+
+// MULTI = false: one layer (`single`), items are independent.  MULTI = true: ALL layers of a forward in one persistent launch:
+// the global item list is layer-major and dealt round-robin to the clusters, an item waits (in its producer) for the items of the
+// previous layer that wrote the frames it reads, and announces itself when its epilogues have stored -- no launch gaps and no
+// idle tail between layers (a layer of cfg 3 is 456 items for 74 clusters: 6.16 rounds that cost 7 as separate launches).
+template <typename C, bool MULTI>
 __global__ void __launch_bounds__(NTHREADS, 1)
-block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW, const BlockParams p) {
+block_fused_kernel(const __grid_constant__ LayerDesc single, const __grid_constant__ CUtensorMap mapW, const BlockParams p) {
     constexpr int CH = C::CH;
+    auto LD = [&](int l) -> const LayerDesc& { return MULTI ? p.layers[l] : single; };
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     unsigned char* zbuf = base;
@@ -108,7 +140,6 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * EPI_WARPS); }
         for (int i = 0; i < 8; ++i) mbar_init(z_ready + i, 2 * EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
     }
     if (warp == 1) tmem2_alloc(tmem_slot, 512);
@@ -130,24 +161,45 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 ++it;
                 return ring + s * SLOT;
             };
-            for (int item = cluster_id; item < p.n_items; item += n_clusters) {
-                const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+            int l = 0;
+            for (int n = cluster_id; n < p.total_items; n += n_clusters) {
+                while (n >= LD(l).item_base + LD(l).n_items) ++l;
+                const LayerDesc& Ld = LD(l);
+                const int item = n - Ld.item_base, dil = Ld.dil, w_row0 = Ld.w_row0;
+                const int b = item / Ld.tiles_per_seq, t0 = Ld.t_begin + (item % Ld.tiles_per_seq) * PM;
                 const bool need_skip = t0 + PM > p.skip_start;
-                const int tc = t0 + (int)rank * BM - p.in_start;           // this CTA's first frame, relative to the map origin
+                const int tc = t0 + (int)rank * BM - Ld.in_start;          // this CTA's first frame, relative to the map origin
+                const CUtensorMap* mapH = &Ld.mapH;
+                if (MULTI && l > 0) {
+                    // the previous layer's items that produced frames [t0 - d, t0 - d + 255] and [t0, t0 + 255] of this sequence
+                    // (they also performed the previous accumulation into the skip frames this item updates)
+                    const LayerDesc& Lp = LD(l - 1);
+                    const int pt = Lp.t_begin, ptiles = Lp.tiles_per_seq;
+                    const unsigned* flags = p.item_done + Lp.item_base + b * ptiles;
+                    for (int rg = 0; rg < 2; ++rg) {
+                        int lo = t0 - (rg == 0 ? dil : 0), hi = lo + PM - 1;
+                        lo = lo < pt ? pt : lo;
+                        hi = hi >= p.L ? p.L - 1 : hi;
+                        if (lo > hi) continue;
+                        for (int tl = (lo - pt) / PM; tl <= (hi - pt) / PM; ++tl) wait_counter(flags + tl, 2 * EPI_WARPS);
+                    }
+                    if (Ld.war_layer >= 0) wait_counter(p.layer_done + Ld.war_layer, (unsigned)LD(Ld.war_layer).n_items);
+                    asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes of other SMs -> this thread's TMA reads
+                }
                 for (int j = 0; j < C::NT_A; ++j)
                     for (int sl = 0; sl < C::SLABS_A; ++sl) {
                         unsigned bar;
                         unsigned char* dst = acquire(bar);
                         const int tap = sl / (C::SLABS_A / 2);              // tap 0 reads h[t - d], tap 1 reads h[t]
-                        tma2_load_4d(dst, &mapH, 2 * (tc - (1 - tap) * p.dil), (sl % (C::SLABS_A / 2)) * C::KC, 0, b, bar);
+                        tma2_load_4d(dst, mapH, 2 * (tc - (1 - tap) * dil), (sl % (C::SLABS_A / 2)) * C::KC, 0, b, bar);
                         dst = acquire(bar);
-                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + ((j * C::SLABS_A + sl) * 2 + (int)rank) * 8, bar);
+                        tma2_load_2d(dst, &mapW, 0, w_row0 + ((j * C::SLABS_A + sl) * 2 + (int)rank) * 8, bar);
                     }
                 for (int j = 0; j < (need_skip ? C::NT_B : C::NT_R); ++j)
                     for (int s8 = 0; s8 < C::SLABS_B; ++s8) {
                         unsigned bar;
                         unsigned char* dst = acquire(bar);
-                        tma2_load_2d(dst, &mapW, 0, p.w_row0 + C::WROWS_A + ((j * C::SLABS_B + s8) * 2 + (int)rank) * 8, bar);
+                        tma2_load_2d(dst, &mapW, 0, w_row0 + C::WROWS_A + ((j * C::SLABS_B + s8) * 2 + (int)rank) * 8, bar);
                     }
             }
         }
@@ -173,8 +225,11 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 tc_fence_after();
                 return ab;
             };
-            for (int item = cluster_id; item < p.n_items; item += n_clusters, ++n_item) {
-                const int t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+            int l = 0;
+            for (int n = cluster_id; n < p.total_items; n += n_clusters, ++n_item) {
+                while (n >= LD(l).item_base + LD(l).n_items) ++l;
+                const int item = n - LD(l).item_base;
+                const int t0 = LD(l).t_begin + (item % LD(l).tiles_per_seq) * PM;
                 const bool need_skip = t0 + PM > p.skip_start;
                 // ---------------- pass A: n-tiles of [tanh | sigmoid] pre-activations, K = 2 taps x CH
                 for (int j = 0; j < C::NT_A; ++j) {
@@ -228,11 +283,18 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         const size_t plane_stride = (size_t)(CH / 8) * p.L;            // 16-byte pieces per plane of a pair tensor
         const int Tsk = p.L - p.skip_start;
         unsigned q = 0;
-        for (int item = cluster_id; item < p.n_items; item += n_clusters) {
-            const int b = item / p.tiles_per_seq, t0 = p.t_begin + (item % p.tiles_per_seq) * PM;
+        int l = 0;
+        for (int n = cluster_id; n < p.total_items; n += n_clusters) {
+            while (n >= LD(l).item_base + LD(l).n_items) ++l;
+            const LayerDesc& Ld = LD(l);
+            const int item = n - Ld.item_base;
+            const int b = item / Ld.tiles_per_seq, t0 = Ld.t_begin + (item % Ld.tiles_per_seq) * PM;
             const bool need_skip = t0 + PM > p.skip_start;
             const int t = t0 + (int)rank * BM + row;                   // this thread's frame
             const bool live = t < p.L;
+            const float* bias = Ld.bias;
+            float4* fg_save = Ld.fg_save;
+            const int skip_init = Ld.skip_init;
             // ---------------- gate: z = tanh(F + bf) * sigmoid(G + bg) -> shared-memory operand image (+ optional saves)
             for (int j = 0; j < C::NT_A; ++j) {
                 const unsigned ab = q & 1, u = q >> 1;
@@ -251,8 +313,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                         tmem_ld16(ta + 128 + c, g);
                         tmem_ld_wait();
                         const int ch = j * 128 + c;                    // first of the 16 dilation channels
-                        const float4* bf4 = reinterpret_cast<const float4*>(p.bias + ch);
-                        const float4* bg4 = reinterpret_cast<const float4*>(p.bias + CH + ch);
+                        const float4* bf4 = reinterpret_cast<const float4*>(bias + ch);
+                        const float4* bg4 = reinterpret_cast<const float4*>(bias + CH + ch);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float4 x = __ldg(bf4 + i), y = __ldg(bg4 + i);
@@ -261,8 +323,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                             g[4 * i] = sigmoid_fast(g[4 * i] + y.x); g[4 * i + 1] = sigmoid_fast(g[4 * i + 1] + y.y);
                             g[4 * i + 2] = sigmoid_fast(g[4 * i + 2] + y.z); g[4 * i + 3] = sigmoid_fast(g[4 * i + 3] + y.w);
                         }
-                        if (p.fg_save != nullptr && live) {
-                            float4* fs = p.fg_save + ((size_t)b * (2 * CH / 4) + ch / 4) * p.L + t;
+                        if (fg_save != nullptr && live) {
+                            float4* fs = fg_save + ((size_t)b * (2 * CH / 4) + ch / 4) * p.L + t;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 fs[(size_t)i * p.L] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -298,8 +360,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 const unsigned ta = lane_addr + ab * 256;
                 if (j < C::NT_R) {
                     const int n0 = j * 256;                                // first residual channel of this tile
-                    const uint4* hin = p.h_in + (size_t)b * 2 * plane_stride + t;
-                    uint4* hout = p.h_out + (size_t)b * 2 * plane_stride + t;
+                    const uint4* hin = Ld.h_in + (size_t)b * 2 * plane_stride + t;
+                    uint4* hout = Ld.h_out + (size_t)b * 2 * plane_stride + t;
                     uint4 nx[4];
                     auto load_res = [&](int c) {
                         nx[0] = nx[1] = nx[2] = nx[3] = make_uint4(0, 0, 0, 0);
@@ -316,7 +378,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                         const uint4 xh0 = nx[0], xh1 = nx[1], xl0 = nx[2], xl1 = nx[3];
                         if (c + 16 < grp * 128 + 128) load_res(c + 16);        // next chunk's loads fly under this chunk's math
                         tmem_ld_wait();
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + 2 * CH + n0 + c);
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + 2 * CH + n0 + c);
                         const unsigned xh[8] = {xh0.x, xh0.y, xh0.z, xh0.w, xh1.x, xh1.y, xh1.z, xh1.w};
                         const unsigned xl[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
                         unsigned hi[8], lo[8];
@@ -341,7 +403,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                     const bool on = live && t >= p.skip_start;
                     float4* sk = p.skip + (size_t)b * (CH / 4) * Tsk + (t - p.skip_start);
                     float4 nx[4];
-                    const bool rmw = on && !p.skip_init;
+                    const bool rmw = on && !skip_init;
                     auto load_skip = [&](int c) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -357,7 +419,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                         const float4 x[4] = {nx[0], nx[1], nx[2], nx[3]};
                         if (c + 16 < grp * 128 + 128) load_skip(c + 16);
                         tmem_ld_wait();
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + 3 * CH + n0 + c);
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + 3 * CH + n0 + c);
                         if (on) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -371,6 +433,15 @@ block_fused_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc_empty_addr[ab]);
+            }
+            if (MULTI) {
+                // this warp's stores of h_out / skip are done: publish (release at gpu scope); the 16th arrival completes the item
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned old = atomicAdd(p.item_done + n, 1u);
+                    if (old == 2 * EPI_WARPS - 1) { __threadfence(); atomicAdd(p.layer_done + l, 1u); }
+                }
             }
         }
     }
@@ -607,41 +678,58 @@ extern "C" int wn_tb_start_index_i64(const int64_t* d_idx, const float* d_w_t, c
     return start_pair(d_idx, false, d_w_t, d_b_p, d_h_pair, B, classes, L, R, d_err, stream);
 }
 
-template <typename C>
-static int launch_block(const wn_tb_block_args* a, cudaStream_t st) {
-    int dev = 0, sms = 0;
-    WN_CUDA(cudaGetDevice(&dev));
-    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CUtensorMap mH, mW;
-    if (int rc = tb::make_pair_map(&mH, a->d_h_in, a->B, a->L, C::CH, a->in_start, tb::BM, C::KC, C::PLANES)) return rc;
-    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)a->n_layers * C::WROWS_LAYER)) return rc;
-    tb::BlockParams p;
-    memset(&p, 0, sizeof(p));
-    p.B = a->B; p.L = a->L; p.t_begin = a->out_start; p.in_start = a->in_start; p.skip_start = a->skip_start;
-    p.skip_init = a->skip_init; p.dil = a->dilation;
-    p.tiles_per_seq = (a->L - a->out_start + tb::PM - 1) / tb::PM;
-    p.n_items = a->B * p.tiles_per_seq;
-    p.w_row0 = a->layer * C::WROWS_LAYER;
-    p.bias = a->d_bias4;
-    p.h_in = (const uint4*)a->d_h_in; p.h_out = (uint4*)a->d_h_out; p.skip = (float4*)a->d_skip;
-    p.fg_save = (float4*)a->d_fg_save;
-    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    int grid = 2 * p.n_items;
-    const int max_grid = (sms / 2) * 2;
-    if (grid > max_grid) grid = max_grid;
-    cudaLaunchConfig_t cfg = {};
+static int launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(tb::NTHREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel<C>, mH, mW, p));
+    return 0;
+}
+
+template <typename C>
+static int fill_layer(tb::LayerDesc& d, const void* h_in, void* h_out, const float* bias4, float* fg_save, int layer, int B, int L,
+                      int dilation, int in_start, int out_start, int skip_init, int item_base) {
+    memset(&d, 0, sizeof(d));
+    if (int rc = tb::make_pair_map(&d.mapH, h_in, B, L, C::CH, in_start, tb::BM, C::KC, C::PLANES)) return rc;
+    d.t_begin = out_start; d.in_start = in_start; d.dil = dilation; d.skip_init = skip_init;
+    d.tiles_per_seq = (L - out_start + tb::PM - 1) / tb::PM;
+    d.n_items = B * d.tiles_per_seq;
+    d.item_base = item_base;
+    d.w_row0 = layer * C::WROWS_LAYER;
+    d.bias = bias4; d.h_in = (const uint4*)h_in; d.h_out = (uint4*)h_out; d.fg_save = (float4*)fg_save;
+    d.war_layer = -1;
+    return 0;
+}
+
+template <typename C>
+static int launch_block(const wn_tb_block_args* a, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    tb::LayerDesc d;
+    CUtensorMap mW;
+    if (int rc = fill_layer<C>(d, a->d_h_in, a->d_h_out, a->d_bias4, a->d_fg_save, a->layer, a->B, a->L, a->dilation, a->in_start,
+                               a->out_start, a->skip_init, 0)) return rc;
+    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)a->n_layers * C::WROWS_LAYER)) return rc;
+    tb::BlockParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.L = a->L; p.skip_start = a->skip_start; p.n_layers = 1; p.total_items = d.n_items;
+    p.skip = (float4*)a->d_skip;
+    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    int grid = 2 * p.total_items;
+    const int max_grid = (sms / 2) * 2;
+    if (grid > max_grid) grid = max_grid;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, grid, C::SMEM_BYTES, st);
+    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel<C, false>, d, mW, p));
     WN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -660,4 +748,72 @@ extern "C" int wn_tb_block_fwd(const wn_tb_block_args* a, void* stream) {
     if (a->precision == WN_PREC_BF16_PAIRS) return launch_block<tb::Cfg<256, true>>(a, st);
     if (a->channels == 256) return launch_block<tb::Cfg<256, false>>(a, st);
     return launch_block<tb::Cfg<512, false>>(a, st);
+}
+
+// ---------------------------------------------------------------------------------------------- the whole stack in one launch
+extern "C" size_t wn_tb_stack_desc_bytes(void) { return sizeof(tb::LayerDesc); }
+extern "C" long long wn_tb_stack_items(int n_layers, int B, int L, const int* out_start) {
+    long long n = 0;
+    for (int i = 0; i < n_layers; ++i) n += (long long)B * ((L - out_start[i] + tb::PM - 1) / tb::PM);
+    return n;
+}
+
+template <typename C>
+static int launch_stack(const wn_tb_stack_args* a, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    WN_CUDA(cudaGetDevice(&dev));
+    WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int nl = a->n_layers;
+    std::vector<tb::LayerDesc> desc((size_t)nl);
+    int base = 0;
+    for (int i = 0; i < nl; ++i) {
+        float* fg = a->d_fg_all ? a->d_fg_all + (size_t)i * a->B * (2 * C::CH) * a->L : nullptr;
+        if (int rc = fill_layer<C>(desc[i], a->h_ptrs[i], const_cast<void*>(a->h_ptrs[i + 1]), a->d_bias_all + (size_t)i * 4 * C::CH, fg, i, a->B, a->L,
+                                   a->dilations[i], a->in_start[i], a->out_start[i], i == 0, base)) return rc;
+        WN_REQUIRE(a->in_start[i] >= 0 && a->out_start[i] >= a->in_start[i] && a->out_start[i] < a->L && a->skip_start >= a->out_start[i],
+                   WN_E_BADARG, "wn_tb_stack_fwd: bad frame ranges of layer %d", i);
+        WN_REQUIRE(a->h_ptrs[i] && a->h_ptrs[i + 1] && a->h_ptrs[i] != a->h_ptrs[i + 1] && (uintptr_t)a->h_ptrs[i + 1] % 16 == 0,
+                   WN_E_BADARG, "wn_tb_stack_fwd: layer %d needs distinct 16-byte aligned input and output buffers", i);
+        WN_REQUIRE(i == 0 || a->h_ptrs[i + 1] != a->h_ptrs[i - 1], WN_E_BADARG,
+                   "wn_tb_stack_fwd: layer %d may not write the buffer layer %d is reading (rotate three buffers)", i, i - 1);
+        // write-after-read: the latest earlier layer that READS the buffer this layer writes must be complete first
+        for (int j = i - 2; j >= 0; --j)
+            if (a->h_ptrs[j] == a->h_ptrs[i + 1]) { desc[i].war_layer = j; break; }
+        base += desc[i].n_items;
+    }
+    CUtensorMap mW;
+    if (int rc = tb::make_wrows_map(&mW, a->d_w_all, (long long)nl * C::WROWS_LAYER)) return rc;
+    WN_CUDA(cudaMemcpyAsync(a->d_desc, desc.data(), sizeof(tb::LayerDesc) * nl, cudaMemcpyHostToDevice, st));
+    WN_CUDA(cudaMemsetAsync(a->d_flags, 0, sizeof(unsigned) * ((size_t)base + nl), st));
+    tb::BlockParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.L = a->L; p.skip_start = a->skip_start; p.n_layers = nl; p.total_items = base;
+    p.skip = (float4*)a->d_skip;
+    p.layers = (const tb::LayerDesc*)a->d_desc;
+    p.item_done = a->d_flags; p.layer_done = a->d_flags + base;
+    WN_CUDA(cudaFuncSetAttribute(tb::block_fused_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    // every cluster must be resident (items wait for items of other clusters): one CTA per SM, at most sms/2 clusters
+    int grid = 2 * base;
+    const int max_grid = (sms / 2) * 2;
+    if (grid > max_grid) grid = max_grid;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, grid, C::SMEM_BYTES, st);
+    WN_CUDA(cudaLaunchKernelEx(&cfg, tb::block_fused_kernel<C, true>, desc[0], mW, p));
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_tb_stack_fwd(const wn_tb_stack_args* a, void* stream) {
+    WN_REQUIRE(a, WN_E_BADARG, "wn_tb_stack_fwd: null args");
+    WN_REQUIRE(a->h_ptrs && a->d_skip && a->d_w_all && a->d_bias_all && a->d_desc && a->d_flags && a->dilations && a->in_start && a->out_start,
+               WN_E_BADARG, "wn_tb_stack_fwd: null pointer");
+    WN_REQUIRE(wn_tb_precision_supported(a->channels, a->precision), WN_E_UNSUPP, "wn_tb_stack_fwd: %d channels with precision %d is not supported",
+               a->channels, a->precision);
+    WN_REQUIRE(a->B > 0 && a->L > 0 && a->n_layers > 0 && a->skip_start >= 0 && a->skip_start < a->L && (uintptr_t)a->d_desc % 128 == 0,
+               WN_E_BADARG, "wn_tb_stack_fwd: bad sizes (d_desc must be 128-byte aligned)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->precision == WN_PREC_BF16_PAIRS) return launch_stack<tb::Cfg<256, true>>(a, st);
+    if (a->channels == 256) return launch_stack<tb::Cfg<256, false>>(a, st);
+    return launch_stack<tb::Cfg<512, false>>(a, st);
 }

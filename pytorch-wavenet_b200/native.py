@@ -68,6 +68,14 @@ class TbBlockArgs(C.Structure):
                 ("d_fg_save", C.c_void_p)]
 
 
+class TbStackArgs(C.Structure):
+    _fields_ = [("h_ptrs", c_void_pp), ("d_skip", C.c_void_p), ("d_w_all", C.c_void_p), ("d_bias_all", C.c_void_p),
+                ("d_fg_all", C.c_void_p), ("d_desc", C.c_void_p), ("d_flags", C.c_void_p),
+                ("n_layers", C.c_int), ("channels", C.c_int), ("precision", C.c_int), ("B", C.c_int), ("L", C.c_int),
+                ("skip_start", C.c_int), ("dilations", C.POINTER(C.c_int)), ("in_start", C.POINTER(C.c_int)),
+                ("out_start", C.POINTER(C.c_int))]
+
+
 class TbBwdArgs(C.Structure):
     _fields_ = [("d_dh_out", C.c_void_p), ("d_dskip", C.c_void_p), ("d_fg", C.c_void_p),
                 ("d_dfg", C.c_void_p), ("d_z", C.c_void_p), ("d_dh_in", C.c_void_p), ("d_wb_all", C.c_void_p),
@@ -141,6 +149,9 @@ SIGNATURES = {
     "wn_frames_from_pair": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "wn_frames_from_chunks4": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "wn_tb_block_fwd": (C.c_int, [C.POINTER(TbBlockArgs), C.c_void_p]),
+    "wn_tb_stack_desc_bytes": (C.c_size_t, []),
+    "wn_tb_stack_items": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "wn_tb_stack_fwd": (C.c_int, [C.POINTER(TbStackArgs), C.c_void_p]),
     "wn_tb_bwd_weight_bytes_per_layer": (C.c_size_t, [C.c_int] * 2),
     "wn_tb_pack_all_bwd_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wn_tb_block_bwd_data": (C.c_int, [C.POINTER(TbBwdArgs), C.c_void_p]),

@@ -406,9 +406,10 @@ class _Runtime:
             key = ("tb", B, L)
             if key not in self.ws:
                 self.ws.clear()
-                self.ws[key] = (torch.empty(B, 2, R // 8, L, 8, **bf16), torch.empty(B, 2, R // 8, L, 8, **bf16),
+                self.ws[key] = (torch.empty(3, B, 2, R // 8, L, 8, **bf16),          # three rotating activation buffers
                                 torch.empty(B, S // 4, plan.t_final, 4, device=dev, dtype=torch.float32))
-            h0, h1, skip = self.ws[key]
+            hbuf, skip = self.ws[key]
+            h0, h1 = hbuf[0], hbuf[1]
         ws_t, bs_p = W["start"]
         if index_input:
             fn = lib.wn_tb_start_index_u8 if x.dtype == torch.uint8 else lib.wn_tb_start_index_i64
@@ -420,24 +421,48 @@ class _Runtime:
             native.check(lib.wn_pair_from_frames(frames.data_ptr(), h0.data_ptr(), B, L, R, 0, stream), "pair from frames")
             del frames
         tb_w, tb_b, prec = W["tb"]
-        a = native.TbBlockArgs()
-        a.B, a.L, a.n_layers, a.channels, a.precision = B, L, n_layers, R, prec
-        a.d_skip, a.skip_start, a.d_w_all = skip.data_ptr(), plan.skip_start, tb_w.data_ptr()
-        a.d_fg_save = None
-        src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
         ev = getattr(self, "block_events", None)
         if ev is not None:
             ev[0].record(torch.cuda.current_stream(dev))
-        for i, d in enumerate(dil):
-            a.d_h_in, a.d_h_out, a.layer, a.d_bias4 = src.data_ptr(), dst.data_ptr(), i, tb_b[i].data_ptr()
-            a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
-            if save is not None:
-                a.d_fg_save = fg_all[i].data_ptr()
-            native.check(lib.wn_tb_block_fwd(ctypes.byref(a), stream), f"tb block {i}")
-            if save is None:
-                src, dst = dst, src
-            elif i + 1 < n_layers:
-                src, dst = h_all[i + 1], h_all[i + 2]
+        if getattr(self, "stack_launch", True):
+            # all blocks in ONE persistent launch (wn_tb_stack_fwd): items of layer i+1 start as soon as the frames they read exist
+            hs = [h_all[i] for i in range(n_layers + 1)] if save is not None else [hbuf[i % 3] for i in range(n_layers + 1)]
+            ints = lambda v: (ctypes.c_int * n_layers)(*v)
+            outs = ints(plan.out_start)
+            n_items = lib.wn_tb_stack_items(n_layers, B, L, outs)
+            skey = ("tb_stack", n_layers, n_items)
+            if skey not in self.ws:
+                self.ws[skey] = (torch.empty(n_layers * lib.wn_tb_stack_desc_bytes() + 128, device=dev, dtype=torch.uint8),
+                                 torch.empty(n_items + n_layers, device=dev, dtype=torch.int32))
+            desc, flags = self.ws[skey]
+            sa = native.TbStackArgs()
+            hp = native.ptr_array(hs)
+            sa.h_ptrs = ctypes.cast(hp, native.c_void_pp)
+            sa.d_skip, sa.d_w_all, sa.d_bias_all = skip.data_ptr(), tb_w.data_ptr(), tb_b.data_ptr()
+            sa.d_fg_all = None if save is None else fg_all.data_ptr()
+            sa.d_desc = (desc.data_ptr() + 127) // 128 * 128
+            sa.d_flags = flags.data_ptr()
+            sa.n_layers, sa.channels, sa.precision, sa.B, sa.L, sa.skip_start = n_layers, R, prec, B, L, plan.skip_start
+            sa.dilations, sa.in_start, sa.out_start = ints(dil), ints(plan.in_start), outs
+            native.check(lib.wn_tb_stack_fwd(ctypes.byref(sa), stream), "tb stack")
+            n_block_launches = 1
+        else:
+            a = native.TbBlockArgs()
+            a.B, a.L, a.n_layers, a.channels, a.precision = B, L, n_layers, R, prec
+            a.d_skip, a.skip_start, a.d_w_all = skip.data_ptr(), plan.skip_start, tb_w.data_ptr()
+            a.d_fg_save = None
+            src, dst = (h0, h1) if save is None else (h_all[0], h_all[1])
+            for i, d in enumerate(dil):
+                a.d_h_in, a.d_h_out, a.layer, a.d_bias4 = src.data_ptr(), dst.data_ptr(), i, tb_b[i].data_ptr()
+                a.dilation, a.in_start, a.out_start, a.skip_init = d, plan.in_start[i], plan.out_start[i], int(i == 0)
+                if save is not None:
+                    a.d_fg_save = fg_all[i].data_ptr()
+                native.check(lib.wn_tb_block_fwd(ctypes.byref(a), stream), f"tb block {i}")
+                if save is None:
+                    src, dst = dst, src
+                elif i + 1 < n_layers:
+                    src, dst = h_all[i + 1], h_all[i + 2]
+            n_block_launches = n_layers
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(dev))
         # head: the last out_len frames of skip, back in the frames layout of wn_head_fwd
@@ -452,7 +477,8 @@ class _Runtime:
         hd.B, hd.L, hd.S, hd.E, hd.classes, hd.skip_start, hd.out_len, hd.mode = B, L, S, E, Cc, L - out_len, out_len, 0
         native.check(lib.wn_head_fwd(ctypes.byref(hd), stream), "head")
         self.last_block_mode = "tb"
-        self.launches_last_forward = (1 if index_input else 2) + n_layers + 2
+        self.launches_last_forward = (1 if index_input else 2) + n_block_launches + 2
+        self.last_block_launches = n_block_launches
         if save is not None:
             save.update(mode="tb", h_all=h_all, fg_all=fg_all, sk_frames=sk_frames, plan=plan, out_len=out_len, x=x,
                         index_input=index_input, B=B, L=L, precision=prec)

@@ -230,3 +230,32 @@ def test_512_channels_take_the_fused_path_by_default():
         rt.block_mode = "ffma"
         y0 = m.forward_indices(idx)
     assert rel_err(y.cpu().numpy(), y0.cpu().numpy()) < 3e-2
+
+
+def test_whole_stack_launch_equals_per_layer_launches():
+    """wn_tb_stack_fwd (all layers in one persistent launch, items chained by device-side flags) does the same arithmetic as
+    one wn_tb_block_fwd launch per layer: identical bits, for the no-grad forward (three rotating buffers) and for the
+    training step (saved activations, gradients), several items per layer and dilations larger than an item."""
+    import torch.nn.functional as F
+    import wavenet_model as wmod
+    kw = dict(layers=10, blocks=2, dilation_channels=256, residual_channels=256, skip_channels=256, end_channels=256,
+              classes=256, output_length=700, kernel_size=2, bias=True)
+    torch.manual_seed(8)
+    m = wmod.WaveNetModel(**kw).cuda()
+    rt = m._runtime()
+    idx = torch.randint(0, 256, (5, 3000), generator=torch.Generator().manual_seed(3)).cuda()
+    tgt = torch.randint(0, 256, (5 * 700,), generator=torch.Generator().manual_seed(4)).cuda()
+    outs, grads = {}, {}
+    for stack in (True, False):
+        rt.stack_launch = stack
+        with torch.no_grad():
+            for _ in range(3):                                  # repeated launches reuse (and must reset) the flag buffer
+                outs[stack] = m.forward_indices(idx).clone()
+        assert rt.last_block_launches == (1 if stack else 20)
+        m.zero_grad()
+        F.cross_entropy(m.forward_indices(idx), tgt).backward()
+        grads[stack] = {k: v.grad.clone() for k, v in m.named_parameters()}
+    rt.stack_launch = True
+    assert torch.equal(outs[True], outs[False])
+    for k in grads[True]:
+        assert torch.equal(grads[True][k], grads[False][k]), k
