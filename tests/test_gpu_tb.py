@@ -258,4 +258,7 @@ def test_whole_stack_launch_equals_per_layer_launches():
     rt.stack_launch = True
     assert torch.equal(outs[True], outs[False])
     for k in grads[True]:
-        assert torch.equal(grads[True][k], grads[False][k]), k
+        if k == "start_conv.weight":         # a scatter-add with float atomics: equal up to summation order
+            assert rel_err(grads[True][k].cpu().numpy(), grads[False][k].cpu().numpy()) < 1e-5
+        else:
+            assert torch.equal(grads[True][k], grads[False][k]), k
