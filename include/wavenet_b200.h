@@ -371,13 +371,18 @@ typedef struct wn_gen_run_args {
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
 /* Which sampler kernel runs (all implement the same schedule; call right after wn_gen_reset):
- *   0  auto: one stream -> the single-stream L2 kernel (lowest latency: the whole GPU works on one sample);
- *            several streams -> one cluster per stream (kernel 4); otherwise the generic kernel
+ *   0  auto: one stream -> the two-level exchange kernel 5 where it applies, else the single-stream L2 kernel 3 (lowest
+ *            latency: the whole GPU works on one sample); several streams -> one cluster per stream (kernel 4);
+ *            otherwise the generic kernel
  *   1  atomic grid barrier between stages (the simple reference kernel)
  *   2  generic flag-in-data exchange through L2 (any shape, any number of streams)
  *   3  single-stream L2 kernel with register-free cooperative polling (k = 2, power-of-two row split)
  *   4  cluster kernel: one 16-CTA thread-block cluster per stream, exchange through distributed shared memory
- * Kernels 2 and 3 sum in the same order; kernel 4 splits rows differently (rounding-level differences). */
+ *   5  single-stream two-level exchange: kernel 3's grid (64 CTAs x 4 rows) as 4 clusters of 16; values go to the 16 CTAs
+ *      of the producer's cluster through distributed shared memory and reach the other clusters through ONE L2 poller per
+ *      (cluster, producer) that forwards them by DSMEM (256-wide nets: R = D = S = E = classes = 256)
+ * Kernels 2, 3 and 5 sum in the same order (bit-identical results); kernel 4 splits rows differently (rounding-level
+ * differences). */
 int wn_gen_set_mode(wn_gen_handle* h, int mode);
 /* Synchronise the stream and report whether a launch aborted (a CTA waited > ~3 s for a tag): 0 = fine. */
 int wn_gen_check(wn_gen_handle* h, void* stream);

@@ -1693,6 +1693,779 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cluster(const GenPa
     cluster_sync_all();                                          // peers may still be storing into this CTA's shared memory
 }
 
+// ================================================================================================ two-level exchange kernel
+// Single stream, the grid of gen_kernel_fast (64 CTAs x 4 rows per stage vector) organised as 4 thread-block clusters of 16.
+// gen_kernel_fast pays ~1650 cycles per stage for an all-to-all in which 64 CTAs poll all 256 {value, tag} pairs through the
+// L2.  Here a value travels two hops instead:
+//   * inside a cluster the producer stores it straight into the shared memory of its 16 CTAs (distributed shared memory,
+//     ~250 cycles) -- and, once, to the L2 buffer the other kernels use (the ring history needs that anyway);
+//   * between clusters ONE CTA per destination cluster polls it in the L2 -- rank r of cluster c fetches the 32-byte sector
+//     of the four values that rank r of each other cluster produced (3 sectors per stage instead of 64) -- and forwards it
+//     to its 16 cluster peers through DSMEM.
+// Every consumer then spins on its OWN shared memory (no polling storm on hot L2 lines, no staging pass and one CTA barrier
+// per stage instead of two).  Same row ownership, K split, summation order and activations as gen_kernel_fast /
+// gen_kernel_ll: logits and indices are bit-identical to theirs.
+__device__ __forceinline__ void wait_local2(const uint2* p, unsigned tag, float& a, float& b) {        // two pairs, 16-byte aligned
+    const unsigned addr = smem_u32(p);
+    unsigned x, y, z, w;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr) : "memory");
+    if (y != tag || w != tag) {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        do {
+            asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr) : "memory");
+            if ((++spins & 1023u) == 0 && clock64() - t0 > GEN_TIMEOUT_CYCLES) asm volatile("trap;");
+        } while (y != tag || w != tag);
+    }
+    a = __uint_as_float(x);
+    b = __uint_as_float(z);
+}
+
+__global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_x2(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    // exchange buffers first: they must sit at the same offset in every CTA (mapa keeps the offset)
+    uint2* Xcur = reinterpret_cast<uint2*>(sm);                  // [2][R]  layer input h, by layer parity
+    uint2* Xz = Xcur + 2 * p.R;                                  // [2][D]  gated activation z, by layer parity
+    uint2* Xhead = Xz + 2 * p.D;                                 // [S + E + C] skip, y1, logits of the current evaluation
+    uint2* old_s = Xhead + (p.S + p.E + p.C);                    // [2][R] prefetched old taps
+    float* part = reinterpret_cast<float*>(old_s + 2 * p.R);     // [2][GEN_WARPS] partial sums, double buffered by stage parity
+    float* skacc = part + 2 * GEN_WARPS;                         // [nS]
+    float* logit_s = skacc + 4;                                  // [C]
+    double* cdf = reinterpret_cast<double*>(logit_s + ((p.C + 3) & ~3));      // [C]
+    float* wbuf = reinterpret_cast<float*>(cdf + p.C);                        // [n_wslots][wslot_floats]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    unsigned long long* emptyb = fullb + 4;
+    GenLayer* lay_s = reinterpret_cast<GenLayer*>(fullb + 8);
+    int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
+    int* misc = slot_s + p.n_layers;                             // [0] current index
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int rank = (int)cluster_rank(), cl = cta / CL, NCL = G / CL;
+    const int R = p.R, D = p.D, S = p.S, E = p.E, C = p.C, NL = p.n_layers;
+    const int K1 = 2 * R;
+    constexpr int NV = 4;                                        // values per CTA per stage vector (host checks D/G = R/G = ... = 4)
+    const int oV = cta * NV;                                     // first index this CTA owns in every stage vector
+    const int NSLOT = p.n_wslots;
+    // fixed warp -> (row, K-part) assignment per stage kind, as in gen_kernel_fast (same summation order)
+    const int HS1 = GEN_WARPS / (2 * NV), HS2 = GEN_WARPS / (2 * NV), HSA = GEN_WARPS / NV, HSB = GEN_WARPS / NV;
+    const int row1 = warp / HS1, g1 = ((warp - row1 * HS1) * (K1 / HS1) >> 2) + lane, n1 = (((K1 / HS1) >> 2) - lane + 31) / 32;
+    const int row2 = warp / HS2, g2 = ((warp - row2 * HS2) * (D / HS2) >> 2) + lane, n2 = (((D / HS2) >> 2) - lane + 31) / 32;
+    const int rowA = warp / HSA, gA = ((warp - rowA * HSA) * (S / HSA) >> 2) + lane, nA = (((S / HSA) >> 2) - lane + 31) / 32;
+    const int rowB = warp / HSB, gB = ((warp - rowB * HSB) * (E / HSB) >> 2) + lane, nB = (((E / HSB) >> 2) - lane + 31) / 32;
+
+    {   // zero the exchange buffers (tag 0 = nothing yet), copy the layer table
+        unsigned long long* z0 = reinterpret_cast<unsigned long long*>(Xcur);
+        const int n0 = 2 * R + 2 * D + S + E + C + 2 * R;
+        for (int i = tid; i < n0; i += GEN_NT + 32) z0[i] = 0ull;
+        const int* src = reinterpret_cast<const int*>(p.layers);
+        int* dst = reinterpret_cast<int*>(lay_s);
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        misc[0] = p.cur_idx[0];
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    for (int l = tid; l < NL; l += GEN_NT) {
+        const int len = lay_s[l].ring_len;
+        slot_s[l] = (p.t0 + len - 1) % len;
+    }
+    cluster_sync_all();                                          // nobody may store into a peer before it is zeroed
+    const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
+
+    // ---- producer warp: weight rows of this CTA for every stage, in order, through the TMA ring (as gen_kernel_fast)
+    if (warp == GEN_WARPS) {
+        if (lane == 0) {
+            unsigned q = 0;
+            for (int ev = 0; ev < p.n_evals; ++ev) {
+                const bool wh = (p.t0 + ev >= p.n_given - 1);
+                const int n_st = wh ? 2 * NL + 2 : 2 * NL;
+                for (int st = 0; st < n_st; ++st, ++q) {
+                    StageDesc d = stage_desc(p, st, true, NV, NV, NV, NV, NV);
+                    if (st < 2 * NL && (st & 1)) { d.n_first = NV; d.n = 2 * NV; }
+                    const int slot = (int)(q & smask);
+                    if (q >= (unsigned)NSLOT) {
+                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                            if (!done && ++spins > (1u << 30)) asm volatile("trap;");
+                        }
+                    }
+                    mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+                    float* dst = wbuf + (size_t)slot * p.wslot_floats;
+                    for (int i = 0; i < d.n; ++i)
+                        bulk_g2s(dst + (size_t)i * d.K, stage_row(p, lay_s, st, d, i, cta, G), d.K * 4, fullb + slot);
+                }
+            }
+        }
+        cluster_sync_all();                                      // matches the workers' final cluster barrier
+        return;
+    }
+    unsigned cons_q = 0;
+    auto stage_weights = [&](int row, int K) -> const float* {
+        const int slot = (int)(cons_q & smask);
+        mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
+        return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * K;
+    };
+    auto release_slot = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask));
+        ++cons_q;
+    };
+    auto prefetch_old = [&](int ln, int te, int slot_te) {
+        const GenLayer& Lp = lay_s[ln];
+        if (te >= Lp.dil && tid < R / 2) {
+            const int so = (slot_te + 1 == Lp.ring_len) ? 0 : slot_te + 1;
+            const uint2* src = p.ringLL + Lp.ring_off + (size_t)so * R + 2 * tid;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(old_s + (ln & 1) * R + 2 * tid);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // Second hop: warps 4 .. 4+NCL-2 each serve one OTHER cluster: fetch the sector (4 pairs) its rank-`rank` CTA published to
+    // the L2 vector `gvec` (tag gtag) and store it, re-tagged, into vector `xvec` of all 16 CTAs of this cluster.
+    auto forward = [&](const uint2* gvec, unsigned gtag, uint2* xvec, unsigned xtag) {
+        const int k = warp - 4;
+        if (k < 0 || k >= NCL - 1) return;
+        const int cp = (cl + 1 + k) % NCL;
+        const int idx = (cp * CL + rank) * NV + 2 * (lane >> 4);        // lanes 0-15: pairs 0,1; lanes 16-31: pairs 2,3
+        Pair2 q = ld_pair2(gvec + idx);
+        if (q.a.y != gtag || q.b.y != gtag) {
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            do {
+                q = ld_pair2(gvec + idx);
+                if ((++spins & 255u) == 0 && clock64() - t0 > GEN_TIMEOUT_CYCLES) asm volatile("trap;");
+            } while (q.a.y != gtag || q.b.y != gtag);
+        }
+        st_remote_pair(xvec + idx, (unsigned)(lane & 15), __uint_as_float(q.a.x), xtag);
+        st_remote_pair(xvec + idx + 1, (unsigned)(lane & 15), __uint_as_float(q.b.x), xtag);
+    };
+    {
+        const int len0 = lay_s[0].ring_len;
+        prefetch_old(0, p.t0, p.t0 % len0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    WORKER_SYNC();
+    unsigned stage_par = 0;
+    unsigned seq = (unsigned)p.t0 * (unsigned)(2 * NL + 4);      // exchange tag counter, unique per (evaluation, stage)
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;
+        const unsigned rtag = (unsigned)t + 1u;                  // tag of time t in the L2 buffers (ring history, exchange vectors)
+        const int par = t & 1;
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);
+        if (tid == 0) {
+            if (t < p.n_given) misc[0] = p.first[t];
+            else if (p.forced != nullptr) misc[0] = p.forced[t - p.n_given];
+        }
+        for (int l = tid; l < NL; l += GEN_NT) {
+            const int s1 = slot_s[l] + 1;
+            slot_s[l] = (s1 == lay_s[l].ring_len) ? 0 : s1;
+        }
+        if (tid < NV) skacc[tid] = 0.f;
+        WORKER_SYNC();
+        int idx = misc[0];
+        idx = idx < 0 ? 0 : (idx >= C ? C - 1 : idx);
+        const unsigned etag = seq + 1u;                          // tags of this evaluation: etag + 2l (h of layer l), etag + 2l + 1 (z)
+        seq += (unsigned)(2 * NL + 4);
+
+        // layer 0's input: the start-conv column, computed locally by every CTA; owners also enqueue it in the L2 ring
+        {
+            const GenLayer& L0 = lay_s[0];
+            for (int r = tid; r < R; r += GEN_NT) {
+                const float v = __ldg(p.start_w + (size_t)r * C + idx) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
+                reinterpret_cast<volatile unsigned long long*>(Xcur)[r] =
+                    ((unsigned long long)etag << 32) | (unsigned long long)__float_as_uint(v);
+                if (r >= oV && r < oV + NV) st_pair(p.ringLL + L0.ring_off + (size_t)slot_s[0] * R + r, v, rtag);
+            }
+        }
+
+        for (int l = 0; l < NL; ++l) {
+            const GenLayer& L = lay_s[l];
+            const int slot_t = slot_s[l];
+            const int slot_old = (slot_t + 1 == L.ring_len) ? 0 : slot_t + 1;
+            const bool have_old = (t >= L.dil);
+            const unsigned tag_old = (unsigned)(t - L.dil) + 1u, tag_cur = etag + 2u * (unsigned)l, tag_z = tag_cur + 1u;
+            const uint2* xc = Xcur + (l & 1) * R;
+            const uint2* os = old_s + (l & 1) * R;
+            uint2* zb = Xz + (l & 1) * D;
+            uint2* zl = p.zLL + (size_t)(par * NL + l) * D;
+            // ================= stage 1: filter/gate rows, K = 2R interleaved (old, cur) per channel
+            {
+                const float* w1 = stage_weights(row1, K1);
+                float acc = 0.f;
+                bool old_ok = true;
+                float cc[FAST_MAXI][2];
+#pragma unroll
+                for (int it = 0; it < FAST_MAXI; ++it)
+                    if (it < n1) wait_local2(xc + 2 * (g1 + it * 32), tag_cur, cc[it][0], cc[it][1]);
+#pragma unroll
+                for (int it = 0; it < FAST_MAXI; ++it)
+                    if (it < n1) {
+                        const int g4 = g1 + it * 32, r0 = 2 * g4;
+                        float o0 = 0.f, o1 = 0.f;
+                        if (have_old) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(os + r0);
+                            old_ok = old_ok && q.y == tag_old && q.w == tag_old;
+                            o0 = __uint_as_float(q.x);
+                            o1 = __uint_as_float(q.z);
+                        }
+                        const float4 w4 = reinterpret_cast<const float4*>(w1)[g4];
+                        acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, cc[it][0], acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, cc[it][1], acc);
+                    }
+                if (!__all_sync(0xffffffffu, old_ok)) {            // prefetched copy not there yet (rare): poll the ring itself
+                    acc = 0.f;
+                    for (int it = 0; it < n1; ++it) {
+                        const int g4 = g1 + it * 32, r0 = 2 * g4;
+                        float o0, o1;
+                        poll2(p.ringLL + L.ring_off + (size_t)slot_old * R + r0, tag_old, o0, o1, p.err, misc + 1);
+                        const float4 w4 = reinterpret_cast<const float4*>(w1)[g4];
+                        acc = fmaf(w4.x, o0, acc); acc = fmaf(w4.y, cc[it][0], acc); acc = fmaf(w4.z, o1, acc); acc = fmaf(w4.w, cc[it][1], acc);
+                    }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                release_slot();
+            }
+            WORKER_SYNC();
+            if (tid < CL * NV) {                                   // publish z: thread -> (value tid / 16, destination CTA tid % 16)
+                const int vi = tid >> 4, c = oV + vi;
+                const float* pf = part + stage_par * GEN_WARPS + (2 * vi) * HS1;
+                float f = pf[0], g = pf[HS1];
+                for (int q = 1; q < HS1; ++q) { f += pf[q]; g += pf[HS1 + q]; }
+                f += L.bf ? __ldg(L.bf + c) : 0.f;
+                g += L.bg ? __ldg(L.bg + c) : 0.f;
+                const float zv = tanh_(f) * sigmoid_(g);
+                st_remote_pair(zb + c, (unsigned)(tid & 15), zv, tag_z);
+                if ((tid & 15) == 0) st_pair(zl + c, zv, rtag);
+            }
+            forward(zl, rtag, zb, tag_z);
+            stage_par ^= 1;
+            // ================= stage 2: residual rows (first NV) and skip rows (next NV), K = D
+            if (l + 1 < NL) prefetch_old(l + 1, t, slot_s[l + 1]);
+            else if (ev + 1 < p.n_evals) prefetch_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
+            {
+                const bool active2 = (row2 < NV) ? (l + 1 < NL) : want_head;
+                const float* w2 = stage_weights(row2, D);
+                float acc = 0.f;
+                if (active2) {
+                    float zz[FAST_MAXI][4];
+#pragma unroll
+                    for (int it = 0; it < FAST_MAXI; ++it)
+                        if (it < n2) {
+                            wait_local2(zb + 4 * (g2 + it * 32), tag_z, zz[it][0], zz[it][1]);
+                            wait_local2(zb + 4 * (g2 + it * 32) + 2, tag_z, zz[it][2], zz[it][3]);
+                        }
+#pragma unroll
+                    for (int it = 0; it < FAST_MAXI; ++it)
+                        if (it < n2) {
+                            const float4 w4 = reinterpret_cast<const float4*>(w2)[g2 + it * 32];
+                            acc = fmaf(w4.x, zz[it][0], acc); acc = fmaf(w4.y, zz[it][1], acc); acc = fmaf(w4.z, zz[it][2], acc); acc = fmaf(w4.w, zz[it][3], acc);
+                        }
+                    acc = warp_sum(acc);
+                }
+                if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+                release_slot();
+                asm volatile("cp.async.wait_group 0;" ::: "memory");      // the old taps for the next stage 1 have landed
+            }
+            WORKER_SYNC();
+            if (tid < CL * NV) {
+                if (l + 1 < NL) {                                  // publish h' = Wr z + br + h
+                    const int vi = tid >> 4, row = oV + vi;
+                    const GenLayer& Ln = lay_s[l + 1];
+                    const float* ps = part + stage_par * GEN_WARPS + vi * HS2;
+                    float v = ps[0];
+                    for (int q = 1; q < HS2; ++q) v += ps[q];
+                    v += L.br ? __ldg(L.br + row) : 0.f;
+                    const float hv = v + wait_local(xc + row, tag_cur, misc + 1);
+                    st_remote_pair(Xcur + ((l + 1) & 1) * R + row, (unsigned)(tid & 15), hv, tag_cur + 2u);
+                    if ((tid & 15) == 0) st_pair(p.ringLL + Ln.ring_off + (size_t)slot_s[l + 1] * R + row, hv, rtag);
+                }
+            } else if (tid < CL * NV + NV && want_head) {          // skip rows accumulate locally
+                const int li = tid - CL * NV;
+                const float* ps = part + stage_par * GEN_WARPS + (NV + li) * HS2;
+                float v = ps[0];
+                for (int q = 1; q < HS2; ++q) v += ps[q];
+                v += L.bs ? __ldg(L.bs + oV + li) : 0.f;
+                skacc[li] = v + skacc[li];
+            }
+            if (l + 1 < NL) {
+                const GenLayer& Ln = lay_s[l + 1];
+                forward(p.ringLL + Ln.ring_off + (size_t)slot_s[l + 1] * R, rtag, Xcur + ((l + 1) & 1) * R, tag_cur + 2u);
+            }
+            stage_par ^= 1;
+        }
+        if (!want_head) continue;
+
+        // ================= head
+        const unsigned tag_s = etag + 2u * (unsigned)NL + 1u, tag_y = tag_s + 1u, tag_l = tag_s + 2u;
+        uint2* xs = Xhead, *xy = Xhead + S, *xl = Xhead + S + E;
+        uint2* skl = p.skipLL + (size_t)par * S;
+        uint2* yl = p.y1LL + (size_t)par * E;
+        uint2* lgl = p.logitLL + (size_t)par * C;
+        WORKER_SYNC();                                           // skacc complete
+        if (tid < CL * NV) {
+            const int vi = tid >> 4;
+            st_remote_pair(xs + oV + vi, (unsigned)(tid & 15), skacc[vi], tag_s);
+            if ((tid & 15) == 0) st_pair(skl + oV + vi, skacc[vi], rtag);
+        }
+        forward(skl, rtag, xs, tag_s);
+        {
+            const float* w = stage_weights(rowA, S);
+            float zz[FAST_MAXI][4];
+#pragma unroll
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nA) {
+                    wait_local2(xs + 4 * (gA + it * 32), tag_s, zz[it][0], zz[it][1]);
+                    wait_local2(xs + 4 * (gA + it * 32) + 2, tag_s, zz[it][2], zz[it][3]);
+                }
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nA) {
+                    const float4 w4 = reinterpret_cast<const float4*>(w)[gA + it * 32];
+                    acc = fmaf(w4.x, fmaxf(zz[it][0], 0.f), acc); acc = fmaf(w4.y, fmaxf(zz[it][1], 0.f), acc);
+                    acc = fmaf(w4.z, fmaxf(zz[it][2], 0.f), acc); acc = fmaf(w4.w, fmaxf(zz[it][3], 0.f), acc);
+                }
+            acc = warp_sum(acc);
+            if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            release_slot();
+        }
+        WORKER_SYNC();
+        if (tid < CL * NV) {
+            const int vi = tid >> 4, row = oV + vi;
+            const float* ps = part + stage_par * GEN_WARPS + vi * HSA;
+            float v = ps[0];
+            for (int q = 1; q < HSA; ++q) v += ps[q];
+            v = fmaxf(v + __ldg(p.e1b + row), 0.f);
+            st_remote_pair(xy + row, (unsigned)(tid & 15), v, tag_y);
+            if ((tid & 15) == 0) st_pair(yl + row, v, rtag);
+        }
+        forward(yl, rtag, xy, tag_y);
+        stage_par ^= 1;
+        {
+            const float* w = stage_weights(rowB, E);
+            float zz[FAST_MAXI][4];
+#pragma unroll
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nB) {
+                    wait_local2(xy + 4 * (gB + it * 32), tag_y, zz[it][0], zz[it][1]);
+                    wait_local2(xy + 4 * (gB + it * 32) + 2, tag_y, zz[it][2], zz[it][3]);
+                }
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < FAST_MAXI; ++it)
+                if (it < nB) {
+                    const float4 w4 = reinterpret_cast<const float4*>(w)[gB + it * 32];
+                    acc = fmaf(w4.x, zz[it][0], acc); acc = fmaf(w4.y, zz[it][1], acc); acc = fmaf(w4.z, zz[it][2], acc); acc = fmaf(w4.w, zz[it][3], acc);
+                }
+            acc = warp_sum(acc);
+            if (lane == 0) part[stage_par * GEN_WARPS + warp] = acc;
+            release_slot();
+        }
+        WORKER_SYNC();
+        if (tid < CL * NV) {
+            const int vi = tid >> 4, row = oV + vi;
+            const float* ps = part + stage_par * GEN_WARPS + vi * HSB;
+            float v = ps[0];
+            for (int q = 1; q < HSB; ++q) v += ps[q];
+            const float dc = (float)row - (float)C / 2.f;
+            v = (v + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+            st_remote_pair(xl + row, (unsigned)(tid & 15), v, tag_l);
+            if ((tid & 15) == 0) {
+                st_pair(lgl + row, v, rtag);
+                if (p.out_logits) p.out_logits[(size_t)samp * C + row] = v;
+            }
+        }
+        forward(lgl, rtag, xl, tag_l);
+        stage_par ^= 1;
+        for (int c = tid; c < C; c += GEN_NT) logit_s[c] = wait_local(xl + c, tag_l, misc + 1);
+        WORKER_SYNC();
+        if (warp == 0) {
+            const int choice = choose_sample(logit_s, cdf, C, lane, p.temperature, p.uniforms ? p.uniforms + samp : nullptr);
+            if (lane == 0) {
+                misc[0] = choice;
+                if (cta == 0) p.out_idx[samp] = choice;
+            }
+        }
+        // the top-of-evaluation barrier publishes misc[0]
+    }
+    WORKER_SYNC();
+    if (cta == 0 && tid == 0) p.cur_idx[0] = misc[0];
+    cluster_sync_all();                                          // peers may still be storing into this CTA's shared memory
+}
+
+// ================================================================================================ batched cluster kernel
+// Several streams per cluster: one 16-CTA cluster advances CL8_SB = 8 independent streams together, so the weights of a
+// stage are streamed into shared memory ONCE for 8 streams (gen_kernel_cluster streams all 79 MB per stream per step, and
+// only 9 clusters fit on the device, so 64 streams ran as 8 waves).  256-wide nets (R = D = S = E = classes = 256, k = 2):
+//   * CTA `rank` owns 16 channels of every stage vector; a stage's rows (32 conv rows, or 16 residual + 16 skip rows, or
+//     16 head rows) x 8 streams are spread one (row, stream) output per lane: lane = (row-in-warp, stream), each lane runs
+//     the whole K loop with the weight row broadcast from shared memory and its stream's activation vector next to it --
+//     no warp reduction, and stream s never sees another stream's data (a multi-stream run equals the single-stream runs
+//     bit for bit);
+//   * exchange: plain fp32 values, `st.async` into the [stream][channel] matrix of all 16 CTAs with the byte count credited
+//     to an mbarrier in the destination CTA; consumers wait on their own mbarrier (hardware sleep) -- no tags to test in the
+//     inner loop, half the distributed-shared-memory bytes of {value, tag} pairs;
+//   * history: the {value, tag} ring of the other kernels (same layout, so sessions, queue export and kernel switches keep
+//     working), written by the owning CTA, fetched one stage ahead into registers and validated by tag.
+constexpr int CL8_SB = 8;             // streams per cluster
+constexpr int CL8_PAD = 4;            // floats of padding per shared-memory matrix row: rows 4 words apart in the banks
+constexpr int CL8_W = 256;            // the width this kernel is specialised for
+
+__device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned dst) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(dst));
+    return r;
+}
+__device__ __forceinline__ void st_async_v2(unsigned raddr, float a, float b, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                 "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, float a, float b, float c, float d, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0, spins = 0;
+    const unsigned a = smem_u32(bar);
+    while (true) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) asm volatile("trap;");        // never hang the GPU
+    }
+}
+
+__global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams p) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int W = CL8_W, PW = CL8_W + CL8_PAD, SB = CL8_SB, NV = CL8_W / CL;     // NV = 16 channels per CTA per vector
+    // exchange matrices first: same offsets in every CTA (mapa keeps the offset)
+    float* Xcur = sm;                                   // [2][SB][PW] layer input h, by layer parity
+    float* Xz = Xcur + 2 * SB * PW;                     // [2][SB][PW] gated activation z, by layer parity
+    float* Xs = Xz + 2 * SB * PW;                       // [SB][PW] skip sum
+    float* Xy = Xs + SB * PW;                           // [SB][PW] end_conv_1 output
+    float* Xl = Xy + SB * PW;                           // [SB][PW] logits
+    float* Xold = Xl + SB * PW;                         // [SB][PW] history taps of the coming stage 1 (local)
+    float* logit_s = Xold + SB * PW;                    // [SB][W]  sampling scratch
+    double* cdf = reinterpret_cast<double*>(logit_s + SB * W);                // [SB][W]
+    float* wbuf = reinterpret_cast<float*>(cdf + SB * W);                     // [n_wslots][wslot_floats]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    unsigned long long* emptyb = fullb + 4;
+    unsigned long long* xbar = emptyb + 4;              // [0,1] h by layer parity, [2,3] z by layer parity, [4] skip, [5] y1, [6] logits
+    GenLayer* lay_s = reinterpret_cast<GenLayer*>(xbar + 8);
+    int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
+    int* idx_s = slot_s + p.n_layers;                   // [SB] current class index per stream
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster_rank(), cl = blockIdx.x / CL, NS = p.NS, NL = p.n_layers;
+    const int o0 = rank * NV;                           // first channel this CTA owns in every stage vector
+    const int NSLOT = p.n_wslots;
+    constexpr unsigned VEC_BYTES = SB * W * 4;          // bytes every CTA receives per exchanged vector
+
+    {
+        const int n0 = 8 * SB * PW;
+        for (int i = tid; i < n0; i += GEN_NT + 32) sm[i] = 0.f;
+        const int* src = reinterpret_cast<const int*>(p.layers);
+        int* dst = reinterpret_cast<int*>(lay_s);
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
+    }
+    if (tid < SB) idx_s[tid] = (cl * SB + tid < NS) ? p.cur_idx[cl * SB + tid] : 0;
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
+        for (int i = 0; i < 7; ++i) mbar_init(xbar + i, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < 7; ++i) mbar_expect_tx(xbar + i, VEC_BYTES);       // arm phase 0 of every exchange barrier
+    for (int l = tid; l < NL; l += GEN_NT) {
+        const int len = lay_s[l].ring_len;
+        slot_s[l] = (p.t0 + len - 1) % len;
+    }
+    cluster_sync_all();                                  // nobody may store into a peer before its barriers exist
+    const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
+
+    // ---- producer warp: weight rows of this CTA for every stage, in order, through the TMA ring (rows padded to PW / 2W+4)
+    if (warp == GEN_WARPS) {
+        if (lane == 0) {
+            unsigned q = 0;
+            for (int ev = 0; ev < p.n_evals; ++ev) {
+                const bool wh = (p.t0 + ev >= p.n_given - 1);
+                const int n_st = wh ? 2 * NL + 2 : 2 * NL;
+                for (int st = 0; st < n_st; ++st, ++q) {
+                    StageDesc d = stage_desc(p, st, true, NV, NV, NV, NV, NV);
+                    if (st < 2 * NL && (st & 1)) { d.n_first = NV; d.n = 2 * NV; }
+                    const int slot = (int)(q & smask);
+                    if (q >= (unsigned)NSLOT) {
+                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                            if (!done && ++spins > (1u << 30)) asm volatile("trap;");
+                        }
+                    }
+                    mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
+                    float* dst = wbuf + (size_t)slot * p.wslot_floats;
+                    for (int i = 0; i < d.n; ++i)
+                        bulk_g2s(dst + (size_t)i * (d.K + CL8_PAD), stage_row(p, lay_s, st, d, i, rank, CL), d.K * 4, fullb + slot);
+                }
+            }
+        }
+        cluster_sync_all();                              // matches the workers' final cluster barrier
+        return;
+    }
+    unsigned cons_q = 0;
+    auto stage_weights = [&](int row, int K) -> const float* {
+        const int slot = (int)(cons_q & smask);
+        mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
+        return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * (K + CL8_PAD);
+    };
+    auto release_slot = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_(emptyb + (cons_q & smask));
+        ++cons_q;
+    };
+    // exchange barrier i: wait for the phase all threads are at, then thread 0 arms the next phase (it has seen this one end)
+    unsigned xpar = 0;                                   // bit i = parity of the phase of xbar[i] to wait for next
+    auto xwait = [&](int i) {
+        mbar_wait_bounded(xbar + i, (xpar >> i) & 1u);
+        xpar ^= 1u << i;
+        if (tid == 0) mbar_expect_tx(xbar + i, VEC_BYTES);
+    };
+    // lane -> (row-in-warp rr, stream s) for the layer stages; destinations of this lane's remote stores: (lane>>3) + 4*it
+    const int rr = lane >> 3, s = lane & 7;
+    const int sg = cl * SB + s;                          // global stream of this lane
+    const bool s_on = sg < NS;
+    const unsigned sm_base = smem_u32(sm);
+    unsigned rdelta[4];                                  // shared::cluster address of CTA (lane>>3)+4*it minus the local address
+#pragma unroll
+    for (int it = 0; it < 4; ++it) rdelta[it] = mapa_u32(sm_base, (unsigned)((lane >> 3) + 4 * it)) - sm_base;
+    // this lane publishes a v2 / v4 piece of stream s to 4 destination CTAs per call (8 lanes x 4 CTAs per instruction)
+    auto publish2 = [&](float* mat, int ch, float a, float b, int bar_i) {
+        const unsigned la = smem_u32(mat + s * PW + ch), lb = smem_u32(xbar + bar_i);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st_async_v2(la + rdelta[it], a, b, lb + rdelta[it]);
+    };
+    auto publish4 = [&](float* mat, int ch, float a, float b, float c, float d, int bar_i) {
+        const unsigned la = smem_u32(mat + s * PW + ch), lb = smem_u32(xbar + bar_i);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st_async_v4(la + rdelta[it], a, b, c, d, lb + rdelta[it]);
+    };
+    // history taps: thread -> (stream = warp, channels 2*lane + 64*j + {0,1}), fetched into registers one stage ahead
+    const int hs_g = cl * SB + warp;                     // global stream whose taps this thread fetches
+    Pair2 hq[4];
+    const uint2* hsrc = nullptr;
+    unsigned htag = 0;
+    auto issue_old = [&](int ln, int te, int slot_te) {  // slot_te = ring slot of time te in layer ln
+        const GenLayer& Lp = lay_s[ln];
+        hsrc = nullptr;
+        if (te >= Lp.dil && hs_g < NS) {
+            const int so = (slot_te + 1 == Lp.ring_len) ? 0 : slot_te + 1;
+            hsrc = p.ringLL + Lp.ring_off + ((size_t)so * NS + hs_g) * W + 2 * lane;
+            htag = (unsigned)(te - Lp.dil) + 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hq[j] = ld_pair2(hsrc + 64 * j);
+        }
+    };
+    auto commit_old = [&]() {
+        float* dst = Xold + warp * PW + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.f, b = 0.f;
+            if (hsrc != nullptr) {
+                if (hq[j].a.y != htag || hq[j].b.y != htag) hq[j] = poll2_spin(hsrc + 64 * j, htag, p.err, idx_s + SB);
+                a = __uint_as_float(hq[j].a.x);
+                b = __uint_as_float(hq[j].b.x);
+            }
+            *reinterpret_cast<float2*>(dst + 64 * j) = make_float2(a, b);
+        }
+    };
+    issue_old(0, p.t0, p.t0 % lay_s[0].ring_len);
+    commit_old();
+    WORKER_SYNC();
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+        const int t = p.t0 + ev;
+        const unsigned rtag = (unsigned)t + 1u;          // ring tag of time t
+        const bool want_head = (t >= p.n_given - 1);
+        const int samp = t - (p.n_given - 1);
+        if (tid < SB && cl * SB + tid < NS) {
+            const int g = cl * SB + tid;
+            if (t < p.n_given) idx_s[tid] = p.first[(size_t)g * p.n_given + t];
+            else if (p.forced != nullptr) idx_s[tid] = p.forced[(size_t)g * p.n_samples + (t - p.n_given)];
+        }
+        for (int l = tid; l < NL; l += GEN_NT) {
+            const int s1 = slot_s[l] + 1;
+            slot_s[l] = (s1 == lay_s[l].ring_len) ? 0 : s1;
+        }
+        WORKER_SYNC();
+        // layer 0's input: the start-conv column of every stream (warp = stream), computed locally by every CTA; the
+        // owners of a channel also enqueue it in the ring
+        {
+            int idx = idx_s[warp];
+            idx = idx < 0 ? 0 : (idx >= W ? W - 1 : idx);
+            const GenLayer& L0 = lay_s[0];
+            uint2* ring0 = p.ringLL + L0.ring_off + ((size_t)slot_s[0] * NS + hs_g) * W;
+#pragma unroll
+            for (int j = 0; j < W / 32; ++j) {
+                const int r = lane + 32 * j;
+                const float v = __ldg(p.start_w + (size_t)r * W + idx) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
+                Xcur[warp * PW + r] = v;
+                if (r >= o0 && r < o0 + NV && hs_g < NS) st_pair(ring0 + r, v, rtag);
+            }
+        }
+        WORKER_SYNC();
+        float skr = 0.f;                                  // skip sum of (channel o0 + 4*(warp-4) + rr, stream s), warps 4-7
+
+        for (int l = 0; l < NL; ++l) {
+            const GenLayer& L = lay_s[l];
+            float* xc = Xcur + (l & 1) * SB * PW;
+            float* zb = Xz + (l & 1) * SB * PW;
+            // ================= stage 1: conv rows 4*warp + rr (filter / gate interleaved), K = 2W interleaved (old, cur)
+            if (l > 0) xwait(l & 1);
+            {
+                const float4* w4p = reinterpret_cast<const float4*>(stage_weights(4 * warp + rr, 2 * W));
+                const float4* o4p = reinterpret_cast<const float4*>(Xold + s * PW);
+                const float4* c4p = reinterpret_cast<const float4*>(xc + s * PW);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < W / 4; ++i) {
+                    const float4 wa = w4p[2 * i], wb = w4p[2 * i + 1], o = o4p[i], c = c4p[i];
+                    a0 = fmaf(wa.x, o.x, a0); a0 = fmaf(wa.y, c.x, a0);
+                    a1 = fmaf(wa.z, o.y, a1); a1 = fmaf(wa.w, c.y, a1);
+                    a2 = fmaf(wb.x, o.z, a2); a2 = fmaf(wb.y, c.z, a2);
+                    a3 = fmaf(wb.z, o.w, a3); a3 = fmaf(wb.w, c.w, a3);
+                }
+                float acc = (a0 + a1) + (a2 + a3);
+                release_slot();
+                const int ch = o0 + 2 * warp + (rr >> 1);
+                const float* bias = (rr & 1) ? L.bg : L.bf;
+                acc += bias ? __ldg(bias + ch) : 0.f;
+                const float gate = __shfl_down_sync(0xffffffffu, acc, 8);
+                const float zv = tanh_(acc) * sigmoid_(gate);           // meaningful in the filter lanes (rr = 0, 2)
+                const float z0 = __shfl_sync(0xffffffffu, zv, s), z1 = __shfl_sync(0xffffffffu, zv, 16 + s);
+                publish2(zb, o0 + 2 * warp, z0, z1, 2 + (l & 1));
+            }
+            // ================= stage 2: warps 0-3 residual rows, warps 4-7 skip rows (4*warp + rr of the slot); K = W
+            {
+                const bool more = (l + 1 < NL);
+                if (more) issue_old(l + 1, t, slot_s[l + 1]);
+                else if (ev + 1 < p.n_evals) issue_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
+                else hsrc = nullptr;
+                xwait(2 + (l & 1));
+                const bool is_res = warp < 4;
+                const bool active = is_res ? more : want_head;
+                const float4* w4p = reinterpret_cast<const float4*>(stage_weights(4 * warp + rr, W));
+                float acc = 0.f;
+                if (active) {
+                    const float4* z4p = reinterpret_cast<const float4*>(zb + s * PW);
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < W / 4; ++i) {
+                        const float4 w4 = w4p[i], z4 = z4p[i];
+                        a0 = fmaf(w4.x, z4.x, a0); a1 = fmaf(w4.y, z4.y, a1); a2 = fmaf(w4.z, z4.z, a2); a3 = fmaf(w4.w, z4.w, a3);
+                    }
+                    acc = (a0 + a1) + (a2 + a3);
+                }
+                release_slot();
+                if (is_res) {
+                    if (more) {
+                        const int row = o0 + 4 * warp + rr;
+                        const GenLayer& Ln = lay_s[l + 1];
+                        float v = acc + (L.br ? __ldg(L.br + row) : 0.f);
+                        v += xc[s * PW + row];
+                        if (s_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + sg) * W + row, v, rtag);
+                        const float q0 = __shfl_sync(0xffffffffu, v, s), q1 = __shfl_sync(0xffffffffu, v, 8 + s);
+                        const float q2 = __shfl_sync(0xffffffffu, v, 16 + s), q3 = __shfl_sync(0xffffffffu, v, 24 + s);
+                        publish4(Xcur + ((l + 1) & 1) * SB * PW, o0 + 4 * warp, q0, q1, q2, q3, (l + 1) & 1);
+                    }
+                } else if (want_head) {
+                    const float v = acc + (L.bs ? __ldg(L.bs + o0 + 4 * (warp - 4) + rr) : 0.f);
+                    skr = v + skr;
+                }
+                // every warp of the cluster is past its stage-1 reads of Xold (z of this layer is complete): refill it
+                commit_old();
+            }
+            WORKER_SYNC();                                // Xold of the next stage 1 is in place
+        }
+        if (!want_head) continue;
+
+        // ================= head: skip -> relu -> end_conv_1 -> relu -> end_conv_2, three exchanges
+        if (warp >= 4) {
+            const float q0 = __shfl_sync(0xffffffffu, skr, s), q1 = __shfl_sync(0xffffffffu, skr, 8 + s);
+            const float q2 = __shfl_sync(0xffffffffu, skr, 16 + s), q3 = __shfl_sync(0xffffffffu, skr, 24 + s);
+            publish4(Xs, o0 + 4 * (warp - 4), q0, q1, q2, q3, 4);
+        }
+        const int kh = lane >> 4, r2 = (lane >> 3) & 1;   // head stages: 2 rows per warp, K split in halves over the lane halves
+        xwait(4);
+        {
+            const float4* w4p = reinterpret_cast<const float4*>(stage_weights(2 * warp + r2, W)) + kh * (W / 8);
+            const float4* x4p = reinterpret_cast<const float4*>(Xs + s * PW) + kh * (W / 8);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < W / 8; ++i) {
+                const float4 w4 = w4p[i], x4 = x4p[i];
+                a0 = fmaf(w4.x, fmaxf(x4.x, 0.f), a0); a1 = fmaf(w4.y, fmaxf(x4.y, 0.f), a1);
+                a2 = fmaf(w4.z, fmaxf(x4.z, 0.f), a2); a3 = fmaf(w4.w, fmaxf(x4.w, 0.f), a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            release_slot();
+            const int row = o0 + 2 * warp + r2;
+            const float y = fmaxf(acc + __ldg(p.e1b + row), 0.f);
+            const float y0 = __shfl_sync(0xffffffffu, y, s), y1 = __shfl_sync(0xffffffffu, y, 8 + s);
+            publish2(Xy, o0 + 2 * warp, y0, y1, 5);
+        }
+        xwait(5);
+        {
+            const float4* w4p = reinterpret_cast<const float4*>(stage_weights(2 * warp + r2, W)) + kh * (W / 8);
+            const float4* x4p = reinterpret_cast<const float4*>(Xy + s * PW) + kh * (W / 8);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < W / 8; ++i) {
+                const float4 w4 = w4p[i], x4 = x4p[i];
+                a0 = fmaf(w4.x, x4.x, a0); a1 = fmaf(w4.y, x4.y, a1); a2 = fmaf(w4.z, x4.z, a2); a3 = fmaf(w4.w, x4.w, a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            release_slot();
+            const int row = o0 + 2 * warp + r2;
+            const float dc = (float)row - (float)W / 2.f;
+            const float v = (acc + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+            if (kh == 0 && s_on && p.out_logits) p.out_logits[((size_t)sg * p.n_samples + samp) * W + row] = v;
+            const float v0 = __shfl_sync(0xffffffffu, v, s), v1 = __shfl_sync(0xffffffffu, v, 8 + s);
+            publish2(Xl, o0 + 2 * warp, v0, v1, 6);
+        }
+        xwait(6);
+        // every CTA holds all logits of its 8 streams: warp = stream draws the next index (all CTAs agree)
+        if (hs_g < NS) {
+            float* lg = logit_s + warp * W;
+            for (int c = lane; c < W; c += 32) lg[c] = Xl[warp * PW + c];
+            __syncwarp();
+            const int choice = choose_sample(lg, cdf + warp * W, W, lane, p.temperature,
+                                             p.uniforms ? p.uniforms + (size_t)hs_g * p.n_samples + samp : nullptr);
+            if (lane == 0) {
+                idx_s[warp] = choice;
+                if (rank == 0) p.out_idx[(size_t)hs_g * p.n_samples + samp] = choice;
+            }
+        }
+        // the top-of-evaluation barrier publishes idx_s
+    }
+    WORKER_SYNC();
+    if (rank == 0 && tid < SB && cl * SB + tid < NS) p.cur_idx[cl * SB + tid] = idx_s[tid];
+    cluster_sync_all();                                  // peers may still be storing into this CTA's shared memory
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
     size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, total;
@@ -1743,7 +2516,7 @@ struct wn_gen_handle {
     size_t smem;
     bool tables_uploaded;
     int cur_t;
-    int mode;               // 0 = best flag-in-data kernel (default), 1 = grid-barrier kernel, 2 = generic flag-in-data kernel
+    int mode;               // 0 = best kernel for the shape (default), 1 = grid barrier, 2 = generic flag-in-data, 3-5 see wn_gen_set_mode
     size_t smem_ll;
     bool fast_ok;           // single stream, k=2, power-of-two grid, rows per stage divide 8: gen_kernel_fast applies
     size_t smem_fast;
@@ -1752,6 +2525,9 @@ struct wn_gen_handle {
     bool cluster_ok;        // k=2, 256-class nets whose rows split over 16 CTAs x 8 warps: gen_kernel_cluster applies
     size_t smem_cluster;
     int n_wslots_cluster, wslot_cluster;
+    bool x2_ok;             // fast_ok on a 64-CTA grid with 4 rows per stage vector per CTA: gen_kernel_x2 applies
+    size_t smem_x2;
+    int n_wslots_x2;
 };
 
 static int validate_shape(const wn_gen_shape* s) {
@@ -1931,6 +2707,23 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
             h->smem_fast = fbase + (size_t)fs * slot * 4;
             h->fast_ok = h->smem_fast <= (size_t)smem_optin;
         }
+        // ---- two-level exchange kernel: the fast kernel's grid as clusters of 16, exactly 4 values per CTA per stage vector
+        h->x2_ok = false;
+        if (ok && G % CL == 0 && G / CL >= 1 && G / CL <= 5 && s->D / G == 4 && s->R / G == 4 && s->S / G == 4 &&
+            s->E / G == 4 && s->classes / G == 4 && !getenv("WN_GEN_NOX2")) {
+            const size_t xbase = sizeof(uint2) * (size_t)(2 * s->R + 2 * s->D + s->S + s->E + s->classes + 2 * s->R) +
+                                 sizeof(float) * (size_t)(2 * GEN_WARPS + 4 + ((s->classes + 3) & ~3)) +
+                                 sizeof(double) * s->classes + 64 + sizeof(GenLayer) * (size_t)s->n_layers +
+                                 sizeof(int) * (size_t)(s->n_layers + 4);
+            int xs = 0;
+            if (xbase < (size_t)smem_optin) {
+                long long fit = ((long long)smem_optin - (long long)xbase) / (slot * 4);
+                xs = fit >= 4 ? 4 : (fit >= 2 ? 2 : 0);
+            }
+            h->n_wslots_x2 = xs;
+            h->smem_x2 = xbase + (size_t)xs * slot * 4;
+            h->x2_ok = xs >= 2 && h->smem_x2 <= (size_t)smem_optin;
+        }
     }
     // ---- cluster kernel eligibility: rows of every stage split evenly over 16 CTAs x 8 warps, <= 4 rows per warp
     {
@@ -2032,6 +2825,34 @@ static int launch_gen_cluster(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     return 0;
 }
 
+// 64 CTAs as 4 clusters of 16, all co-resident (the clusters exchange through the L2 while they run): launched with the
+// cluster dimension AND the cooperative attribute, which makes the driver refuse the launch unless every CTA fits at once.
+static int launch_gen_x2(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_x2));
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_x2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)h->grid);
+    cfg.blockDim = dim3(GEN_NT + 32);
+    cfg.dynamicSmemBytes = h->smem_x2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_x2, &cfg));
+    WN_REQUIRE(max_clusters >= h->grid / CL, WN_E_UNSUPP, "wn_gen_run: %d clusters of %d CTAs cannot be co-resident (%d fit)",
+               h->grid / CL, CL, max_clusters);
+    cfg.numAttrs = 2;
+    WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_x2, p));
+    return 0;
+}
+
 template <bool PF, bool TRACE>
 static int launch_gen_fast_t(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_CUDA(cudaFuncSetAttribute(gen_kernel_fast<PF, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fast));
@@ -2051,11 +2872,12 @@ static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
 
 extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_set_mode: null handle");
-    WN_REQUIRE(mode >= 0 && mode <= 4, WN_E_BADARG,
-               "wn_gen_set_mode: mode must be 0 (auto), 1 (grid barrier), 2 (generic flag exchange), 3 (single-stream L2 kernel) "
-               "or 4 (cluster / DSMEM kernel)");
+    WN_REQUIRE(mode >= 0 && mode <= 5, WN_E_BADARG,
+               "wn_gen_set_mode: mode must be 0 (auto), 1 (grid barrier), 2 (generic flag exchange), 3 (single-stream L2 kernel), "
+               "4 (cluster / DSMEM kernel) or 5 (single-stream two-level exchange kernel)");
     if (mode == 3) WN_REQUIRE(h->fast_ok, WN_E_UNSUPP, "wn_gen_set_mode: the single-stream L2 kernel does not apply to this shape");
     if (mode == 4) WN_REQUIRE(h->cluster_ok, WN_E_UNSUPP, "wn_gen_set_mode: the cluster kernel does not apply to this shape");
+    if (mode == 5) WN_REQUIRE(h->x2_ok, WN_E_UNSUPP, "wn_gen_set_mode: the two-level exchange kernel does not apply to this shape");
     WN_REQUIRE(h->cur_t == 0, WN_E_STATE, "wn_gen_set_mode: switch kernels only right after wn_gen_reset");
     if (mode != 1) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
     h->mode = mode;
@@ -2102,6 +2924,9 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
             p.n_wslots = h->n_wslots_cluster;
             p.wslot_floats = h->wslot_cluster;
             rc = launch_gen_cluster(h, p, st);
+        } else if ((h->mode == 0 || h->mode == 5) && h->x2_ok) {
+            p.n_wslots = h->n_wslots_x2;
+            rc = launch_gen_x2(h, p, st);
         } else if ((h->mode == 0 || h->mode == 3) && h->fast_ok) {
             p.n_wslots = h->n_wslots_fast;
             p.regA = h->xn_fast;                    // the fast kernel reads its input-vector pitch from regA
@@ -2139,7 +2964,7 @@ extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block,
     // the kernel wn_gen_run would pick in the handle's current mode (same selection as in wn_gen_run)
     const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
     const bool cluster = (auto_cluster || h->mode == 4) && h->cluster_ok;
-    const bool fast = !cluster && (h->mode == 0 || h->mode == 3) && h->fast_ok;
+    const bool fast = !cluster && (((h->mode == 0 || h->mode == 5) && h->x2_ok) || ((h->mode == 0 || h->mode == 3) && h->fast_ok));
     if (grid) *grid = cluster ? h->shape.n_streams * CL : h->grid;
     if (block) *block = (cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer warp
     if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
