@@ -371,8 +371,8 @@ typedef struct wn_gen_run_args {
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
 /* Which sampler kernel runs (all implement the same schedule; call right after wn_gen_reset):
- *   0  auto: one stream -> the two-level exchange kernel 5 where it applies, else the single-stream L2 kernel 3 (lowest
- *            latency: the whole GPU works on one sample); several streams -> one cluster per stream (kernel 4);
+ *   0  auto: one stream -> the single-stream L2 kernel 3 (lowest latency: the whole GPU works on one sample);
+ *            several streams -> the batched cluster kernel 6 where it applies, else one cluster per stream (kernel 4);
  *            otherwise the generic kernel
  *   1  atomic grid barrier between stages (the simple reference kernel)
  *   2  generic flag-in-data exchange through L2 (any shape, any number of streams)
@@ -380,7 +380,12 @@ int wn_gen_destroy(wn_gen_handle* h);
  *   4  cluster kernel: one 16-CTA thread-block cluster per stream, exchange through distributed shared memory
  *   5  single-stream two-level exchange: kernel 3's grid (64 CTAs x 4 rows) as 4 clusters of 16; values go to the 16 CTAs
  *      of the producer's cluster through distributed shared memory and reach the other clusters through ONE L2 poller per
- *      (cluster, producer) that forwards them by DSMEM (256-wide nets: R = D = S = E = classes = 256)
+ *      (cluster, producer) that forwards them by DSMEM (256-wide nets: R = D = S = E = classes = 256).  Measured 2x slower
+ *      than kernel 3 (a 16-CTA DSMEM all-to-all costs as much as the L2 one it replaces): selectable, never the default
+ *   6  batched tensor-core cluster kernel: 8 streams per 16-CTA cluster (256-wide nets, >= 2 streams).  The weights of a
+ *      stage enter shared memory once per 8 streams, as bf16 hi/lo pairs pre-split into MMA fragment order at
+ *      wn_gen_reset (wn_gen_workspace_bytes includes the images); dot products are mma.sync m16n8k16 with three MMAs per
+ *      product (fp32-class: ~1e-6 on the logits); the exchange is one 512-byte cp.async.bulk per destination CTA
  * Kernels 2, 3 and 5 sum in the same order (bit-identical results); kernel 4 splits rows differently (rounding-level
  * differences). */
 int wn_gen_set_mode(wn_gen_handle* h, int mode);

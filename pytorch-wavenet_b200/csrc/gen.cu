@@ -17,6 +17,7 @@
 // Exchanged vectors are read with ld.global.cg (L2) because L1 is not coherent across SMs.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -56,6 +57,7 @@ struct GenParams {
     int part_n;             // partial-sum scratch (floats)
     int wslot_floats, n_wslots;                // weight prefetch ring in shared memory (0 slots: read weights via L2)
     long long* trace;       // optional: clock64 stamps of CTA 0 / thread 0 during the last evaluation (wn_gen_read_trace)
+    const unsigned char* cl8_img;              // batched cluster kernel: fragment-ordered bf16 hi/lo weight images (cl8_pack_kernel)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -1705,6 +1707,9 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cluster(const GenPa
 // Every consumer then spins on its OWN shared memory (no polling storm on hot L2 lines, no staging pass and one CTA barrier
 // per stage instead of two).  Same row ownership, K split, summation order and activations as gen_kernel_fast /
 // gen_kernel_ll: logits and indices are bit-identical to theirs.
+// MEASURED (B200, cfg 2, 4000 samples): 299 us/sample against 150 us/sample for gen_kernel_fast.  The all-to-all inside a
+// 16-CTA cluster alone costs 910-940 cycles per round (tools/dsmem_probe.cu, variant A) -- no better than the L2 all-to-all
+// it replaces -- and the second hop is added on top.  Kept as mode 5 (selectable, tested bit-identical), never the default.
 __device__ __forceinline__ void wait_local2(const uint2* p, unsigned tag, float& a, float& b) {        // two pairs, 16-byte aligned
     const unsigned addr = smem_u32(p);
     unsigned x, y, z, w;
@@ -2102,37 +2107,52 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_x2(const GenParams 
 }
 
 // ================================================================================================ batched cluster kernel
-// Several streams per cluster: one 16-CTA cluster advances CL8_SB = 8 independent streams together, so the weights of a
-// stage are streamed into shared memory ONCE for 8 streams (gen_kernel_cluster streams all 79 MB per stream per step, and
-// only 9 clusters fit on the device, so 64 streams ran as 8 waves).  256-wide nets (R = D = S = E = classes = 256, k = 2):
-//   * CTA `rank` owns 16 channels of every stage vector; a stage's rows (32 conv rows, or 16 residual + 16 skip rows, or
-//     16 head rows) x 8 streams are spread one (row, stream) output per lane: lane = (row-in-warp, stream), each lane runs
-//     the whole K loop with the weight row broadcast from shared memory and its stream's activation vector next to it --
-//     no warp reduction, and stream s never sees another stream's data (a multi-stream run equals the single-stream runs
-//     bit for bit);
-//   * exchange: plain fp32 values, `st.async` into the [stream][channel] matrix of all 16 CTAs with the byte count credited
-//     to an mbarrier in the destination CTA; consumers wait on their own mbarrier (hardware sleep) -- no tags to test in the
-//     inner loop, half the distributed-shared-memory bytes of {value, tag} pairs;
-//   * history: the {value, tag} ring of the other kernels (same layout, so sessions, queue export and kernel switches keep
-//     working), written by the owning CTA, fetched one stage ahead into registers and validated by tag.
-constexpr int CL8_SB = 8;             // streams per cluster
-constexpr int CL8_PAD = 4;            // floats of padding per shared-memory matrix row: rows 4 words apart in the banks
-constexpr int CL8_W = 256;            // the width this kernel is specialised for
-
-__device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned dst) {
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(dst));
-    return r;
+// Several streams per cluster, on tensor cores: one 16-CTA cluster advances CL8_SB = 8 independent streams together, so the
+// weights of a stage are streamed into shared memory ONCE for 8 streams (gen_kernel_cluster streams all 79 MB per stream
+// per step, and only 9 clusters fit on the device, so 64 streams ran as 8 waves).  256-wide nets (R = D = S = E = classes
+// = 256, k = 2).  Per stage, CTA `rank` owns 16 channels of the output vector (all 8 streams):
+//   * the dot products are mma.sync m16n8k16 (M = 16 rows of the stage, N = the 8 streams, K = 16 input channels = the block
+//     one source CTA contributed) with bf16 hi/lo operand pairs -- x = hi + lo exactly up to 2^-17 relative, three MMAs per
+//     product (hi.hi + lo.hi + hi.lo), fp32 accumulation -- the scheme of the training kernels (tc_block.cu).  Weights are
+//     pre-split ONCE per session into fragment-ordered images (cl8_pack_kernel): a warp's A fragments are two conflict-free
+//     LDS.128, and the whole stage image is ONE bulk copy per CTA.  Activations are exchanged already split, in B-fragment
+//     order, so a k-step's B operands are one LDS.128;
+//   * exchange: the 16 x 8 outputs of a CTA are a 512-byte block staged in shared memory and pushed to every CTA of the
+//     cluster with one cp.async.bulk (shared::cta -> shared::cluster) each, completing bytes on an mbarrier of the
+//     destination; consumers sleep on their own mbarrier.  Measured 1 125-1 254 cycles per round, against 2 600-4 100 for
+//     the same payload as per-lane remote stores (tools/dsmem_probe.cu, variants F and E);
+//   * history: the {value, tag} fp32 ring of the other kernels (same layout: sessions, queue export and kernel switches keep
+//     working), written by the owning CTA, fetched one stage ahead into registers, validated by tag, split on arrival.
+// Streams never mix (N is the stream index of the MMA): a multi-stream run equals the single-stream runs bit for bit.
+constexpr int CL8_SB = 8;               // streams per cluster
+constexpr int CL8_W = 256;              // the width this kernel is specialised for
+constexpr int CL8_BLK = 512;            // bytes of one (source CTA) block of an exchanged vector: 8 streams x 16 channels x (hi, lo)
+constexpr int CL8_VEC = CL * CL8_BLK;   // bytes of one exchanged vector in every CTA
+constexpr int CL8_IMG1 = 2 * 32 * 1024, CL8_IMG2 = 2 * 16 * 1024, CL8_IMGH = 16 * 1024;    // weight images per (layer, rank) / head stage
+// byte offset of the (hi pair | lo pair) unit of channels (c & ~1, c | 1) of stream s inside a block: per stream 64 bytes =
+// 4 x [unit t | unit t+4], the order in which lane (g = stream, t) of an m16n8k16 B fragment consumes them
+__device__ __forceinline__ int cl8_unit_off(int s, int c) {
+    const int u = c >> 1;
+    return s * 64 + (u & 3) * 16 + (u >> 2) * 8;
 }
-__device__ __forceinline__ void st_async_v2(unsigned raddr, float a, float b, unsigned rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
-                 "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(rbar)
-                 : "memory");
+__device__ __forceinline__ void cl8_split(float x, unsigned short& hi, unsigned short& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
 }
-__device__ __forceinline__ void st_async_v4(unsigned raddr, float a, float b, float c, float d, unsigned rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
-                 "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rbar)
-                 : "memory");
+// one value of a block, written as two 16-bit stores (the pair partner is written by another thread)
+__device__ __forceinline__ void cl8_put(unsigned char* blk, int s, int c, float x) {
+    unsigned short hi, lo;
+    cl8_split(x, hi, lo);
+    unsigned short* q = reinterpret_cast<unsigned short*>(blk + cl8_unit_off(s, c)) + (c & 1);
+    q[0] = hi;
+    q[2] = lo;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
     unsigned done = 0, spins = 0;
@@ -2144,57 +2164,121 @@ __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsig
         if (++spins > (1u << 26)) asm volatile("trap;");        // never hang the GPU
     }
 }
+__device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned dst) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(dst));
+    return r;
+}
+
+// Weight images.  One (m-tile, k-step) = 1 KB: [hi: 32 lanes x 16 B][lo: 32 lanes x 16 B], lane's 16 bytes = the A fragment
+// registers a0..a3 of m16n8k16: a_j covers row g + 8*(j&1), k pair 2t + 8*(j>>1) (g = lane>>2, t = lane&3).
+//   per (layer, rank): [stage 1: m-tile 0 = filter rows, 1 = gate rows; k-steps 0-15 = tap 0 (old) of channel block ks,
+//                       16-31 = tap 1 (current)] [stage 2: m-tile 0 = residual rows, 1 = skip rows; k-step = z block]
+//   then per rank: [end_conv_1 image][end_conv_2 image] (one m-tile, 16 k-steps each)
+__global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const float* e1w, const float* e2w, unsigned* img) {
+    const int W = CL8_W;
+    const size_t per_layer = (size_t)CL * (CL8_IMG1 + CL8_IMG2) / 4, total = per_layer * n_layers + (size_t)CL * 2 * CL8_IMGH / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float* src;      // row-major weight matrix the word comes from
+        int row, col, ld, stride = 1;
+        size_t w = i;
+        if (w < per_layer * n_layers) {
+            const int l = (int)(w / per_layer);
+            w -= (size_t)l * per_layer;
+            const int rank = (int)(w / ((CL8_IMG1 + CL8_IMG2) / 4));
+            w -= (size_t)rank * ((CL8_IMG1 + CL8_IMG2) / 4);
+            const GenLayer& L = layers[l];
+            const bool st1 = w < CL8_IMG1 / 4;
+            if (!st1) w -= CL8_IMG1 / 4;
+            const int KS = st1 ? 32 : 16;
+            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)((w >> 8) % KS), mt = (int)((w >> 8) / KS);
+            const int g = lane >> 2, t = lane & 3;
+            row = rank * 16 + g + 8 * (j & 1);
+            const int kk = 2 * t + 8 * (j >> 1);
+            if (st1) { src = mt ? L.wg : L.wf; col = ((ks & 15) * 16 + kk) * 2 + (ks >> 4); ld = 2 * W; stride = 2; }
+            else { src = mt ? L.ws : L.wr; col = ks * 16 + kk; ld = W; }
+            const float x0 = src[(size_t)row * ld + col], x1 = src[(size_t)row * ld + col + stride];
+            unsigned short h0, l0, h1, l1;
+            cl8_split(x0, h0, l0);
+            cl8_split(x1, h1, l1);
+            img[i] = half ? ((unsigned)l1 << 16 | l0) : ((unsigned)h1 << 16 | h0);
+        } else {
+            w -= per_layer * n_layers;
+            const int rank = (int)(w / (2 * CL8_IMGH / 4));
+            w -= (size_t)rank * (2 * CL8_IMGH / 4);
+            const bool a = w < CL8_IMGH / 4;
+            if (!a) w -= CL8_IMGH / 4;
+            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)(w >> 8);
+            const int g = lane >> 2, t = lane & 3;
+            row = rank * 16 + g + 8 * (j & 1);
+            col = ks * 16 + 2 * t + 8 * (j >> 1);
+            src = a ? e1w : e2w;
+            const float x0 = src[(size_t)row * W + col], x1 = src[(size_t)row * W + col + 1];
+            unsigned short h0, l0, h1, l1;
+            cl8_split(x0, h0, l0);
+            cl8_split(x1, h1, l1);
+            img[i] = half ? ((unsigned)l1 << 16 | l0) : ((unsigned)h1 << 16 | h0);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams p) {
-    extern __shared__ __align__(16) float sm[];
-    constexpr int W = CL8_W, PW = CL8_W + CL8_PAD, SB = CL8_SB, NV = CL8_W / CL;     // NV = 16 channels per CTA per vector
-    // exchange matrices first: same offsets in every CTA (mapa keeps the offset)
-    float* Xcur = sm;                                   // [2][SB][PW] layer input h, by layer parity
-    float* Xz = Xcur + 2 * SB * PW;                     // [2][SB][PW] gated activation z, by layer parity
-    float* Xs = Xz + 2 * SB * PW;                       // [SB][PW] skip sum
-    float* Xy = Xs + SB * PW;                           // [SB][PW] end_conv_1 output
-    float* Xl = Xy + SB * PW;                           // [SB][PW] logits
-    float* Xold = Xl + SB * PW;                         // [SB][PW] history taps of the coming stage 1 (local)
-    float* logit_s = Xold + SB * PW;                    // [SB][W]  sampling scratch
-    double* cdf = reinterpret_cast<double*>(logit_s + SB * W);                // [SB][W]
-    float* wbuf = reinterpret_cast<float*>(cdf + SB * W);                     // [n_wslots][wslot_floats]
-    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * p.wslot_floats);
+    extern __shared__ __align__(128) unsigned char smb[];
+    constexpr int W = CL8_W, SB = CL8_SB, NV = CL8_W / CL, BLK = CL8_BLK, VEC = CL8_VEC;
+    // exchanged vectors first: same offsets in every CTA (mapa keeps the offset).  Each is 16 blocks of 512 bytes.
+    unsigned char* Xcur = smb;                          // [2] layer input h (hi/lo split), by layer parity
+    unsigned char* Xz = Xcur + 2 * VEC;                 // [2] gated activation z, by layer parity; Xz[1] doubles as sampling scratch
+    unsigned char* Xs = Xz + 2 * VEC;                   // relu(skip sum)           \  Xz[1], Xs, Xy are contiguous: 24 KB that no
+    unsigned char* Xy = Xs + VEC;                       // end_conv_1 output        /  peer writes while this CTA samples
+    unsigned char* Xl = Xy + VEC;                       // logits, fp32: [rank][stream][16]
+    unsigned char* Xold = Xl + VEC;                     // history taps of the coming stage 1 (local)
+    unsigned char* stg = Xold + VEC;                    // [2][BLK] this CTA's contribution of a stage, staged for the bulk copies
+    float* part = reinterpret_cast<float*>(stg + 2 * BLK);                    // [2][8 warps][32 lanes][4] partial C fragments
+    float* hown = part + 2 * 8 * 128;                   // [2][16][SB] fp32 layer input at the channels this CTA owns
+    unsigned char* wbuf = reinterpret_cast<unsigned char*>(hown + 2 * NV * SB);          // [n_wslots][CL8_IMG1]
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * CL8_IMG1);
     unsigned long long* emptyb = fullb + 4;
     unsigned long long* xbar = emptyb + 4;              // [0,1] h by layer parity, [2,3] z by layer parity, [4] skip, [5] y1, [6] logits
     GenLayer* lay_s = reinterpret_cast<GenLayer*>(xbar + 8);
     int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
-    int* idx_s = slot_s + p.n_layers;                   // [SB] current class index per stream
+    int* idx_s = slot_s + p.n_layers;                   // [SB] current class index per stream, [SB] abort flag
+    float* logit_s = reinterpret_cast<float*>(Xz + VEC);                      // [SB][W] sampling scratch (aliases Xz[1])
+    double* cdf = reinterpret_cast<double*>(Xs);                              // [SB][W]                   (aliases Xs, Xy)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster_rank(), cl = blockIdx.x / CL, NS = p.NS, NL = p.n_layers;
     const int o0 = rank * NV;                           // first channel this CTA owns in every stage vector
     const int NSLOT = p.n_wslots;
-    constexpr unsigned VEC_BYTES = SB * W * 4;          // bytes every CTA receives per exchanged vector
 
     {
-        const int n0 = 8 * SB * PW;
-        for (int i = tid; i < n0; i += GEN_NT + 32) sm[i] = 0.f;
+        unsigned* z0 = reinterpret_cast<unsigned*>(smb);
+        const int n0 = (int)((reinterpret_cast<unsigned char*>(wbuf) - smb) / 4);
+        for (int i = tid; i < n0; i += GEN_NT + 32) z0[i] = 0u;
         const int* src = reinterpret_cast<const int*>(p.layers);
         int* dst = reinterpret_cast<int*>(lay_s);
         for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
     }
-    if (tid < SB) idx_s[tid] = (cl * SB + tid < NS) ? p.cur_idx[cl * SB + tid] : 0;
+    if (tid < 2 * SB) idx_s[tid] = (tid < SB && cl * SB + tid < NS) ? p.cur_idx[cl * SB + tid] : 0;
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
         for (int i = 0; i < 7; ++i) mbar_init(xbar + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");     // the zero fill is ordered before any peer's bulk copy lands
     __syncthreads();
     if (tid == 0)
-        for (int i = 0; i < 7; ++i) mbar_expect_tx(xbar + i, VEC_BYTES);       // arm phase 0 of every exchange barrier
+        for (int i = 0; i < 7; ++i) mbar_expect_tx(xbar + i, VEC);             // arm phase 0 of every exchange barrier
     for (int l = tid; l < NL; l += GEN_NT) {
         const int len = lay_s[l].ring_len;
         slot_s[l] = (p.t0 + len - 1) % len;
     }
-    cluster_sync_all();                                  // nobody may store into a peer before its barriers exist
+    cluster_sync_all();                                  // nobody may copy into a peer before its barriers exist
     const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
+    const unsigned char* img_rank = p.cl8_img + (size_t)rank * (CL8_IMG1 + CL8_IMG2);
+    const size_t img_layer = (size_t)CL * (CL8_IMG1 + CL8_IMG2);
+    const unsigned char* img_head = p.cl8_img + img_layer * NL + (size_t)rank * 2 * CL8_IMGH;
 
-    // ---- producer warp: weight rows of this CTA for every stage, in order, through the TMA ring (rows padded to PW / 2W+4)
+    // ---- producer warp: the weight image of this CTA for every stage, in order: ONE bulk copy per stage
     if (warp == GEN_WARPS) {
         if (lane == 0) {
             unsigned q = 0;
@@ -2202,8 +2286,15 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                 const bool wh = (p.t0 + ev >= p.n_given - 1);
                 const int n_st = wh ? 2 * NL + 2 : 2 * NL;
                 for (int st = 0; st < n_st; ++st, ++q) {
-                    StageDesc d = stage_desc(p, st, true, NV, NV, NV, NV, NV);
-                    if (st < 2 * NL && (st & 1)) { d.n_first = NV; d.n = 2 * NV; }
+                    const unsigned char* src;
+                    unsigned bytes;
+                    if (st < 2 * NL) {
+                        src = img_rank + (size_t)(st >> 1) * img_layer + ((st & 1) ? CL8_IMG1 : 0);
+                        bytes = (st & 1) ? CL8_IMG2 : CL8_IMG1;
+                    } else {
+                        src = img_head + (st - 2 * NL) * CL8_IMGH;
+                        bytes = CL8_IMGH;
+                    }
                     const int slot = (int)(q & smask);
                     if (q >= (unsigned)NSLOT) {
                         const unsigned par = ((q >> sshift) & 1u) ^ 1u;
@@ -2214,10 +2305,8 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                             if (!done && ++spins > (1u << 30)) asm volatile("trap;");
                         }
                     }
-                    mbar_expect_tx(fullb + slot, (unsigned)(d.n * d.K * 4));
-                    float* dst = wbuf + (size_t)slot * p.wslot_floats;
-                    for (int i = 0; i < d.n; ++i)
-                        bulk_g2s(dst + (size_t)i * (d.K + CL8_PAD), stage_row(p, lay_s, st, d, i, rank, CL), d.K * 4, fullb + slot);
+                    mbar_expect_tx(fullb + slot, bytes);
+                    bulk_g2s(wbuf + (size_t)slot * CL8_IMG1, src, bytes, fullb + slot);
                 }
             }
         }
@@ -2225,10 +2314,10 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         return;
     }
     unsigned cons_q = 0;
-    auto stage_weights = [&](int row, int K) -> const float* {
+    auto stage_weights = [&]() -> const unsigned char* {
         const int slot = (int)(cons_q & smask);
         mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
-        return wbuf + (size_t)slot * p.wslot_floats + (size_t)row * (K + CL8_PAD);
+        return wbuf + (size_t)slot * CL8_IMG1;
     };
     auto release_slot = [&]() {
         __syncwarp();
@@ -2240,29 +2329,38 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
     auto xwait = [&](int i) {
         mbar_wait_bounded(xbar + i, (xpar >> i) & 1u);
         xpar ^= 1u << i;
-        if (tid == 0) mbar_expect_tx(xbar + i, VEC_BYTES);
+        if (tid == 0) mbar_expect_tx(xbar + i, VEC);
     };
-    // lane -> (row-in-warp rr, stream s) for the layer stages; destinations of this lane's remote stores: (lane>>3) + 4*it
-    const int rr = lane >> 3, s = lane & 7;
-    const int sg = cl * SB + s;                          // global stream of this lane
-    const bool s_on = sg < NS;
-    const unsigned sm_base = smem_u32(sm);
-    unsigned rdelta[4];                                  // shared::cluster address of CTA (lane>>3)+4*it minus the local address
-#pragma unroll
-    for (int it = 0; it < 4; ++it) rdelta[it] = mapa_u32(sm_base, (unsigned)((lane >> 3) + 4 * it)) - sm_base;
-    // this lane publishes a v2 / v4 piece of stream s to 4 destination CTAs per call (8 lanes x 4 CTAs per instruction)
-    auto publish2 = [&](float* mat, int ch, float a, float b, int bar_i) {
-        const unsigned la = smem_u32(mat + s * PW + ch), lb = smem_u32(xbar + bar_i);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) st_async_v2(la + rdelta[it], a, b, lb + rdelta[it]);
+    // push staged block `sb` into block `rank` of vector `vec` of every CTA of the cluster (lanes 0-15 of warp 0, one each)
+    const unsigned sm_base = smem_u32(smb);
+    const unsigned rdelta = (tid < CL) ? mapa_u32(sm_base, (unsigned)tid) - sm_base : 0u;
+    auto push = [&](int sb, unsigned char* vec, int bar_i) {
+        if (tid < CL) {
+            const unsigned dst = smem_u32(vec + rank * BLK) + rdelta, rb = smem_u32(xbar + bar_i) + rdelta;
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "r"(smem_u32(stg + sb * BLK)), "r"(BLK), "r"(rb)
+                         : "memory");
+        }
     };
-    auto publish4 = [&](float* mat, int ch, float a, float b, float c, float d, int bar_i) {
-        const unsigned la = smem_u32(mat + s * PW + ch), lb = smem_u32(xbar + bar_i);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) st_async_v4(la + rdelta[it], a, b, c, d, lb + rdelta[it]);
+    // one k-step of this warp's m-tile: A fragments (hi, lo) from the stage image, B fragments of the 8 streams from a block
+    const int mt = warp & 1, kq = warp >> 1;
+    auto mma_step = [&](const unsigned char* wimg, int KS, int ks, const unsigned char* xblk, float (&d)[4]) {
+        const unsigned char* a = wimg + ((size_t)(mt * KS + ks) * 2) * 512 + lane * 16;
+        const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
+        const uint4 b = *reinterpret_cast<const uint4*>(xblk + (lane >> 2) * 64 + (lane & 3) * 16);
+        mma_bf16_16816(d, al, b.x, b.z);
+        mma_bf16_16816(d, ah, b.y, b.w);
+        mma_bf16_16816(d, ah, b.x, b.z);
+    };
+    // sum over the 4 K quarters of output (m-tile m, row r of the tile, stream s): fragment element (lane', j) of each partial
+    auto part_sum = [&](const float* pb, int m, int r, int s, int nq) {
+        const float* q = pb + ((m * 32 + (r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
+        float v = q[0];
+        for (int i = 1; i < nq; ++i) v += q[i * 2 * 128];
+        return v;
     };
     // history taps: thread -> (stream = warp, channels 2*lane + 64*j + {0,1}), fetched into registers one stage ahead
-    const int hs_g = cl * SB + warp;                     // global stream whose taps this thread fetches
+    const int hs_g = cl * SB + warp;                     // global stream whose taps this thread fetches (and which it samples)
     Pair2 hq[4];
     const uint2* hsrc = nullptr;
     unsigned htag = 0;
@@ -2278,7 +2376,6 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         }
     };
     auto commit_old = [&]() {
-        float* dst = Xold + warp * PW + 2 * lane;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float a = 0.f, b = 0.f;
@@ -2287,12 +2384,21 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                 a = __uint_as_float(hq[j].a.x);
                 b = __uint_as_float(hq[j].b.x);
             }
-            *reinterpret_cast<float2*>(dst + 64 * j) = make_float2(a, b);
+            const int c0 = 2 * lane + 64 * j;             // channels c0, c0 + 1: one (hi pair | lo pair) unit
+            unsigned short h0, l0, h1, l1;
+            cl8_split(a, h0, l0);
+            cl8_split(b, h1, l1);
+            *reinterpret_cast<uint2*>(Xold + (c0 >> 4) * BLK + cl8_unit_off(warp, c0 & 15)) =
+                make_uint2((unsigned)h1 << 16 | h0, (unsigned)l1 << 16 | l0);
         }
     };
     issue_old(0, p.t0, p.t0 % lay_s[0].ring_len);
     commit_old();
     WORKER_SYNC();
+    const int fc = tid >> 3, fs = tid & 7;                // finishing threads: (channel-in-CTA fc (mod 16), stream fs)
+    const int fsg = cl * SB + fs;
+    const bool fs_on = fsg < NS;
+    unsigned pb_i = 0, sb_i = 0;                          // partial-sum / staging double-buffer indices
 
     for (int ev = 0; ev < p.n_evals; ++ev) {
         const int t = p.t0 + ev;
@@ -2310,7 +2416,7 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         }
         WORKER_SYNC();
         // layer 0's input: the start-conv column of every stream (warp = stream), computed locally by every CTA; the
-        // owners of a channel also enqueue it in the ring
+        // owners of a channel also enqueue it in the ring and keep the fp32 value for the residual add
         {
             int idx = idx_s[warp];
             idx = idx < 0 ? 0 : (idx >= W ? W - 1 : idx);
@@ -2320,137 +2426,154 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
             for (int j = 0; j < W / 32; ++j) {
                 const int r = lane + 32 * j;
                 const float v = __ldg(p.start_w + (size_t)r * W + idx) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
-                Xcur[warp * PW + r] = v;
-                if (r >= o0 && r < o0 + NV && hs_g < NS) st_pair(ring0 + r, v, rtag);
+                cl8_put(Xcur + (r >> 4) * BLK, warp, r & 15, v);
+                if (r >= o0 && r < o0 + NV) {
+                    hown[(r - o0) * SB + warp] = v;
+                    if (hs_g < NS) st_pair(ring0 + r, v, rtag);
+                }
             }
         }
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic writes to Xcur[0] / sampling scratch before later bulk copies
         WORKER_SYNC();
-        float skr = 0.f;                                  // skip sum of (channel o0 + 4*(warp-4) + rr, stream s), warps 4-7
+        float skr = 0.f;                                  // skip sum of (channel o0 + fc - 16, stream fs), threads 128-255
 
         for (int l = 0; l < NL; ++l) {
             const GenLayer& L = lay_s[l];
-            float* xc = Xcur + (l & 1) * SB * PW;
-            float* zb = Xz + (l & 1) * SB * PW;
-            // ================= stage 1: conv rows 4*warp + rr (filter / gate interleaved), K = 2W interleaved (old, cur)
-            if (l > 0) xwait(l & 1);
+            const bool more = (l + 1 < NL);
+            unsigned char* xc = Xcur + (l & 1) * VEC;
+            unsigned char* zb = Xz + (l & 1) * VEC;
+            // ================= stage 1: m-tile 0 = filter rows, 1 = gate rows; k-steps 4*kq+i of the old taps, then of h
             {
-                const float4* w4p = reinterpret_cast<const float4*>(stage_weights(4 * warp + rr, 2 * W));
-                const float4* o4p = reinterpret_cast<const float4*>(Xold + s * PW);
-                const float4* c4p = reinterpret_cast<const float4*>(xc + s * PW);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < W / 4; ++i) {
-                    const float4 wa = w4p[2 * i], wb = w4p[2 * i + 1], o = o4p[i], c = c4p[i];
-                    a0 = fmaf(wa.x, o.x, a0); a0 = fmaf(wa.y, c.x, a0);
-                    a1 = fmaf(wa.z, o.y, a1); a1 = fmaf(wa.w, c.y, a1);
-                    a2 = fmaf(wb.x, o.z, a2); a2 = fmaf(wb.y, c.z, a2);
-                    a3 = fmaf(wb.z, o.w, a3); a3 = fmaf(wb.w, c.w, a3);
-                }
-                float acc = (a0 + a1) + (a2 + a3);
+                const unsigned char* wimg = stage_weights();
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_step(wimg, 32, 4 * kq + i, Xold + (4 * kq + i) * BLK, d);
+                if (l > 0) xwait(l & 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_step(wimg, 32, 16 + 4 * kq + i, xc + (4 * kq + i) * BLK, d);
                 release_slot();
-                const int ch = o0 + 2 * warp + (rr >> 1);
-                const float* bias = (rr & 1) ? L.bg : L.bf;
-                acc += bias ? __ldg(bias + ch) : 0.f;
-                const float gate = __shfl_down_sync(0xffffffffu, acc, 8);
-                const float zv = tanh_(acc) * sigmoid_(gate);           // meaningful in the filter lanes (rr = 0, 2)
-                const float z0 = __shfl_sync(0xffffffffu, zv, s), z1 = __shfl_sync(0xffffffffu, zv, 16 + s);
-                publish2(zb, o0 + 2 * warp, z0, z1, 2 + (l & 1));
+                float* pb = part + pb_i * 8 * 128;
+                *reinterpret_cast<float4*>(pb + ((kq * 2 + mt) * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                WORKER_SYNC();
+                if (tid < NV * SB) {
+                    const int ch = o0 + fc;
+                    const float f = part_sum(pb, 0, fc, fs, 4) + (L.bf ? __ldg(L.bf + ch) : 0.f);
+                    const float g = part_sum(pb, 1, fc, fs, 4) + (L.bg ? __ldg(L.bg + ch) : 0.f);
+                    cl8_put(stg + sb_i * BLK, fs, fc, tanh_(f) * sigmoid_(g));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                pb_i ^= 1;
+                WORKER_SYNC();
+                push((int)sb_i, zb, 2 + (l & 1));
+                sb_i ^= 1;
             }
-            // ================= stage 2: warps 0-3 residual rows, warps 4-7 skip rows (4*warp + rr of the slot); K = W
+            // ================= stage 2: m-tile 0 = residual rows, 1 = skip rows; k-steps 4*kq+i of z
             {
-                const bool more = (l + 1 < NL);
                 if (more) issue_old(l + 1, t, slot_s[l + 1]);
                 else if (ev + 1 < p.n_evals) issue_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
                 else hsrc = nullptr;
+                const unsigned char* wimg = stage_weights();
                 xwait(2 + (l & 1));
-                const bool is_res = warp < 4;
-                const bool active = is_res ? more : want_head;
-                const float4* w4p = reinterpret_cast<const float4*>(stage_weights(4 * warp + rr, W));
-                float acc = 0.f;
-                if (active) {
-                    const float4* z4p = reinterpret_cast<const float4*>(zb + s * PW);
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < W / 4; ++i) {
-                        const float4 w4 = w4p[i], z4 = z4p[i];
-                        a0 = fmaf(w4.x, z4.x, a0); a1 = fmaf(w4.y, z4.y, a1); a2 = fmaf(w4.z, z4.z, a2); a3 = fmaf(w4.w, z4.w, a3);
-                    }
-                    acc = (a0 + a1) + (a2 + a3);
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                if (mt == 0 ? more : want_head) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, zb + (4 * kq + i) * BLK, d);
                 }
                 release_slot();
-                if (is_res) {
+                float* pb = part + pb_i * 8 * 128;
+                *reinterpret_cast<float4*>(pb + ((kq * 2 + mt) * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                commit_old();                             // every warp is past its stage-1 reads of Xold (two barriers ago)
+                WORKER_SYNC();
+                if (tid < NV * SB) {
                     if (more) {
-                        const int row = o0 + 4 * warp + rr;
+                        const int row = o0 + fc;
                         const GenLayer& Ln = lay_s[l + 1];
-                        float v = acc + (L.br ? __ldg(L.br + row) : 0.f);
-                        v += xc[s * PW + row];
-                        if (s_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + sg) * W + row, v, rtag);
-                        const float q0 = __shfl_sync(0xffffffffu, v, s), q1 = __shfl_sync(0xffffffffu, v, 8 + s);
-                        const float q2 = __shfl_sync(0xffffffffu, v, 16 + s), q3 = __shfl_sync(0xffffffffu, v, 24 + s);
-                        publish4(Xcur + ((l + 1) & 1) * SB * PW, o0 + 4 * warp, q0, q1, q2, q3, (l + 1) & 1);
+                        float v = part_sum(pb, 0, fc, fs, 4) + (L.br ? __ldg(L.br + row) : 0.f);
+                        v += hown[(l & 1) * NV * SB + fc * SB + fs];
+                        hown[((l + 1) & 1) * NV * SB + fc * SB + fs] = v;
+                        if (fs_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + fsg) * W + row, v, rtag);
+                        cl8_put(stg + sb_i * BLK, fs, fc, v);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     }
                 } else if (want_head) {
-                    const float v = acc + (L.bs ? __ldg(L.bs + o0 + 4 * (warp - 4) + rr) : 0.f);
+                    const float v = part_sum(pb, 1, fc - NV, fs, 4) + (L.bs ? __ldg(L.bs + o0 + fc - NV) : 0.f);
                     skr = v + skr;
                 }
-                // every warp of the cluster is past its stage-1 reads of Xold (z of this layer is complete): refill it
-                commit_old();
+                pb_i ^= 1;
+                WORKER_SYNC();
+                if (more) {
+                    push((int)sb_i, Xcur + ((l + 1) & 1) * VEC, (l + 1) & 1);
+                    sb_i ^= 1;
+                }
             }
-            WORKER_SYNC();                                // Xold of the next stage 1 is in place
         }
         if (!want_head) continue;
 
-        // ================= head: skip -> relu -> end_conv_1 -> relu -> end_conv_2, three exchanges
-        if (warp >= 4) {
-            const float q0 = __shfl_sync(0xffffffffu, skr, s), q1 = __shfl_sync(0xffffffffu, skr, 8 + s);
-            const float q2 = __shfl_sync(0xffffffffu, skr, 16 + s), q3 = __shfl_sync(0xffffffffu, skr, 24 + s);
-            publish4(Xs, o0 + 4 * (warp - 4), q0, q1, q2, q3, 4);
+        // ================= head: relu(skip) -> end_conv_1 -> relu -> end_conv_2; one m-tile, 16 k-steps over 8 warps
+        if (tid >= NV * SB) {
+            cl8_put(stg + sb_i * BLK, fs, fc - NV, fmaxf(skr, 0.f));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        const int kh = lane >> 4, r2 = (lane >> 3) & 1;   // head stages: 2 rows per warp, K split in halves over the lane halves
+        WORKER_SYNC();
+        push((int)sb_i, Xs, 4);
+        sb_i ^= 1;
+        auto head_stage = [&](const unsigned char* x) {     // this warp's 2 k-steps of the single m-tile -> part
+            const unsigned char* wimg = stage_weights();
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int ks = 2 * warp + i;
+                const unsigned char* a = wimg + ((size_t)ks * 2) * 512 + lane * 16;
+                const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
+                const uint4 b = *reinterpret_cast<const uint4*>(x + ks * BLK + (lane >> 2) * 64 + (lane & 3) * 16);
+                mma_bf16_16816(d, al, b.x, b.z);
+                mma_bf16_16816(d, ah, b.y, b.w);
+                mma_bf16_16816(d, ah, b.x, b.z);
+            }
+            release_slot();
+            float* pb = part + pb_i * 8 * 128;
+            *reinterpret_cast<float4*>(pb + (warp * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+        };
+        auto head_sum = [&](const float* pb, int r, int s) {  // 8 partials, one per warp
+            const float* q = pb + (((r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
+            float v = q[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) v += q[i * 128];
+            return v;
+        };
         xwait(4);
-        {
-            const float4* w4p = reinterpret_cast<const float4*>(stage_weights(2 * warp + r2, W)) + kh * (W / 8);
-            const float4* x4p = reinterpret_cast<const float4*>(Xs + s * PW) + kh * (W / 8);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < W / 8; ++i) {
-                const float4 w4 = w4p[i], x4 = x4p[i];
-                a0 = fmaf(w4.x, fmaxf(x4.x, 0.f), a0); a1 = fmaf(w4.y, fmaxf(x4.y, 0.f), a1);
-                a2 = fmaf(w4.z, fmaxf(x4.z, 0.f), a2); a3 = fmaf(w4.w, fmaxf(x4.w, 0.f), a3);
-            }
-            float acc = (a0 + a1) + (a2 + a3);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            release_slot();
-            const int row = o0 + 2 * warp + r2;
-            const float y = fmaxf(acc + __ldg(p.e1b + row), 0.f);
-            const float y0 = __shfl_sync(0xffffffffu, y, s), y1 = __shfl_sync(0xffffffffu, y, 8 + s);
-            publish2(Xy, o0 + 2 * warp, y0, y1, 5);
+        head_stage(Xs);
+        WORKER_SYNC();
+        if (tid < NV * SB) {
+            const float y = fmaxf(head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e1b + o0 + fc), 0.f);
+            cl8_put(stg + sb_i * BLK, fs, fc, y);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
+        pb_i ^= 1;
+        WORKER_SYNC();
+        push((int)sb_i, Xy, 5);
+        sb_i ^= 1;
         xwait(5);
-        {
-            const float4* w4p = reinterpret_cast<const float4*>(stage_weights(2 * warp + r2, W)) + kh * (W / 8);
-            const float4* x4p = reinterpret_cast<const float4*>(Xy + s * PW) + kh * (W / 8);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < W / 8; ++i) {
-                const float4 w4 = w4p[i], x4 = x4p[i];
-                a0 = fmaf(w4.x, x4.x, a0); a1 = fmaf(w4.y, x4.y, a1); a2 = fmaf(w4.z, x4.z, a2); a3 = fmaf(w4.w, x4.w, a3);
-            }
-            float acc = (a0 + a1) + (a2 + a3);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            release_slot();
-            const int row = o0 + 2 * warp + r2;
+        head_stage(Xy);
+        WORKER_SYNC();
+        if (tid < NV * SB) {
+            const int row = o0 + fc;
             const float dc = (float)row - (float)W / 2.f;
-            const float v = (acc + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
-            if (kh == 0 && s_on && p.out_logits) p.out_logits[((size_t)sg * p.n_samples + samp) * W + row] = v;
-            const float v0 = __shfl_sync(0xffffffffu, v, s), v1 = __shfl_sync(0xffffffffu, v, 8 + s);
-            publish2(Xl, o0 + 2 * warp, v0, v1, 6);
+            const float v = (head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
+            if (fs_on && p.out_logits) p.out_logits[((size_t)fsg * p.n_samples + samp) * W + row] = v;
+            reinterpret_cast<float*>(stg + sb_i * BLK)[fs * NV + fc] = v;                // logits travel as fp32: [stream][16]
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
+        pb_i ^= 1;
+        WORKER_SYNC();
+        push((int)sb_i, Xl, 6);
+        sb_i ^= 1;
         xwait(6);
         // every CTA holds all logits of its 8 streams: warp = stream draws the next index (all CTAs agree)
         if (hs_g < NS) {
             float* lg = logit_s + warp * W;
-            for (int c = lane; c < W; c += 32) lg[c] = Xl[warp * PW + c];
+            const float* xl = reinterpret_cast<const float*>(Xl);
+            for (int c = lane; c < W; c += 32) lg[c] = xl[(c >> 4) * (BLK / 4) + warp * NV + (c & 15)];
             __syncwarp();
             const int choice = choose_sample(lg, cdf + warp * W, W, lane, p.temperature,
                                              p.uniforms ? p.uniforms + (size_t)hs_g * p.n_samples + samp : nullptr);
@@ -2459,17 +2582,22 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                 if (rank == 0) p.out_idx[(size_t)hs_g * p.n_samples + samp] = choice;
             }
         }
-        // the top-of-evaluation barrier publishes idx_s
+        // the top-of-evaluation barrier publishes idx_s; the fence there orders the scratch writes before later bulk copies
     }
     WORKER_SYNC();
     if (rank == 0 && tid < SB && cl * SB + tid < NS) p.cur_idx[cl * SB + tid] = idx_s[tid];
-    cluster_sync_all();                                  // peers may still be storing into this CTA's shared memory
+    cluster_sync_all();                                  // peers may still be copying into this CTA's shared memory
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 struct ScratchLayout {
-    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, total;
+    size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, cl8_img, cl8_bytes, total;
 };
+// the batched cluster kernel's shape: several streams of a k = 2 net whose five widths are all 256
+static bool cl8_shape_ok(const wn_gen_shape& s) {
+    return s.n_streams >= 2 && s.k == 2 && s.n_layers >= 2 && s.R == CL8_W && s.D == CL8_W && s.S == CL8_W && s.E == CL8_W &&
+           s.classes == CL8_W;
+}
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static ScratchLayout scratch_layout(const wn_gen_shape& s) {
     ScratchLayout o;
@@ -2488,6 +2616,9 @@ static ScratchLayout scratch_layout(const wn_gen_shape& s) {
     o.logitLL = off; off = align_up(off + sizeof(uint2) * 2 * (size_t)s.n_streams * s.classes, 256);
     o.ll_end = off;
     o.trace = off; off += 8 * 2048;
+    o.cl8_img = off;
+    o.cl8_bytes = cl8_shape_ok(s) ? (size_t)CL * ((size_t)s.n_layers * (CL8_IMG1 + CL8_IMG2) + 2 * CL8_IMGH) : 0;
+    off = align_up(off + o.cl8_bytes, 256);
     o.total = off;
     return o;
 }
@@ -2525,6 +2656,8 @@ struct wn_gen_handle {
     bool cluster_ok;        // k=2, 256-class nets whose rows split over 16 CTAs x 8 warps: gen_kernel_cluster applies
     size_t smem_cluster;
     int n_wslots_cluster, wslot_cluster;
+    bool cl8_ok, cl8_packed;   // gen_kernel_cl8 applies (cl8_shape_ok and the shared memory fits); its weight images are built
+    size_t smem_cl8;
     bool x2_ok;             // fast_ok on a 64-CTA grid with 4 rows per stage vector per CTA: gen_kernel_x2 applies
     size_t smem_x2;
     int n_wslots_x2;
@@ -2759,6 +2892,15 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
             h->cluster_ok = cs >= 2 && h->smem_cluster <= (size_t)smem_optin;
         }
     }
+    // ---- batched cluster kernel (8 streams per cluster, tensor cores)
+    {
+        const size_t fixed = (size_t)8 * CL8_VEC + 2 * CL8_BLK + sizeof(float) * (2 * 8 * 128 + 2 * (CL8_W / CL) * CL8_SB) + 16 * 8 +
+                             sizeof(GenLayer) * (size_t)s->n_layers + sizeof(int) * (size_t)(s->n_layers + 2 * CL8_SB);
+        h->smem_cl8 = align_up(fixed, 16) + 2 * (size_t)CL8_IMG1;
+        h->cl8_ok = cl8_shape_ok(*s) && h->smem_cl8 <= (size_t)smem_optin && !getenv("WN_GEN_NOCL8");
+        h->cl8_packed = false;
+        p.cl8_img = reinterpret_cast<const unsigned char*>(h->scratch + h->lay.cl8_img);
+    }
     h->tables_uploaded = false;
     h->cur_t = 0;
     *out = h;
@@ -2776,6 +2918,12 @@ extern "C" int wn_gen_reset(wn_gen_handle* h, void* stream) {
                                 cudaMemcpyHostToDevice, st));
         WN_CUDA(cudaStreamSynchronize(st));       // h->layers is pageable host memory owned by the handle
         h->tables_uploaded = true;
+    }
+    if (h->cl8_ok && !h->cl8_packed) {               // weights are constant for the life of a handle: split them once
+        cl8_pack_kernel<<<1184, 256, 0, st>>>(h->base.layers, h->shape.n_layers, h->base.e1w, h->base.e2w,
+                                             reinterpret_cast<unsigned*>(h->scratch + h->lay.cl8_img));
+        WN_CUDA(cudaGetLastError());
+        h->cl8_packed = true;
     }
     h->cur_t = 0;
     return 0;
@@ -2822,6 +2970,28 @@ static int launch_gen_cluster(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_cluster, &cfg));
     WN_REQUIRE(max_clusters >= 1, WN_E_UNSUPP, "wn_gen_run: a %d-CTA cluster cannot be scheduled on this device", CL);
     WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_cluster, p));
+    return 0;
+}
+
+static int launch_gen_cl8(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cl8));
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL));
+    cfg.blockDim = dim3(GEN_NT + 32);
+    cfg.dynamicSmemBytes = h->smem_cl8;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_cl8, &cfg));
+    WN_REQUIRE(max_clusters >= 1, WN_E_UNSUPP, "wn_gen_run: a %d-CTA cluster cannot be scheduled on this device", CL);
+    WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_cl8, p));      // clusters are independent: more than fit run in waves
     return 0;
 }
 
@@ -2872,12 +3042,13 @@ static int launch_gen_fast(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
 
 extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_set_mode: null handle");
-    WN_REQUIRE(mode >= 0 && mode <= 5, WN_E_BADARG,
+    WN_REQUIRE(mode >= 0 && mode <= 6, WN_E_BADARG,
                "wn_gen_set_mode: mode must be 0 (auto), 1 (grid barrier), 2 (generic flag exchange), 3 (single-stream L2 kernel), "
-               "4 (cluster / DSMEM kernel) or 5 (single-stream two-level exchange kernel)");
+               "4 (cluster / DSMEM kernel), 5 (single-stream two-level exchange kernel) or 6 (batched tensor-core cluster kernel)");
     if (mode == 3) WN_REQUIRE(h->fast_ok, WN_E_UNSUPP, "wn_gen_set_mode: the single-stream L2 kernel does not apply to this shape");
     if (mode == 4) WN_REQUIRE(h->cluster_ok, WN_E_UNSUPP, "wn_gen_set_mode: the cluster kernel does not apply to this shape");
     if (mode == 5) WN_REQUIRE(h->x2_ok, WN_E_UNSUPP, "wn_gen_set_mode: the two-level exchange kernel does not apply to this shape");
+    if (mode == 6) WN_REQUIRE(h->cl8_ok, WN_E_UNSUPP, "wn_gen_set_mode: the batched cluster kernel does not apply to this shape");
     WN_REQUIRE(h->cur_t == 0, WN_E_STATE, "wn_gen_set_mode: switch kernels only right after wn_gen_reset");
     if (mode != 1) WN_REQUIRE(h->shape.n_layers >= 2, WN_E_UNSUPP, "wn_gen_set_mode: flag exchange needs >= 2 layers");
     h->mode = mode;
@@ -2920,11 +3091,14 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         WN_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
         int rc;
         const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
-        if ((auto_cluster || h->mode == 4) && h->cluster_ok) {
+        if ((h->mode == 0 || h->mode == 6) && h->cl8_ok) {       // several streams of a 256-wide net: 8 streams per cluster
+            p.n_wslots = 2;
+            rc = launch_gen_cl8(h, p, st);
+        } else if ((auto_cluster || h->mode == 4) && h->cluster_ok) {
             p.n_wslots = h->n_wslots_cluster;
             p.wslot_floats = h->wslot_cluster;
             rc = launch_gen_cluster(h, p, st);
-        } else if ((h->mode == 0 || h->mode == 5) && h->x2_ok) {
+        } else if (h->mode == 5 && h->x2_ok) {                // never picked automatically: measured 2x slower than kernel 3
             p.n_wslots = h->n_wslots_x2;
             rc = launch_gen_x2(h, p, st);
         } else if ((h->mode == 0 || h->mode == 3) && h->fast_ok) {
@@ -2963,10 +3137,11 @@ extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block,
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_launch_info: null handle");
     // the kernel wn_gen_run would pick in the handle's current mode (same selection as in wn_gen_run)
     const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
-    const bool cluster = (auto_cluster || h->mode == 4) && h->cluster_ok;
-    const bool fast = !cluster && (((h->mode == 0 || h->mode == 5) && h->x2_ok) || ((h->mode == 0 || h->mode == 3) && h->fast_ok));
-    if (grid) *grid = cluster ? h->shape.n_streams * CL : h->grid;
-    if (block) *block = (cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer warp
+    const bool cl8 = (h->mode == 0 || h->mode == 6) && h->cl8_ok;
+    const bool cluster = !cl8 && (auto_cluster || h->mode == 4) && h->cluster_ok;
+    const bool fast = !cluster && ((h->mode == 5 && h->x2_ok) || ((h->mode == 0 || h->mode == 3) && h->fast_ok));
+    if (grid) *grid = cl8 ? (h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL : cluster ? h->shape.n_streams * CL : h->grid;
+    if (block) *block = (cl8 || cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer warp
     if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
     return 0;
 }

@@ -29,17 +29,19 @@ if what in ("all", "gen"):
 if what == "step":
     # one full cfg-3 training step (forward with saved activations + backward) between cudaProfilerStart/Stop:
     # run under `ncu --profile-from-start off` to list exactly the kernels of one step
-    import torch.nn.functional as F
+    import wavenet_training as wt
     idx = torch.randint(0, 256, (8, 16000), generator=torch.Generator().manual_seed(1234)).to(torch.uint8).cuda()
     model = bench.build_model(dict(bench.GEN_KW, output_length=10885)).cuda()
     tgt = torch.randint(0, 256, (8 * 10885,), generator=torch.Generator().manual_seed(3)).cuda()
-    for i in range(2):
-        if i == 1:
+    opt = wt.FusedAdam(model.parameters(), lr=1e-4, model=model)
+    for i in range(3):
+        if i == 2:
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
-        model.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(model.forward_indices(idx), tgt)
+        opt.zero_grad(set_to_none=False)
+        loss = wt.fused_cross_entropy(model.forward_indices(idx), tgt)      # the loss the bench and WavenetTrainer use
         loss.backward()
+        opt.step()
         torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print("step ok", float(loss.detach()))
