@@ -2172,8 +2172,9 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned dst) {
 
 // Weight images.  One (m-tile, k-step) = 1 KB: [hi: 32 lanes x 16 B][lo: 32 lanes x 16 B], lane's 16 bytes = the A fragment
 // registers a0..a3 of m16n8k16: a_j covers row g + 8*(j&1), k pair 2t + 8*(j>>1) (g = lane>>2, t = lane&3).
-//   per (layer, rank): [stage 1: m-tile 0 = filter rows, 1 = gate rows; k-steps 0-15 = tap 0 (old) of channel block ks,
-//                       16-31 = tap 1 (current)] [stage 2: m-tile 0 = residual rows, 1 = skip rows; k-step = z block]
+//   per (layer, rank): three 32 KB images [m-tile][k-step 0-15][hi | lo]: [stage 1, tap 0 (old): m-tile 0 = filter rows,
+//                       1 = gate rows; k-step = channel block] [stage 1, tap 1 (current)] [stage 2: m-tile 0 = residual
+//                       rows, 1 = skip rows; k-step = z block]
 //   then per rank: [end_conv_1 image][end_conv_2 image] (one m-tile, 16 k-steps each)
 __global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const float* e1w, const float* e2w, unsigned* img) {
     const int W = CL8_W;
@@ -2190,12 +2191,13 @@ __global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const floa
             const GenLayer& L = layers[l];
             const bool st1 = w < CL8_IMG1 / 4;
             if (!st1) w -= CL8_IMG1 / 4;
-            const int KS = st1 ? 32 : 16;
-            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)((w >> 8) % KS), mt = (int)((w >> 8) / KS);
+            int tap = 0;                                   // stage 1 = two images of the stage-2 shape: tap 0 (old), then tap 1
+            if (st1 && w >= CL8_IMG2 / 4) { tap = 1; w -= CL8_IMG2 / 4; }
+            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)((w >> 8) & 15), mt = (int)(w >> 12);
             const int g = lane >> 2, t = lane & 3;
             row = rank * 16 + g + 8 * (j & 1);
             const int kk = 2 * t + 8 * (j >> 1);
-            if (st1) { src = mt ? L.wg : L.wf; col = ((ks & 15) * 16 + kk) * 2 + (ks >> 4); ld = 2 * W; stride = 2; }
+            if (st1) { src = mt ? L.wg : L.wf; col = (ks * 16 + kk) * 2 + tap; ld = 2 * W; stride = 2; }
             else { src = mt ? L.ws : L.wr; col = ks * 16 + kk; ld = W; }
             const float x0 = src[(size_t)row * ld + col], x1 = src[(size_t)row * ld + col + stride];
             unsigned short h0, l0, h1, l1;
@@ -2222,7 +2224,7 @@ __global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const floa
     }
 }
 
-__global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams p) {
+__global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams p) {
     extern __shared__ __align__(128) unsigned char smb[];
     constexpr int W = CL8_W, SB = CL8_SB, NV = CL8_W / CL, BLK = CL8_BLK, VEC = CL8_VEC;
     // exchanged vectors first: same offsets in every CTA (mapa keeps the offset).  Each is 16 blocks of 512 bytes.
@@ -2235,13 +2237,14 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
     unsigned char* stg = Xold + VEC;                    // [2][BLK] this CTA's contribution of a stage, staged for the bulk copies
     float* part = reinterpret_cast<float*>(stg + 2 * BLK);                    // [2][8 warps][32 lanes][4] partial C fragments
     float* hown = part + 2 * 8 * 128;                   // [2][16][SB] fp32 layer input at the channels this CTA owns
-    unsigned char* wbuf = reinterpret_cast<unsigned char*>(hown + 2 * NV * SB);          // [n_wslots][CL8_IMG1]
-    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * CL8_IMG1);
+    unsigned char* wbuf = reinterpret_cast<unsigned char*>(hown + 2 * NV * SB);          // [n_wslots = 4][CL8_IMG2] weight image ring
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * CL8_IMG2);
     unsigned long long* emptyb = fullb + 4;
     unsigned long long* xbar = emptyb + 4;              // [0,1] h by layer parity, [2,3] z by layer parity, [4] skip, [5] y1, [6] logits
     GenLayer* lay_s = reinterpret_cast<GenLayer*>(xbar + 8);
     int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
     int* idx_s = slot_s + p.n_layers;                   // [SB] current class index per stream, [SB] abort flag
+    float* bias_s = reinterpret_cast<float*>(idx_s + 2 * SB);                 // [NL][4: f, g, residual, skip][16 own channels]
     float* logit_s = reinterpret_cast<float*>(Xz + VEC);                      // [SB][W] sampling scratch (aliases Xz[1])
     double* cdf = reinterpret_cast<double*>(Xs);                              // [SB][W]                   (aliases Xs, Xy)
 
@@ -2253,14 +2256,20 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
     {
         unsigned* z0 = reinterpret_cast<unsigned*>(smb);
         const int n0 = (int)((reinterpret_cast<unsigned char*>(wbuf) - smb) / 4);
-        for (int i = tid; i < n0; i += GEN_NT + 32) z0[i] = 0u;
+        for (int i = tid; i < n0; i += GEN_NT + 64) z0[i] = 0u;
         const int* src = reinterpret_cast<const int*>(p.layers);
         int* dst = reinterpret_cast<int*>(lay_s);
-        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 32) dst[i] = src[i];
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 64) dst[i] = src[i];
     }
     if (tid < 2 * SB) idx_s[tid] = (tid < SB && cl * SB + tid < NS) ? p.cur_idx[cl * SB + tid] : 0;
+    for (int i = tid; i < NL * 4 * NV; i += GEN_NT + 64) {
+        const GenLayer& Lg = p.layers[i / (4 * NV)];
+        const int kind = (i / NV) & 3;
+        const float* bp = kind == 0 ? Lg.bf : kind == 1 ? Lg.bg : kind == 2 ? Lg.br : Lg.bs;
+        bias_s[i] = bp ? __ldg(bp + o0 + (i & (NV - 1))) : 0.f;
+    }
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 1); mbar_init(emptyb + i, GEN_WARPS); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 32); mbar_init(emptyb + i, GEN_WARPS); }
         for (int i = 0; i < 7; ++i) mbar_init(xbar + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2278,36 +2287,87 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
     const size_t img_layer = (size_t)CL * (CL8_IMG1 + CL8_IMG2);
     const unsigned char* img_head = p.cl8_img + img_layer * NL + (size_t)rank * 2 * CL8_IMGH;
 
-    // ---- producer warp: the weight image of this CTA for every stage, in order: ONE bulk copy per stage
-    if (warp == GEN_WARPS) {
-        if (lane == 0) {
-            unsigned q = 0;
-            for (int ev = 0; ev < p.n_evals; ++ev) {
-                const bool wh = (p.t0 + ev >= p.n_given - 1);
-                const int n_st = wh ? 2 * NL + 2 : 2 * NL;
-                for (int st = 0; st < n_st; ++st, ++q) {
-                    const unsigned char* src;
-                    unsigned bytes;
-                    if (st < 2 * NL) {
-                        src = img_rank + (size_t)(st >> 1) * img_layer + ((st & 1) ? CL8_IMG1 : 0);
-                        bytes = (st & 1) ? CL8_IMG2 : CL8_IMG1;
-                    } else {
-                        src = img_head + (st - 2 * NL) * CL8_IMGH;
-                        bytes = CL8_IMGH;
-                    }
-                    const int slot = (int)(q & smask);
-                    if (q >= (unsigned)NSLOT) {
-                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
-                        unsigned done = 0, spins = 0;
-                        while (!done) {
-                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
-                            if (!done && ++spins > (1u << 30)) asm volatile("trap;");
-                        }
-                    }
-                    mbar_expect_tx(fullb + slot, bytes);
-                    bulk_g2s(wbuf + (size_t)slot * CL8_IMG1, src, bytes, fullb + slot);
+    // push staged block `sb` into block `rank` of vector `vec` of every CTA of the cluster: the pusher warp (warp 9) reads the
+    // 512 bytes back (16 per lane) and issues ONE st.async.v4 per destination -- a whole block per instruction, its bytes
+    // credited to the destination's mbarrier.  Measured per exchange round (tools/dsmem_probe.cu, 8 clusters): 1 017 cycles
+    // this way (H), 1 254 with one cp.async.bulk per destination (F, which also occupies the SM's bulk-copy engine and
+    // needs a proxy fence after staging), 4 144 with per-lane 8-byte stores from the worker warps (E), and ~1 200 more for a
+    // multicast copy from a global staging slot (the fence after the global stores).  The workers only signal "staged"
+    // (bar.arrive on barrier 2) and move on to the work of the next stage.
+    const unsigned sm_base = smem_u32(smb);
+    auto push = [&](int sb, unsigned char* vec, int bar_i) {
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + sb * BLK + lane * 16);
+        const unsigned la = smem_u32(vec + rank * BLK + lane * 16), lb = smem_u32(xbar + bar_i);
+#pragma unroll
+        for (int d = 0; d < CL; ++d) {
+            const unsigned delta = mapa_u32(sm_base, (unsigned)d) - sm_base;
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(la + delta),
+                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(lb + delta)
+                         : "memory");
+        }
+    };
+#define CL8_STAGED_SYNC() asm volatile("bar.sync 2, 288;" ::: "memory")
+#define CL8_STAGED_ARRIVE() asm volatile("bar.arrive 2, 288;" ::: "memory")
+    if (warp == GEN_WARPS + 1) {
+        int sb = 0;
+        for (int ev = 0; ev < p.n_evals; ++ev) {
+            const bool wh = (p.t0 + ev >= p.n_given - 1);
+            for (int l = 0; l < NL; ++l) {
+                CL8_STAGED_SYNC();
+                push(sb, Xz + (l & 1) * VEC, 2 + (l & 1));
+                sb ^= 1;
+                if (l + 1 < NL) {
+                    CL8_STAGED_SYNC();
+                    push(sb, Xcur + ((l + 1) & 1) * VEC, (l + 1) & 1);
+                    sb ^= 1;
                 }
+            }
+            if (wh) {
+                CL8_STAGED_SYNC(); push(sb, Xs, 4); sb ^= 1;
+                CL8_STAGED_SYNC(); push(sb, Xy, 5); sb ^= 1;
+                CL8_STAGED_SYNC(); push(sb, Xl, 6); sb ^= 1;
+            }
+        }
+        cluster_sync_all();
+        return;
+    }
+    // ---- producer warp: the weight image of this CTA for every stage, in order, as 16-byte cp.async copies by all 32 lanes
+    // (LDGSTS through the load/store path).  Bulk copies would share the SM's bulk-copy engine with the exchange: measured,
+    // the images then stream at ~22 bytes/cycle and the layer time equals the streaming time, whatever the prefetch depth.
+    if (warp == GEN_WARPS) {
+        unsigned q = 0;
+        for (int ev = 0; ev < p.n_evals; ++ev) {
+            const bool wh = (p.t0 + ev >= p.n_given - 1);
+            const int n_st = wh ? 3 * NL + 2 : 3 * NL;          // three 32 KB images per layer, two 16 KB head images
+            for (int st = 0; st < n_st; ++st, ++q) {
+                const unsigned char* src;
+                unsigned bytes;
+                if (st < 3 * NL) {
+                    src = img_rank + (size_t)(st / 3) * img_layer + (size_t)(st % 3) * CL8_IMG2;
+                    bytes = CL8_IMG2;
+                } else {
+                    src = img_head + (st - 3 * NL) * CL8_IMGH;
+                    bytes = CL8_IMGH;
+                }
+                const int slot = (int)(q & smask);
+                if (q >= (unsigned)NSLOT) {
+                    const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                    unsigned done = 0, spins = 0;
+                    while (!done) {
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                        if (!done && ++spins > (1u << 30)) asm volatile("trap;");
+                    }
+                }
+                if (lane == 0 && p.trace != nullptr && blockIdx.x == 0 && ev == p.n_evals - 1 && st < 3 * NL)
+                    p.trace[1000 + st] = clock64();
+                const unsigned dst = smem_u32(wbuf + (size_t)slot * CL8_IMG2) + lane * 16;
+                const unsigned char* sp = src + lane * 16;
+#pragma unroll 8
+                for (unsigned o = 0; o < bytes; o += 512)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(sp + o) : "memory");
+                // this lane's arrival on the slot's "full" barrier fires when its copies above have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(fullb + slot)) : "memory");
             }
         }
         cluster_sync_all();                              // matches the workers' final cluster barrier
@@ -2317,7 +2377,7 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
     auto stage_weights = [&]() -> const unsigned char* {
         const int slot = (int)(cons_q & smask);
         mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
-        return wbuf + (size_t)slot * CL8_IMG1;
+        return wbuf + (size_t)slot * CL8_IMG2;
     };
     auto release_slot = [&]() {
         __syncwarp();
@@ -2331,26 +2391,26 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         xpar ^= 1u << i;
         if (tid == 0) mbar_expect_tx(xbar + i, VEC);
     };
-    // push staged block `sb` into block `rank` of vector `vec` of every CTA of the cluster (lanes 0-15 of warp 0, one each)
-    const unsigned sm_base = smem_u32(smb);
-    const unsigned rdelta = (tid < CL) ? mapa_u32(sm_base, (unsigned)tid) - sm_base : 0u;
-    auto push = [&](int sb, unsigned char* vec, int bar_i) {
-        if (tid < CL) {
-            const unsigned dst = smem_u32(vec + rank * BLK) + rdelta, rb = smem_u32(xbar + bar_i) + rdelta;
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "r"(smem_u32(stg + sb * BLK)), "r"(BLK), "r"(rb)
-                         : "memory");
-        }
-    };
     // one k-step of this warp's m-tile: A fragments (hi, lo) from the stage image, B fragments of the 8 streams from a block
     const int mt = warp & 1, kq = warp >> 1;
-    auto mma_step = [&](const unsigned char* wimg, int KS, int ks, const unsigned char* xblk, float (&d)[4]) {
+    // three independent accumulation chains (lo.hi, hi.lo, hi.hi) so that consecutive MMAs do not wait for each other; they
+    // are added in a fixed order when the partial is stored
+    struct Acc3 { float lh[4], hl[4], hh[4]; };
+    auto acc_zero = [](Acc3& d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d.lh[i] = d.hl[i] = d.hh[i] = 0.f;
+    };
+    auto acc_store = [&](const Acc3& d, float* dst) {
+        *reinterpret_cast<float4*>(dst) = make_float4((d.lh[0] + d.hl[0]) + d.hh[0], (d.lh[1] + d.hl[1]) + d.hh[1],
+                                                      (d.lh[2] + d.hl[2]) + d.hh[2], (d.lh[3] + d.hl[3]) + d.hh[3]);
+    };
+    auto mma_step = [&](const unsigned char* wimg, int KS, int ks, const unsigned char* xblk, Acc3& d) {
         const unsigned char* a = wimg + ((size_t)(mt * KS + ks) * 2) * 512 + lane * 16;
         const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
         const uint4 b = *reinterpret_cast<const uint4*>(xblk + (lane >> 2) * 64 + (lane & 3) * 16);
-        mma_bf16_16816(d, al, b.x, b.z);
-        mma_bf16_16816(d, ah, b.y, b.w);
-        mma_bf16_16816(d, ah, b.x, b.z);
+        mma_bf16_16816(d.lh, al, b.x, b.z);
+        mma_bf16_16816(d.hl, ah, b.y, b.w);
+        mma_bf16_16816(d.hh, ah, b.x, b.z);
     };
     // sum over the 4 K quarters of output (m-tile m, row r of the tile, stream s): fragment element (lane', j) of each partial
     auto part_sum = [&](const float* pb, int m, int r, int s, int nq) {
@@ -2405,6 +2465,10 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         const unsigned rtag = (unsigned)t + 1u;          // ring tag of time t
         const bool want_head = (t >= p.n_given - 1);
         const int samp = t - (p.n_given - 1);
+        const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && tid == 0 && ev == p.n_evals - 1;
+        int tr_n = 0;
+#define TR8() do { if (tr_on && tr_n < 2040) p.trace[tr_n++] = clock64(); } while (0)
+        if (tr_on) p.trace[2040] = clock64();             // whole-evaluation stamps live at [2040..2047]
         if (tid < SB && cl * SB + tid < NS) {
             const int g = cl * SB + tid;
             if (t < p.n_given) idx_s[tid] = p.first[(size_t)g * p.n_given + t];
@@ -2433,106 +2497,118 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                 }
             }
         }
-        asm volatile("fence.proxy.async;" ::: "memory");   // generic writes to Xcur[0] / sampling scratch before later bulk copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes to Xcur[0] / sampling scratch before later bulk copies
         WORKER_SYNC();
         float skr = 0.f;                                  // skip sum of (channel o0 + fc - 16, stream fs), threads 128-255
+        TR8();             // layer stamps start here (index 0)
 
         for (int l = 0; l < NL; ++l) {
-            const GenLayer& L = lay_s[l];
             const bool more = (l + 1 < NL);
             unsigned char* xc = Xcur + (l & 1) * VEC;
             unsigned char* zb = Xz + (l & 1) * VEC;
             // ================= stage 1: m-tile 0 = filter rows, 1 = gate rows; k-steps 4*kq+i of the old taps, then of h
             {
-                const unsigned char* wimg = stage_weights();
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) mma_step(wimg, 32, 4 * kq + i, Xold + (4 * kq + i) * BLK, d);
-                if (l > 0) xwait(l & 1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) mma_step(wimg, 32, 16 + 4 * kq + i, xc + (4 * kq + i) * BLK, d);
-                release_slot();
-                float* pb = part + pb_i * 8 * 128;
-                *reinterpret_cast<float4*>(pb + ((kq * 2 + mt) * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
-                WORKER_SYNC();
-                if (tid < NV * SB) {
-                    const int ch = o0 + fc;
-                    const float f = part_sum(pb, 0, fc, fs, 4) + (L.bf ? __ldg(L.bf + ch) : 0.f);
-                    const float g = part_sum(pb, 1, fc, fs, 4) + (L.bg ? __ldg(L.bg + ch) : 0.f);
-                    cl8_put(stg + sb_i * BLK, fs, fc, tanh_(f) * sigmoid_(g));
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                }
-                pb_i ^= 1;
-                WORKER_SYNC();
-                push((int)sb_i, zb, 2 + (l & 1));
-                sb_i ^= 1;
-            }
-            // ================= stage 2: m-tile 0 = residual rows, 1 = skip rows; k-steps 4*kq+i of z
-            {
+                // history taps of the NEXT stage 1 start their trip through the L2 now; they are used a whole stage later
                 if (more) issue_old(l + 1, t, slot_s[l + 1]);
                 else if (ev + 1 < p.n_evals) issue_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
                 else hsrc = nullptr;
                 const unsigned char* wimg = stage_weights();
+                TR8();         // 1: stage-1 weights (old tap) landed
+                Acc3 d;
+                acc_zero(d);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, Xold + (4 * kq + i) * BLK, d);
+                release_slot();
+                wimg = stage_weights();
+                if (l > 0) xwait(l & 1);
+                TR8();         // 2: old-tap MMAs done, h arrived
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, xc + (4 * kq + i) * BLK, d);
+                release_slot();
+                float* pb = part + pb_i * 8 * 128;
+                acc_store(d, pb + ((kq * 2 + mt) * 32 + lane) * 4);
+                TR8();         // 3: MMAs done, partials stored
+                WORKER_SYNC();
+                TR8();         // 4: barrier
+                if (tid < NV * SB) {
+                    const float f = part_sum(pb, 0, fc, fs, 4) + bias_s[(l * 4 + 0) * NV + fc];
+                    const float g = part_sum(pb, 1, fc, fs, 4) + bias_s[(l * 4 + 1) * NV + fc];
+                    cl8_put(stg + sb_i * BLK, fs, fc, tanh_(f) * sigmoid_(g));
+                }
+                pb_i ^= 1;
+                TR8();         // 5: z computed and staged
+                CL8_STAGED_ARRIVE();
+                sb_i ^= 1;
+            }
+            // ================= stage 2: m-tile 0 = residual rows, 1 = skip rows; k-steps 4*kq+i of z
+            {
+                // every warp is past its stage-1 reads of Xold (two barriers ago): refill it while z is in flight
+                commit_old();
+                TR8();         // 7: next history taps in place
+                const unsigned char* wimg = stage_weights();
+                TR8();         // 8: stage-2 weights landed
                 xwait(2 + (l & 1));
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                TR8();         // 9: z arrived
+                Acc3 d;
+                acc_zero(d);
                 if (mt == 0 ? more : want_head) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, zb + (4 * kq + i) * BLK, d);
                 }
                 release_slot();
                 float* pb = part + pb_i * 8 * 128;
-                *reinterpret_cast<float4*>(pb + ((kq * 2 + mt) * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
-                commit_old();                             // every warp is past its stage-1 reads of Xold (two barriers ago)
+                acc_store(d, pb + ((kq * 2 + mt) * 32 + lane) * 4);
+                TR8();         // 10: MMAs done, partials stored
                 WORKER_SYNC();
+                TR8();         // 11: barrier
                 if (tid < NV * SB) {
                     if (more) {
                         const int row = o0 + fc;
                         const GenLayer& Ln = lay_s[l + 1];
-                        float v = part_sum(pb, 0, fc, fs, 4) + (L.br ? __ldg(L.br + row) : 0.f);
+                        float v = part_sum(pb, 0, fc, fs, 4) + bias_s[(l * 4 + 2) * NV + fc];
                         v += hown[(l & 1) * NV * SB + fc * SB + fs];
                         hown[((l + 1) & 1) * NV * SB + fc * SB + fs] = v;
                         if (fs_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + fsg) * W + row, v, rtag);
                         cl8_put(stg + sb_i * BLK, fs, fc, v);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     }
                 } else if (want_head) {
-                    const float v = part_sum(pb, 1, fc - NV, fs, 4) + (L.bs ? __ldg(L.bs + o0 + fc - NV) : 0.f);
+                    const float v = part_sum(pb, 1, fc - NV, fs, 4) + bias_s[(l * 4 + 3) * NV + fc - NV];
                     skr = v + skr;
                 }
                 pb_i ^= 1;
-                WORKER_SYNC();
+                TR8();         // 12: h' computed and staged
                 if (more) {
-                    push((int)sb_i, Xcur + ((l + 1) & 1) * VEC, (l + 1) & 1);
+                    CL8_STAGED_ARRIVE();
                     sb_i ^= 1;
                 }
             }
         }
+        if (tr_on) p.trace[2041] = clock64();             // layers done
         if (!want_head) continue;
 
         // ================= head: relu(skip) -> end_conv_1 -> relu -> end_conv_2; one m-tile, 16 k-steps over 8 warps
         if (tid >= NV * SB) {
             cl8_put(stg + sb_i * BLK, fs, fc - NV, fmaxf(skr, 0.f));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        WORKER_SYNC();
-        push((int)sb_i, Xs, 4);
+        CL8_STAGED_ARRIVE();
         sb_i ^= 1;
         auto head_stage = [&](const unsigned char* x) {     // this warp's 2 k-steps of the single m-tile -> part
             const unsigned char* wimg = stage_weights();
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            Acc3 d;
+            acc_zero(d);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int ks = 2 * warp + i;
                 const unsigned char* a = wimg + ((size_t)ks * 2) * 512 + lane * 16;
                 const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
                 const uint4 b = *reinterpret_cast<const uint4*>(x + ks * BLK + (lane >> 2) * 64 + (lane & 3) * 16);
-                mma_bf16_16816(d, al, b.x, b.z);
-                mma_bf16_16816(d, ah, b.y, b.w);
-                mma_bf16_16816(d, ah, b.x, b.z);
+                mma_bf16_16816(d.lh, al, b.x, b.z);
+                mma_bf16_16816(d.hl, ah, b.y, b.w);
+                mma_bf16_16816(d.hh, ah, b.x, b.z);
             }
             release_slot();
             float* pb = part + pb_i * 8 * 128;
-            *reinterpret_cast<float4*>(pb + (warp * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+            acc_store(d, pb + (warp * 32 + lane) * 4);
         };
         auto head_sum = [&](const float* pb, int r, int s) {  // 8 partials, one per warp
             const float* q = pb + (((r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
@@ -2547,11 +2623,9 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
         if (tid < NV * SB) {
             const float y = fmaxf(head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e1b + o0 + fc), 0.f);
             cl8_put(stg + sb_i * BLK, fs, fc, y);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         pb_i ^= 1;
-        WORKER_SYNC();
-        push((int)sb_i, Xy, 5);
+        CL8_STAGED_ARRIVE();
         sb_i ^= 1;
         xwait(5);
         head_stage(Xy);
@@ -2562,13 +2636,12 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
             const float v = (head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
             if (fs_on && p.out_logits) p.out_logits[((size_t)fsg * p.n_samples + samp) * W + row] = v;
             reinterpret_cast<float*>(stg + sb_i * BLK)[fs * NV + fc] = v;                // logits travel as fp32: [stream][16]
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         pb_i ^= 1;
-        WORKER_SYNC();
-        push((int)sb_i, Xl, 6);
+        CL8_STAGED_ARRIVE();
         sb_i ^= 1;
         xwait(6);
+        if (tr_on) p.trace[2042] = clock64();             // head done, logits everywhere
         // every CTA holds all logits of its 8 streams: warp = stream draws the next index (all CTAs agree)
         if (hs_g < NS) {
             float* lg = logit_s + warp * W;
@@ -2582,6 +2655,7 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_cl8(const GenParams
                 if (rank == 0) p.out_idx[(size_t)hs_g * p.n_samples + samp] = choice;
             }
         }
+        if (tr_on) p.trace[2043] = clock64();             // sampled
         // the top-of-evaluation barrier publishes idx_s; the fence there orders the scratch writes before later bulk copies
     }
     WORKER_SYNC();
@@ -2895,8 +2969,9 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     // ---- batched cluster kernel (8 streams per cluster, tensor cores)
     {
         const size_t fixed = (size_t)8 * CL8_VEC + 2 * CL8_BLK + sizeof(float) * (2 * 8 * 128 + 2 * (CL8_W / CL) * CL8_SB) + 16 * 8 +
-                             sizeof(GenLayer) * (size_t)s->n_layers + sizeof(int) * (size_t)(s->n_layers + 2 * CL8_SB);
-        h->smem_cl8 = align_up(fixed, 16) + 2 * (size_t)CL8_IMG1;
+                             sizeof(GenLayer) * (size_t)s->n_layers + sizeof(int) * (size_t)(s->n_layers + 2 * CL8_SB) +
+                             sizeof(float) * (size_t)s->n_layers * 4 * (CL8_W / CL);
+        h->smem_cl8 = align_up(fixed, 16) + 4 * (size_t)CL8_IMG2;
         h->cl8_ok = cl8_shape_ok(*s) && h->smem_cl8 <= (size_t)smem_optin && !getenv("WN_GEN_NOCL8");
         h->cl8_packed = false;
         p.cl8_img = reinterpret_cast<const unsigned char*>(h->scratch + h->lay.cl8_img);
@@ -2978,7 +3053,7 @@ static int launch_gen_cl8(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL));
-    cfg.blockDim = dim3(GEN_NT + 32);
+    cfg.blockDim = dim3(GEN_NT + 64);                 // 8 worker warps, the weight producer warp, the pusher warp
     cfg.dynamicSmemBytes = h->smem_cl8;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -3092,7 +3167,7 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         int rc;
         const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
         if ((h->mode == 0 || h->mode == 6) && h->cl8_ok) {       // several streams of a 256-wide net: 8 streams per cluster
-            p.n_wslots = 2;
+            p.n_wslots = 4;
             rc = launch_gen_cl8(h, p, st);
         } else if ((auto_cluster || h->mode == 4) && h->cluster_ok) {
             p.n_wslots = h->n_wslots_cluster;
@@ -3141,7 +3216,7 @@ extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block,
     const bool cluster = !cl8 && (auto_cluster || h->mode == 4) && h->cluster_ok;
     const bool fast = !cluster && ((h->mode == 5 && h->x2_ok) || ((h->mode == 0 || h->mode == 3) && h->fast_ok));
     if (grid) *grid = cl8 ? (h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL : cluster ? h->shape.n_streams * CL : h->grid;
-    if (block) *block = (cl8 || cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer warp
+    if (block) *block = cl8 ? GEN_NT + 64 : (cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer (and pusher) warp
     if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
     return 0;
 }

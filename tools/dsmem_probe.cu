@@ -7,6 +7,8 @@
 //   F  the payload of E staged in local shared memory, then ONE cp.async.bulk (shared::cta -> shared::cluster, 512 B,
 //      complete_tx on the destination's mbarrier) per destination, issued by 16 lanes
 //   G  like F with 1 KB per (source, destination)
+//   H  the payload of F staged in local shared memory, then ONE warp reads it back (16 B per lane) and issues one
+//      st.async.v4 per destination: a whole 512-byte block per instruction
 // Each round every CTA publishes V=16 values (x8 in E) to all 16 CTAs and needs all 256 values of the round before it may
 // publish the next one.  Prints cycles per round.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dsmem_probe tools/dsmem_probe.cu
@@ -33,6 +35,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned par) {
 __device__ __forceinline__ void st_async1(unsigned raddr, float a, unsigned rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(a)), "r"(rbar) : "memory");
 }
+__device__ __forceinline__ void st_async4(unsigned raddr, uint4 v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
+}
 __device__ __forceinline__ void st_async2(unsigned raddr, float a, float b, unsigned rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(rbar) : "memory");
 }
@@ -49,7 +54,7 @@ __global__ void __launch_bounds__(NT, 1) probe(int rounds, long long* cycles, fl
     if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const unsigned bytes = (MODE == 4 || MODE == 5) ? 8 * CL * V * 4 : (MODE == 6) ? 16 * CL * V * 4 : CL * V * 4;
+    const unsigned bytes = (MODE == 4 || MODE == 5 || MODE == 7) ? 8 * CL * V * 4 : (MODE == 6) ? 16 * CL * V * 4 : CL * V * 4;
     if (tid == 0) { mbar_expect(bar, bytes); mbar_expect(bar + 1, bytes); }
     csync();
     float acc = 0.f;
@@ -110,6 +115,20 @@ __global__ void __launch_bounds__(NT, 1) probe(int rounds, long long* cycles, fl
             if (tid == 0) mbar_expect(bar + b, bytes);
             acc += blocks[b][tid >> 4][tid & 15];
             __syncthreads();
+        } else if (MODE == 7) {
+            if (tid < 128) stage[b][tid] = myv;
+            __syncthreads();
+            if (warp == 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&stage[b][lane * 4]);
+                const unsigned la = s32(&blocks[b][rank][lane * 4]), lb = s32(bar + b);
+#pragma unroll
+                for (int d = 0; d < CL; ++d) st_async4(mapa(la, d), v, mapa(lb, d));
+            }
+            mbar_wait(bar + b, par[b]);
+            par[b] ^= 1;
+            if (tid == 0) mbar_expect(bar + b, bytes);
+            acc += blocks[b][tid >> 4][tid & 15];
+            __syncthreads();
         } else {                                                 // E: warp w publishes channels 2w,2w+1 of 8 streams as v2
             const int s = lane & 7;
 #pragma unroll
@@ -159,6 +178,7 @@ int main() {
         run<4>("E st.async v2, 8 streams (8 KB per CTA per round)", rounds, clusters);
         run<5>("F bulk copy smem->dsmem, 512 B x 16 destinations", rounds, clusters);
         run<6>("G bulk copy smem->dsmem, 1 KB x 16 destinations", rounds, clusters);
+        run<7>("H one warp: LDS.128 + st.async.v4, 512 B per instruction per destination", rounds, clusters);
     }
     return 0;
 }
