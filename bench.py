@@ -218,6 +218,26 @@ def bench_generate(args, world, rank):
 
     # cfg4: 64 independent streams batched on one GPU (aggregate samples/s); shorter run, same per-sample cost
     batched = None
+
+    def run_streams(NB, nb):
+        sb = rt.sampler(NB)
+        first_b = torch.full((NB, 1), 128, dtype=torch.int32, device=dev)
+        uni_b = torch.from_numpy(np.random.random_sample((NB, nb))).to(dev)
+        out_b = torch.zeros(NB, nb, dtype=torch.int32, device=dev)
+        rt.generate_resident(sb, first_b, 1, 64, TEMPERATURE, 0.0, out_b[:, :64].contiguous(), d_uni=uni_b[:, :64].contiguous())
+        tb = []
+        for _ in range(2):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rt.generate_resident(sb, first_b, 1, nb, TEMPERATURE, 0.0, out_b, d_uni=uni_b)
+            e1.record()
+            torch.cuda.synchronize()
+            tb.append(e0.elapsed_time(e1))
+        g_, b_, x_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        native.lib().wn_gen_launch_info(sb["handle"], ctypes.byref(g_), ctypes.byref(b_), ctypes.byref(x_))
+        return max_over_ranks(min(tb), world), g_.value, b_.value
+
     if not args.no_batched:
         NB, nb = 64, 1000
         sb = rt.sampler(NB)
@@ -237,7 +257,14 @@ def bench_generate(args, world, rank):
         tbm = max_over_ranks(min(tb), world)
         gb_, bb_, _bars = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         native.lib().wn_gen_launch_info(sb["handle"], ctypes.byref(gb_), ctypes.byref(bb_), ctypes.byref(_bars))
+        # the same kernel where its 16-CTA clusters are all co-resident (7 x 8 streams) and at the 8-CTA variant's capacity
+        t56, g56, _ = run_streams(56, nb)
+        t120, g120, _ = run_streams(120, nb)
+        other = {"56_streams": {"value": world * 56 * nb / (t56 / 1e3), "us_per_step": t56 * 1e3 / nb, "grid": g56},
+                 "120_streams": {"value": world * 120 * nb / (t120 / 1e3), "us_per_step": t120 * 1e3 / nb, "grid": g120}}
         batched = {"workload": "cfg4: 64 independent streams, same net, 1000 samples per stream, temperature=1.0",
+                   "kernel": "gen_kernel_cl8 (8 streams per cluster, mma.sync bf16 hi/lo pairs, st.async block exchange)",
+                   "us_per_step": tbm * 1e3 / nb, "other_stream_counts": other,
                    "value": world * NB * nb / (tbm / 1e3), "unit": "samples/s (aggregate over streams)",
                    "per_stream_samples_per_s": nb / (tbm / 1e3), "ms_per_launch": tbm, "grid": gb_.value, "block": bb_.value,
                    "distinct_streams": int(len({tuple(r) for r in out_b[:, :32].cpu().numpy().tolist()}))}

@@ -389,6 +389,9 @@ int wn_gen_destroy(wn_gen_handle* h);
  * Kernels 2, 3 and 5 sum in the same order (bit-identical results); kernel 4 splits rows differently (rounding-level
  * differences). */
 int wn_gen_set_mode(wn_gen_handle* h, int mode);
+/* The parameter tensors given to wn_gen_create were written in place (an optimizer step): kernels 1-5 read them on every
+ * launch and need nothing; kernel 6 keeps pre-split copies, which the next wn_gen_reset rebuilds after this call. */
+int wn_gen_weights_changed(wn_gen_handle* h);
 /* Synchronise the stream and report whether a launch aborted (a CTA waited > ~3 s for a tag): 0 = fine. */
 int wn_gen_check(wn_gen_handle* h, void* stream);
 /* Debug aid: with WN_GEN_TRACE=1 in the environment at wn_gen_create, CTA 0 stamps clock64() at 8 points of every layer

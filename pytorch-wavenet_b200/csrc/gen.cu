@@ -2172,13 +2172,14 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned dst) {
 
 // Weight images.  One (m-tile, k-step) = 1 KB: [hi: 32 lanes x 16 B][lo: 32 lanes x 16 B], lane's 16 bytes = the A fragment
 // registers a0..a3 of m16n8k16: a_j covers row g + 8*(j&1), k pair 2t + 8*(j>>1) (g = lane>>2, t = lane&3).
-//   per (layer, rank): three 32 KB images [m-tile][k-step 0-15][hi | lo]: [stage 1, tap 0 (old): m-tile 0 = filter rows,
-//                       1 = gate rows; k-step = channel block] [stage 1, tap 1 (current)] [stage 2: m-tile 0 = residual
-//                       rows, 1 = skip rows; k-step = z block]
-//   then per rank: [end_conv_1 image][end_conv_2 image] (one m-tile, 16 k-steps each)
+//   layout [layer][kind][virtual rank 0-15][32 KB image = [m-tile][k-step 0-15][hi | lo]], kind 0 = stage 1, tap 0 (old;
+//   m-tile 0 = filter rows, 1 = gate rows; k-step = channel block), 1 = stage 1, tap 1 (current), 2 = stage 2 (m-tile 0 =
+//   residual rows, 1 = skip rows; k-step = z block); then [end_conv_1 | end_conv_2][virtual rank][16 KB: one m-tile].
+//   The images of consecutive virtual ranks are adjacent, so a CTA that owns VR of them fetches a stage with ONE copy.
 __global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const float* e1w, const float* e2w, unsigned* img) {
     const int W = CL8_W;
-    const size_t per_layer = (size_t)CL * (CL8_IMG1 + CL8_IMG2) / 4, total = per_layer * n_layers + (size_t)CL * 2 * CL8_IMGH / 4;
+    constexpr size_t IW = CL8_IMG2 / 4, HW = CL8_IMGH / 4;          // words per layer image / head image
+    const size_t per_layer = 3 * CL * IW, total = per_layer * n_layers + 2 * CL * HW;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const float* src;      // row-major weight matrix the word comes from
         int row, col, ld, stride = 1;
@@ -2186,94 +2187,88 @@ __global__ void cl8_pack_kernel(const GenLayer* layers, int n_layers, const floa
         if (w < per_layer * n_layers) {
             const int l = (int)(w / per_layer);
             w -= (size_t)l * per_layer;
-            const int rank = (int)(w / ((CL8_IMG1 + CL8_IMG2) / 4));
-            w -= (size_t)rank * ((CL8_IMG1 + CL8_IMG2) / 4);
+            const int kind = (int)(w / (CL * IW));          // 0: stage 1, tap 0 (old)   1: stage 1, tap 1 (current)   2: stage 2
+            w -= (size_t)kind * CL * IW;
+            const int vrank = (int)(w / IW);
+            w -= (size_t)vrank * IW;
             const GenLayer& L = layers[l];
-            const bool st1 = w < CL8_IMG1 / 4;
-            if (!st1) w -= CL8_IMG1 / 4;
-            int tap = 0;                                   // stage 1 = two images of the stage-2 shape: tap 0 (old), then tap 1
-            if (st1 && w >= CL8_IMG2 / 4) { tap = 1; w -= CL8_IMG2 / 4; }
-            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)((w >> 8) & 15), mt = (int)(w >> 12);
+            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), ks = (int)((w >> 8) & 15), mt = (int)(w >> 12);
             const int g = lane >> 2, t = lane & 3;
-            row = rank * 16 + g + 8 * (j & 1);
+            row = vrank * 16 + g + 8 * (j & 1);
             const int kk = 2 * t + 8 * (j >> 1);
-            if (st1) { src = mt ? L.wg : L.wf; col = (ks * 16 + kk) * 2 + tap; ld = 2 * W; stride = 2; }
+            if (kind < 2) { src = mt ? L.wg : L.wf; col = (ks * 16 + kk) * 2 + kind; ld = 2 * W; stride = 2; }
             else { src = mt ? L.ws : L.wr; col = ks * 16 + kk; ld = W; }
-            const float x0 = src[(size_t)row * ld + col], x1 = src[(size_t)row * ld + col + stride];
-            unsigned short h0, l0, h1, l1;
-            cl8_split(x0, h0, l0);
-            cl8_split(x1, h1, l1);
-            img[i] = half ? ((unsigned)l1 << 16 | l0) : ((unsigned)h1 << 16 | h0);
         } else {
             w -= per_layer * n_layers;
-            const int rank = (int)(w / (2 * CL8_IMGH / 4));
-            w -= (size_t)rank * (2 * CL8_IMGH / 4);
-            const bool a = w < CL8_IMGH / 4;
-            if (!a) w -= CL8_IMGH / 4;
-            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), half = (int)((w >> 7) & 1), ks = (int)(w >> 8);
+            const int which = (int)(w / (CL * HW));         // 0: end_conv_1   1: end_conv_2
+            w -= (size_t)which * CL * HW;
+            const int vrank = (int)(w / HW);
+            w -= (size_t)vrank * HW;
+            const int j = (int)(w & 3), lane = (int)((w >> 2) & 31), ks = (int)(w >> 8);
             const int g = lane >> 2, t = lane & 3;
-            row = rank * 16 + g + 8 * (j & 1);
+            row = vrank * 16 + g + 8 * (j & 1);
             col = ks * 16 + 2 * t + 8 * (j >> 1);
-            src = a ? e1w : e2w;
-            const float x0 = src[(size_t)row * W + col], x1 = src[(size_t)row * W + col + 1];
-            unsigned short h0, l0, h1, l1;
-            cl8_split(x0, h0, l0);
-            cl8_split(x1, h1, l1);
-            img[i] = half ? ((unsigned)l1 << 16 | l0) : ((unsigned)h1 << 16 | h0);
+            ld = W;
+            src = which ? e2w : e1w;
         }
+        const int half = (int)((i >> 7) & 1);                // every image is a multiple of 256 words: bit 7 of i is the hi/lo plane
+        const float x0 = src[(size_t)row * ld + col], x1 = src[(size_t)row * ld + col + stride];
+        unsigned short h0, l0, h1, l1;
+        cl8_split(x0, h0, l0);
+        cl8_split(x1, h1, l1);
+        img[i] = half ? ((unsigned)l1 << 16 | l0) : ((unsigned)h1 << 16 | h0);
     }
 }
 
-__global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams p) {
+// CS = CTAs per cluster (16 or 8).  The exchanged vectors always consist of 16 blocks ("virtual ranks" of 16 channels);
+// a CTA of a CS-cluster owns VR = 16 / CS consecutive virtual ranks and walks them one after the other in every stage.  At
+// most 7 clusters of 16 CTAs are co-resident on a B200 (tools/cluster_occ.cu) but 15 clusters of 8: CS = 8 runs 64 streams
+// (8 clusters) in one wave on 64 SMs, at twice the per-CTA work -- the step is bound by the exchange latency, not by it.
+template <int CS>
+__global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kernel_cl8(const GenParams p) {
     extern __shared__ __align__(128) unsigned char smb[];
-    constexpr int W = CL8_W, SB = CL8_SB, NV = CL8_W / CL, BLK = CL8_BLK, VEC = CL8_VEC;
+    constexpr int W = CL8_W, SB = CL8_SB, NV = 16, BLK = CL8_BLK, VEC = CL8_VEC, VR = CL / CS, NVC = NV * VR;
     // exchanged vectors first: same offsets in every CTA (mapa keeps the offset).  Each is 16 blocks of 512 bytes.
     unsigned char* Xcur = smb;                          // [2] layer input h (hi/lo split), by layer parity
     unsigned char* Xz = Xcur + 2 * VEC;                 // [2] gated activation z, by layer parity; Xz[1] doubles as sampling scratch
     unsigned char* Xs = Xz + 2 * VEC;                   // relu(skip sum)           \  Xz[1], Xs, Xy are contiguous: 24 KB that no
     unsigned char* Xy = Xs + VEC;                       // end_conv_1 output        /  peer writes while this CTA samples
-    unsigned char* Xl = Xy + VEC;                       // logits, fp32: [rank][stream][16]
+    unsigned char* Xl = Xy + VEC;                       // logits, fp32: [virtual rank][stream][16]
     unsigned char* Xold = Xl + VEC;                     // history taps of the coming stage 1 (local)
-    unsigned char* stg = Xold + VEC;                    // [2][BLK] this CTA's contribution of a stage, staged for the bulk copies
-    float* part = reinterpret_cast<float*>(stg + 2 * BLK);                    // [2][8 warps][32 lanes][4] partial C fragments
-    float* hown = part + 2 * 8 * 128;                   // [2][16][SB] fp32 layer input at the channels this CTA owns
-    unsigned char* wbuf = reinterpret_cast<unsigned char*>(hown + 2 * NV * SB);          // [n_wslots = 4][CL8_IMG2] weight image ring
-    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)p.n_wslots * CL8_IMG2);
+    unsigned char* stg = Xold + VEC;                    // [2][VR][BLK] this CTA's contribution of a stage, staged for the pusher
+    float* part = reinterpret_cast<float*>(stg + 2 * VR * BLK);               // [2][VR][8 warps][32 lanes][4] partial C fragments
+    float* hown = part + 2 * VR * 8 * 128;              // [2][VR][16][SB] fp32 layer input at the channels this CTA owns
+    constexpr int SLOTB = VR * CL8_IMG2, NSLOT = 4 / VR;         // weight ring: 4 x 32 KB (VR = 1) or 2 x 64 KB (VR = 2)
+    constexpr int NTHR = GEN_NT + 64 + (VR == 2 ? 32 : 0);      // workers + producer + pusher (+ second producer for VR = 2)
+    unsigned char* wbuf = reinterpret_cast<unsigned char*>(hown + 2 * NVC * SB);         // [NSLOT][SLOTB] weight image ring
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(wbuf + (size_t)NSLOT * SLOTB);
     unsigned long long* emptyb = fullb + 4;
     unsigned long long* xbar = emptyb + 4;              // [0,1] h by layer parity, [2,3] z by layer parity, [4] skip, [5] y1, [6] logits
     GenLayer* lay_s = reinterpret_cast<GenLayer*>(xbar + 8);
     int* slot_s = reinterpret_cast<int*>(lay_s + p.n_layers);
     int* idx_s = slot_s + p.n_layers;                   // [SB] current class index per stream, [SB] abort flag
-    float* bias_s = reinterpret_cast<float*>(idx_s + 2 * SB);                 // [NL][4: f, g, residual, skip][16 own channels]
     float* logit_s = reinterpret_cast<float*>(Xz + VEC);                      // [SB][W] sampling scratch (aliases Xz[1])
     double* cdf = reinterpret_cast<double*>(Xs);                              // [SB][W]                   (aliases Xs, Xy)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rank = (int)cluster_rank(), cl = blockIdx.x / CL, NS = p.NS, NL = p.n_layers;
-    const int o0 = rank * NV;                           // first channel this CTA owns in every stage vector
-    const int NSLOT = p.n_wslots;
+    const int rank = (int)cluster_rank(), cl = blockIdx.x / CS, NS = p.NS, NL = p.n_layers;
+    const int v0 = rank * VR;                           // first virtual rank of this CTA
+    const int o0 = v0 * NV;                             // first channel this CTA owns in every stage vector
 
     {
         unsigned* z0 = reinterpret_cast<unsigned*>(smb);
         const int n0 = (int)((reinterpret_cast<unsigned char*>(wbuf) - smb) / 4);
-        for (int i = tid; i < n0; i += GEN_NT + 64) z0[i] = 0u;
+        for (int i = tid; i < n0; i += NTHR) z0[i] = 0u;
         const int* src = reinterpret_cast<const int*>(p.layers);
         int* dst = reinterpret_cast<int*>(lay_s);
-        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += GEN_NT + 64) dst[i] = src[i];
+        for (int i = tid; i < NL * (int)(sizeof(GenLayer) / sizeof(int)); i += NTHR) dst[i] = src[i];
     }
     if (tid < 2 * SB) idx_s[tid] = (tid < SB && cl * SB + tid < NS) ? p.cur_idx[cl * SB + tid] : 0;
-    for (int i = tid; i < NL * 4 * NV; i += GEN_NT + 64) {
-        const GenLayer& Lg = p.layers[i / (4 * NV)];
-        const int kind = (i / NV) & 3;
-        const float* bp = kind == 0 ? Lg.bf : kind == 1 ? Lg.bg : kind == 2 ? Lg.br : Lg.bs;
-        bias_s[i] = bp ? __ldg(bp + o0 + (i & (NV - 1))) : 0.f;
-    }
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, 32); mbar_init(emptyb + i, GEN_WARPS); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(fullb + i, VR == 2 ? 33 : 1); mbar_init(emptyb + i, GEN_WARPS); }
         for (int i = 0; i < 7; ++i) mbar_init(xbar + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async;" ::: "memory");     // the zero fill is ordered before any peer's bulk copy lands
     __syncthreads();
     if (tid == 0)
         for (int i = 0; i < 7; ++i) mbar_expect_tx(xbar + i, VEC);             // arm phase 0 of every exchange barrier
@@ -2281,29 +2276,33 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         const int len = lay_s[l].ring_len;
         slot_s[l] = (p.t0 + len - 1) % len;
     }
-    cluster_sync_all();                                  // nobody may copy into a peer before its barriers exist
-    const unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
-    const unsigned char* img_rank = p.cl8_img + (size_t)rank * (CL8_IMG1 + CL8_IMG2);
-    const size_t img_layer = (size_t)CL * (CL8_IMG1 + CL8_IMG2);
-    const unsigned char* img_head = p.cl8_img + img_layer * NL + (size_t)rank * 2 * CL8_IMGH;
+    cluster_sync_all();                                  // nobody may store into a peer before its barriers exist
+    constexpr unsigned smask = (unsigned)NSLOT - 1u, sshift = (NSLOT == 4) ? 2u : 1u;
+    const size_t img_kind = (size_t)CL * CL8_IMG2;       // bytes of one (layer, kind): 16 virtual ranks
+    const unsigned char* img_mine = p.cl8_img + (size_t)v0 * CL8_IMG2;
+    const unsigned char* img_head = p.cl8_img + 3 * img_kind * NL + (size_t)v0 * CL8_IMGH;
 
-    // push staged block `sb` into block `rank` of vector `vec` of every CTA of the cluster: the pusher warp (warp 9) reads the
-    // 512 bytes back (16 per lane) and issues ONE st.async.v4 per destination -- a whole block per instruction, its bytes
-    // credited to the destination's mbarrier.  Measured per exchange round (tools/dsmem_probe.cu, 8 clusters): 1 017 cycles
-    // this way (H), 1 254 with one cp.async.bulk per destination (F, which also occupies the SM's bulk-copy engine and
-    // needs a proxy fence after staging), 4 144 with per-lane 8-byte stores from the worker warps (E), and ~1 200 more for a
-    // multicast copy from a global staging slot (the fence after the global stores).  The workers only signal "staged"
-    // (bar.arrive on barrier 2) and move on to the work of the next stage.
+    // push the staged blocks `sb` into blocks v0 .. v0+VR-1 of vector `vec` of every CTA of the cluster: the pusher warp
+    // (warp 9) reads each 512-byte block back (16 bytes per lane) and issues ONE st.async.v4 per destination -- a whole
+    // block per instruction, its bytes credited to the destination's mbarrier.  Measured per exchange round
+    // (tools/dsmem_probe.cu, 8 clusters of 16): 1 017 cycles this way (H), 1 254 with one cp.async.bulk per destination (F,
+    // which also occupies the SM's bulk-copy engine and needs a proxy fence after staging), 4 144 with per-lane 8-byte
+    // stores from the worker warps (E), and ~1 200 more for a multicast copy from a global staging slot (the fence after the
+    // global stores).  The workers only signal "staged" (bar.arrive on barrier 2) and move on to the next stage.
     const unsigned sm_base = smem_u32(smb);
     auto push = [&](int sb, unsigned char* vec, int bar_i) {
-        const uint4 v = *reinterpret_cast<const uint4*>(stg + sb * BLK + lane * 16);
-        const unsigned la = smem_u32(vec + rank * BLK + lane * 16), lb = smem_u32(xbar + bar_i);
 #pragma unroll
-        for (int d = 0; d < CL; ++d) {
-            const unsigned delta = mapa_u32(sm_base, (unsigned)d) - sm_base;
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(la + delta),
-                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(lb + delta)
-                         : "memory");
+        for (int vr = 0; vr < VR; ++vr) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + (sb * VR + vr) * BLK + lane * 16);
+            const unsigned la = smem_u32(vec + (v0 + vr) * BLK + lane * 16), lb = smem_u32(xbar + bar_i);
+#pragma unroll
+            for (int d = 0; d < CS; ++d) {
+                const unsigned delta = mapa_u32(sm_base, (unsigned)d) - sm_base;
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                                 la + delta),
+                             "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(lb + delta)
+                             : "memory");
+            }
         }
     };
 #define CL8_STAGED_SYNC() asm volatile("bar.sync 2, 288;" ::: "memory")
@@ -2331,24 +2330,58 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         cluster_sync_all();
         return;
     }
-    // ---- producer warp: the weight image of this CTA for every stage, in order, as 16-byte cp.async copies by all 32 lanes
-    // (LDGSTS through the load/store path).  Bulk copies would share the SM's bulk-copy engine with the exchange: measured,
-    // the images then stream at ~22 bytes/cycle and the layer time equals the streaming time, whatever the prefetch depth.
+    // ---- producer warp: the weight images of this CTA for every stage, in order: ONE bulk copy per stage kind (the images
+    // of the CTA's VR virtual ranks are adjacent).  One lane issues; the issuing thread is held ~100 cycles + bytes/84 per
+    // instruction, so whole images it is: 8 KB pieces cap an SM at 45 B/cycle, 32 KB images reach 42 and 64 KB images 84
+    // with two in flight (tools/bulk_bw_probe.cu).  The exchange no longer uses the bulk-copy engine (st.async), which had
+    // throttled these copies to ~22 B/cycle.
     if (warp == GEN_WARPS) {
+        if (lane == 0) {
+            unsigned q = 0;
+            for (int ev = 0; ev < p.n_evals; ++ev) {
+                const bool wh = (p.t0 + ev >= p.n_given - 1);
+                const int n_st = wh ? 3 * NL + 2 : 3 * NL;      // per layer: old taps, current input, stage 2; then the two head stages
+                for (int st = 0; st < n_st; ++st, ++q) {
+                    const unsigned char* src;
+                    unsigned bytes;
+                    if (st < 3 * NL) {
+                        src = img_mine + (size_t)st * img_kind;
+                        bytes = VR * CL8_IMG2;
+                    } else {
+                        src = img_head + (size_t)(st - 3 * NL) * CL * CL8_IMGH;
+                        bytes = VR * CL8_IMGH;
+                    }
+                    const int slot = (int)(q & smask);
+                    if (q >= (unsigned)NSLOT) {
+                        const unsigned par = ((q >> sshift) & 1u) ^ 1u;
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(smem_u32(emptyb + slot)), "r"(par) : "memory");
+                            if (!done && ++spins > (1u << 30)) asm volatile("trap;");
+                        }
+                    }
+                    // VR = 2: the bulk copy brings the first virtual rank's image, warp 10 the second one (below)
+                    mbar_expect_tx(fullb + slot, bytes / VR);
+                    bulk_g2s(wbuf + (size_t)slot * SLOTB, src, bytes / VR, fullb + slot);
+                }
+            }
+        }
+        cluster_sync_all();                              // matches the workers' final cluster barrier
+        return;
+    }
+    // ---- second producer (VR = 2 only): one bulk copy at a time streams ~31 bytes/cycle into the 2-slot ring, which made
+    // the 192 KB of a layer the bottleneck; this warp fetches the second virtual rank's image of every stage as 16-byte
+    // cp.async copies (load/store path, ~27 bytes/cycle for one warp) in parallel with the bulk copy of the first.
+    if (VR == 2 && warp == GEN_WARPS + 2) {
         unsigned q = 0;
         for (int ev = 0; ev < p.n_evals; ++ev) {
             const bool wh = (p.t0 + ev >= p.n_given - 1);
-            const int n_st = wh ? 3 * NL + 2 : 3 * NL;          // three 32 KB images per layer, two 16 KB head images
+            const int n_st = wh ? 3 * NL + 2 : 3 * NL;
             for (int st = 0; st < n_st; ++st, ++q) {
-                const unsigned char* src;
-                unsigned bytes;
-                if (st < 3 * NL) {
-                    src = img_rank + (size_t)(st / 3) * img_layer + (size_t)(st % 3) * CL8_IMG2;
-                    bytes = CL8_IMG2;
-                } else {
-                    src = img_head + (st - 3 * NL) * CL8_IMGH;
-                    bytes = CL8_IMGH;
-                }
+                const unsigned half = (st < 3 * NL) ? CL8_IMG2 : CL8_IMGH;
+                const unsigned char* src = (st < 3 * NL) ? img_mine + (size_t)st * img_kind + half
+                                                         : img_head + (size_t)(st - 3 * NL) * CL * CL8_IMGH + half;
                 const int slot = (int)(q & smask);
                 if (q >= (unsigned)NSLOT) {
                     const unsigned par = ((q >> sshift) & 1u) ^ 1u;
@@ -2359,25 +2392,23 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
                         if (!done && ++spins > (1u << 30)) asm volatile("trap;");
                     }
                 }
-                if (lane == 0 && p.trace != nullptr && blockIdx.x == 0 && ev == p.n_evals - 1 && st < 3 * NL)
-                    p.trace[1000 + st] = clock64();
-                const unsigned dst = smem_u32(wbuf + (size_t)slot * CL8_IMG2) + lane * 16;
+                const unsigned dst = smem_u32(wbuf + (size_t)slot * SLOTB + half) + lane * 16;
                 const unsigned char* sp = src + lane * 16;
 #pragma unroll 8
-                for (unsigned o = 0; o < bytes; o += 512)
+                for (unsigned o = 0; o < half; o += 512)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(sp + o) : "memory");
                 // this lane's arrival on the slot's "full" barrier fires when its copies above have landed
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(fullb + slot)) : "memory");
             }
         }
-        cluster_sync_all();                              // matches the workers' final cluster barrier
+        cluster_sync_all();
         return;
     }
     unsigned cons_q = 0;
     auto stage_weights = [&]() -> const unsigned char* {
         const int slot = (int)(cons_q & smask);
         mbar_wait(fullb + slot, (cons_q >> sshift) & 1u);
-        return wbuf + (size_t)slot * CL8_IMG2;
+        return wbuf + (size_t)slot * SLOTB;
     };
     auto release_slot = [&]() {
         __syncwarp();
@@ -2404,20 +2435,23 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         *reinterpret_cast<float4*>(dst) = make_float4((d.lh[0] + d.hl[0]) + d.hh[0], (d.lh[1] + d.hl[1]) + d.hh[1],
                                                       (d.lh[2] + d.hl[2]) + d.hh[2], (d.lh[3] + d.hl[3]) + d.hh[3]);
     };
-    auto mma_step = [&](const unsigned char* wimg, int KS, int ks, const unsigned char* xblk, Acc3& d) {
-        const unsigned char* a = wimg + ((size_t)(mt * KS + ks) * 2) * 512 + lane * 16;
+    auto mma_step = [&](const unsigned char* a, const unsigned char* xblk, Acc3& d) {      // a: this lane's hi fragment; lo at +512
         const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
         const uint4 b = *reinterpret_cast<const uint4*>(xblk + (lane >> 2) * 64 + (lane & 3) * 16);
         mma_bf16_16816(d.lh, al, b.x, b.z);
         mma_bf16_16816(d.hl, ah, b.y, b.w);
         mma_bf16_16816(d.hh, ah, b.x, b.z);
     };
+    // this warp's four k-steps (4*kq .. 4*kq+3) of its m-tile of a 32 KB layer image against blocks 4*kq.. of vector x
+    auto mma_quarter = [&](const unsigned char* wimg, const unsigned char* x, Acc3& d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            mma_step(wimg + ((size_t)(mt * 16 + 4 * kq + i) * 2) * 512 + lane * 16, x + (4 * kq + i) * BLK, d);
+    };
     // sum over the 4 K quarters of output (m-tile m, row r of the tile, stream s): fragment element (lane', j) of each partial
-    auto part_sum = [&](const float* pb, int m, int r, int s, int nq) {
+    auto part_sum = [&](const float* pb, int m, int r, int s) {
         const float* q = pb + ((m * 32 + (r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
-        float v = q[0];
-        for (int i = 1; i < nq; ++i) v += q[i * 2 * 128];
-        return v;
+        return ((q[0] + q[256]) + q[512]) + q[768];
     };
     // history taps: thread -> (stream = warp, channels 2*lane + 64*j + {0,1}), fetched into registers one stage ahead
     const int hs_g = cl * SB + warp;                     // global stream whose taps this thread fetches (and which it samples)
@@ -2455,10 +2489,16 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
     issue_old(0, p.t0, p.t0 % lay_s[0].ring_len);
     commit_old();
     WORKER_SYNC();
-    const int fc = tid >> 3, fs = tid & 7;                // finishing threads: (channel-in-CTA fc (mod 16), stream fs)
+    // finishing threads: output (virtual rank fvr of this CTA, channel fc of its 16, stream fs).  VR = 2: every thread finishes
+    // one conv / residual output AND one skip output; VR = 1: threads 0-127 the conv / residual ones, 128-255 the skip ones.
+    const int fvr = (VR == 2) ? (tid >> 7) : 0, fc = (tid >> 3) & 15, fs = tid & 7;
+    const bool fin_a = (VR == 2) || tid < NV * SB, fin_s = (VR == 2) || tid >= NV * SB;
+    const int fch = o0 + fvr * NV + fc;                   // the channel (= row of the stage's weight matrix) this thread finishes
     const int fsg = cl * SB + fs;
     const bool fs_on = fsg < NS;
     unsigned pb_i = 0, sb_i = 0;                          // partial-sum / staging double-buffer indices
+    auto part_of = [&](unsigned pb, int vr) { return part + (pb * VR + vr) * 8 * 128; };
+    auto stg_of = [&](unsigned sb, int vr) { return stg + (sb * VR + vr) * BLK; };
 
     for (int ev = 0; ev < p.n_evals; ++ev) {
         const int t = p.t0 + ev;
@@ -2491,49 +2531,56 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
                 const int r = lane + 32 * j;
                 const float v = __ldg(p.start_w + (size_t)r * W + idx) + (p.start_b ? __ldg(p.start_b + r) : 0.f);
                 cl8_put(Xcur + (r >> 4) * BLK, warp, r & 15, v);
-                if (r >= o0 && r < o0 + NV) {
+                if (r >= o0 && r < o0 + NVC) {
                     hown[(r - o0) * SB + warp] = v;
                     if (hs_g < NS) st_pair(ring0 + r, v, rtag);
                 }
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes to Xcur[0] / sampling scratch before later bulk copies
         WORKER_SYNC();
-        float skr = 0.f;                                  // skip sum of (channel o0 + fc - 16, stream fs), threads 128-255
+        float skr = 0.f;                                  // skip sum of (channel fch, stream fs) in the fin_s threads
         TR8();             // layer stamps start here (index 0)
 
         for (int l = 0; l < NL; ++l) {
+            const GenLayer& L = lay_s[l];
             const bool more = (l + 1 < NL);
             unsigned char* xc = Xcur + (l & 1) * VEC;
             unsigned char* zb = Xz + (l & 1) * VEC;
+            // biases of this thread's outputs: requested now, used one or two stages later
+            const float b_f = (fin_a && L.bf) ? __ldg(L.bf + fch) : 0.f, b_g = (fin_a && L.bg) ? __ldg(L.bg + fch) : 0.f;
+            const float b_r = (fin_a && L.br) ? __ldg(L.br + fch) : 0.f, b_s = (fin_s && L.bs) ? __ldg(L.bs + fch) : 0.f;
             // ================= stage 1: m-tile 0 = filter rows, 1 = gate rows; k-steps 4*kq+i of the old taps, then of h
             {
                 // history taps of the NEXT stage 1 start their trip through the L2 now; they are used a whole stage later
                 if (more) issue_old(l + 1, t, slot_s[l + 1]);
                 else if (ev + 1 < p.n_evals) issue_old(0, t + 1, (slot_s[0] + 1 == lay_s[0].ring_len) ? 0 : slot_s[0] + 1);
                 else hsrc = nullptr;
+                Acc3 d[VR];
                 const unsigned char* wimg = stage_weights();
                 TR8();         // 1: stage-1 weights (old tap) landed
-                Acc3 d;
-                acc_zero(d);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, Xold + (4 * kq + i) * BLK, d);
+                for (int vr = 0; vr < VR; ++vr) {
+                    acc_zero(d[vr]);
+                    mma_quarter(wimg + vr * CL8_IMG2, Xold, d[vr]);
+                }
                 release_slot();
                 wimg = stage_weights();
                 if (l > 0) xwait(l & 1);
                 TR8();         // 2: old-tap MMAs done, h arrived
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, xc + (4 * kq + i) * BLK, d);
+                for (int vr = 0; vr < VR; ++vr) {
+                    mma_quarter(wimg + vr * CL8_IMG2, xc, d[vr]);
+                    acc_store(d[vr], part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
+                }
                 release_slot();
-                float* pb = part + pb_i * 8 * 128;
-                acc_store(d, pb + ((kq * 2 + mt) * 32 + lane) * 4);
                 TR8();         // 3: MMAs done, partials stored
                 WORKER_SYNC();
                 TR8();         // 4: barrier
-                if (tid < NV * SB) {
-                    const float f = part_sum(pb, 0, fc, fs, 4) + bias_s[(l * 4 + 0) * NV + fc];
-                    const float g = part_sum(pb, 1, fc, fs, 4) + bias_s[(l * 4 + 1) * NV + fc];
-                    cl8_put(stg + sb_i * BLK, fs, fc, tanh_(f) * sigmoid_(g));
+                if (fin_a) {
+                    const float* pb = part_of(pb_i, fvr);
+                    const float f = part_sum(pb, 0, fc, fs) + b_f;
+                    const float g = part_sum(pb, 1, fc, fs) + b_g;
+                    cl8_put(stg_of(sb_i, fvr), fs, fc, tanh_(f) * sigmoid_(g));
                 }
                 pb_i ^= 1;
                 TR8();         // 5: z computed and staged
@@ -2544,39 +2591,38 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
             {
                 // every warp is past its stage-1 reads of Xold (two barriers ago): refill it while z is in flight
                 commit_old();
-                TR8();         // 7: next history taps in place
+                TR8();         // 6: next history taps in place
+                const bool active = (mt == 0) ? more : want_head;
                 const unsigned char* wimg = stage_weights();
-                TR8();         // 8: stage-2 weights landed
+                TR8();         // 7: stage-2 weights landed
                 xwait(2 + (l & 1));
-                TR8();         // 9: z arrived
-                Acc3 d;
-                acc_zero(d);
-                if (mt == 0 ? more : want_head) {
+                TR8();         // 8: z arrived
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) mma_step(wimg, 16, 4 * kq + i, zb + (4 * kq + i) * BLK, d);
+                for (int vr = 0; vr < VR; ++vr) {
+                    Acc3 d;
+                    acc_zero(d);
+                    if (active) mma_quarter(wimg + vr * CL8_IMG2, zb, d);
+                    acc_store(d, part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
                 }
                 release_slot();
-                float* pb = part + pb_i * 8 * 128;
-                acc_store(d, pb + ((kq * 2 + mt) * 32 + lane) * 4);
-                TR8();         // 10: MMAs done, partials stored
+                TR8();         // 9: MMAs done, partials stored
                 WORKER_SYNC();
-                TR8();         // 11: barrier
-                if (tid < NV * SB) {
-                    if (more) {
-                        const int row = o0 + fc;
-                        const GenLayer& Ln = lay_s[l + 1];
-                        float v = part_sum(pb, 0, fc, fs, 4) + bias_s[(l * 4 + 2) * NV + fc];
-                        v += hown[(l & 1) * NV * SB + fc * SB + fs];
-                        hown[((l + 1) & 1) * NV * SB + fc * SB + fs] = v;
-                        if (fs_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + fsg) * W + row, v, rtag);
-                        cl8_put(stg + sb_i * BLK, fs, fc, v);
-                    }
-                } else if (want_head) {
-                    const float v = part_sum(pb, 1, fc - NV, fs, 4) + bias_s[(l * 4 + 3) * NV + fc - NV];
+                TR8();         // 10: barrier
+                const float* pb = part_of(pb_i, fvr);
+                if (fin_a && more) {
+                    const GenLayer& Ln = lay_s[l + 1];
+                    float v = part_sum(pb, 0, fc, fs) + b_r;
+                    v += hown[(l & 1) * NVC * SB + (fvr * NV + fc) * SB + fs];
+                    hown[((l + 1) & 1) * NVC * SB + (fvr * NV + fc) * SB + fs] = v;
+                    if (fs_on) st_pair(p.ringLL + Ln.ring_off + ((size_t)slot_s[l + 1] * NS + fsg) * W + fch, v, rtag);
+                    cl8_put(stg_of(sb_i, fvr), fs, fc, v);
+                }
+                if (fin_s && want_head) {
+                    const float v = part_sum(pb, 1, fc, fs) + b_s;
                     skr = v + skr;
                 }
                 pb_i ^= 1;
-                TR8();         // 12: h' computed and staged
+                TR8();         // 11: h' computed and staged
                 if (more) {
                     CL8_STAGED_ARRIVE();
                     sb_i ^= 1;
@@ -2586,29 +2632,25 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         if (tr_on) p.trace[2041] = clock64();             // layers done
         if (!want_head) continue;
 
-        // ================= head: relu(skip) -> end_conv_1 -> relu -> end_conv_2; one m-tile, 16 k-steps over 8 warps
-        if (tid >= NV * SB) {
-            cl8_put(stg + sb_i * BLK, fs, fc - NV, fmaxf(skr, 0.f));
-        }
+        // ================= head: relu(skip) -> end_conv_1 -> relu -> end_conv_2; one m-tile per virtual rank, 16 k-steps
+        // over the 8 warps (2 each)
+        if (fin_s) cl8_put(stg_of(sb_i, fvr), fs, fc, fmaxf(skr, 0.f));
         CL8_STAGED_ARRIVE();
         sb_i ^= 1;
-        auto head_stage = [&](const unsigned char* x) {     // this warp's 2 k-steps of the single m-tile -> part
+        auto head_stage = [&](const unsigned char* x) {     // this warp's 2 k-steps of each virtual rank's m-tile -> part
             const unsigned char* wimg = stage_weights();
-            Acc3 d;
-            acc_zero(d);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int ks = 2 * warp + i;
-                const unsigned char* a = wimg + ((size_t)ks * 2) * 512 + lane * 16;
-                const uint4 ah = *reinterpret_cast<const uint4*>(a), al = *reinterpret_cast<const uint4*>(a + 512);
-                const uint4 b = *reinterpret_cast<const uint4*>(x + ks * BLK + (lane >> 2) * 64 + (lane & 3) * 16);
-                mma_bf16_16816(d.lh, al, b.x, b.z);
-                mma_bf16_16816(d.hl, ah, b.y, b.w);
-                mma_bf16_16816(d.hh, ah, b.x, b.z);
+            for (int vr = 0; vr < VR; ++vr) {
+                Acc3 d;
+                acc_zero(d);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int ks = 2 * warp + i;
+                    mma_step(wimg + vr * CL8_IMGH + ((size_t)ks * 2) * 512 + lane * 16, x + ks * BLK, d);
+                }
+                acc_store(d, part_of(pb_i, vr) + (warp * 32 + lane) * 4);
             }
             release_slot();
-            float* pb = part + pb_i * 8 * 128;
-            acc_store(d, pb + (warp * 32 + lane) * 4);
         };
         auto head_sum = [&](const float* pb, int r, int s) {  // 8 partials, one per warp
             const float* q = pb + (((r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
@@ -2620,9 +2662,9 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         xwait(4);
         head_stage(Xs);
         WORKER_SYNC();
-        if (tid < NV * SB) {
-            const float y = fmaxf(head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e1b + o0 + fc), 0.f);
-            cl8_put(stg + sb_i * BLK, fs, fc, y);
+        if (fin_a) {
+            const float y = fmaxf(head_sum(part_of(pb_i, fvr), fc, fs) + __ldg(p.e1b + fch), 0.f);
+            cl8_put(stg_of(sb_i, fvr), fs, fc, y);
         }
         pb_i ^= 1;
         CL8_STAGED_ARRIVE();
@@ -2630,12 +2672,11 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
         xwait(5);
         head_stage(Xy);
         WORKER_SYNC();
-        if (tid < NV * SB) {
-            const int row = o0 + fc;
-            const float dc = (float)row - (float)W / 2.f;
-            const float v = (head_sum(part + pb_i * 8 * 128, fc, fs) + __ldg(p.e2b + row)) - (dc * dc) * p.regularize;
-            if (fs_on && p.out_logits) p.out_logits[((size_t)fsg * p.n_samples + samp) * W + row] = v;
-            reinterpret_cast<float*>(stg + sb_i * BLK)[fs * NV + fc] = v;                // logits travel as fp32: [stream][16]
+        if (fin_a) {
+            const float dc = (float)fch - (float)W / 2.f;
+            const float v = (head_sum(part_of(pb_i, fvr), fc, fs) + __ldg(p.e2b + fch)) - (dc * dc) * p.regularize;
+            if (fs_on && p.out_logits) p.out_logits[((size_t)fsg * p.n_samples + samp) * W + fch] = v;
+            reinterpret_cast<float*>(stg_of(sb_i, fvr))[fs * NV + fc] = v;               // logits travel as fp32: [stream][16]
         }
         pb_i ^= 1;
         CL8_STAGED_ARRIVE();
@@ -2656,11 +2697,11 @@ __global__ void __launch_bounds__(GEN_NT + 64, 1) gen_kernel_cl8(const GenParams
             }
         }
         if (tr_on) p.trace[2043] = clock64();             // sampled
-        // the top-of-evaluation barrier publishes idx_s; the fence there orders the scratch writes before later bulk copies
+        // the top-of-evaluation barrier publishes idx_s
     }
     WORKER_SYNC();
     if (rank == 0 && tid < SB && cl * SB + tid < NS) p.cur_idx[cl * SB + tid] = idx_s[tid];
-    cluster_sync_all();                                  // peers may still be copying into this CTA's shared memory
+    cluster_sync_all();                                  // peers may still be storing into this CTA's shared memory
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -2731,7 +2772,10 @@ struct wn_gen_handle {
     size_t smem_cluster;
     int n_wslots_cluster, wslot_cluster;
     bool cl8_ok, cl8_packed;   // gen_kernel_cl8 applies (cl8_shape_ok and the shared memory fits); its weight images are built
-    size_t smem_cl8;
+    bool generic_ok, ll_ok;    // the grid-barrier / the generic flag-exchange kernel fit in shared memory for this stream count
+    bool cl8_8_ok;             // ... and so does its 8-CTA-cluster instantiation
+    int cl8_cs;                // cluster size picked at the first launch (0 = not yet)
+    size_t smem_cl8, smem_cl8_8;
     bool x2_ok;             // fast_ok on a 64-CTA grid with 4 rows per stage vector per CTA: gen_kernel_x2 applies
     size_t smem_x2;
     int n_wslots_x2;
@@ -2833,7 +2877,11 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     p.regA = (p.regA + 3) / 4 * 4; p.regB = (p.regB + 3) / 4 * 4; p.pre_n = (p.pre_n + 3) / 4 * 4;
     p.skacc_n = (p.skacc_n + 3) / 4 * 4;
     h->smem = sizeof(float) * ((size_t)p.regA + p.regB + p.pre_n + p.skacc_n + NS + (size_t)GEN_WARPS * s->classes);
-    if (h->smem > (size_t)smem_optin) {
+    // the grid-barrier / generic kernels stage all streams' vectors in every CTA; the cluster kernels do not
+    h->generic_ok = h->smem <= (size_t)smem_optin;
+    const bool cluster_shape = s->k == 2 && s->n_layers >= 2 && s->D % CL == 0 && s->R % CL == 0 && s->S % CL == 0 &&
+                               s->E % CL == 0 && s->classes % CL == 0;
+    if (!h->generic_ok && !cluster_shape) {
         const size_t need = h->smem;
         delete h;
         return set_err(WN_E_UNSUPP, "wn_gen_create: %zu bytes of shared memory needed for %d streams, %d available", need,
@@ -2968,13 +3016,27 @@ extern "C" int wn_gen_create(const wn_gen_shape* s, const wn_gen_weights* w, flo
     }
     // ---- batched cluster kernel (8 streams per cluster, tensor cores)
     {
-        const size_t fixed = (size_t)8 * CL8_VEC + 2 * CL8_BLK + sizeof(float) * (2 * 8 * 128 + 2 * (CL8_W / CL) * CL8_SB) + 16 * 8 +
-                             sizeof(GenLayer) * (size_t)s->n_layers + sizeof(int) * (size_t)(s->n_layers + 2 * CL8_SB) +
-                             sizeof(float) * (size_t)s->n_layers * 4 * (CL8_W / CL);
-        h->smem_cl8 = align_up(fixed, 16) + 4 * (size_t)CL8_IMG2;
+        auto smem_for = [&](int vr) {
+            const size_t fixed = (size_t)8 * CL8_VEC + (size_t)2 * vr * CL8_BLK + sizeof(float) * (size_t)(2 * vr * 8 * 128 + 2 * 16 * vr * CL8_SB) +
+                                 16 * 8 + sizeof(GenLayer) * (size_t)s->n_layers + sizeof(int) * (size_t)(s->n_layers + 2 * CL8_SB);
+            return align_up(fixed, 16) + 4 * (size_t)CL8_IMG2;
+        };
+        h->smem_cl8 = smem_for(1);
+        h->smem_cl8_8 = smem_for(2);
         h->cl8_ok = cl8_shape_ok(*s) && h->smem_cl8 <= (size_t)smem_optin && !getenv("WN_GEN_NOCL8");
+        h->cl8_8_ok = h->cl8_ok && h->smem_cl8_8 <= (size_t)smem_optin;
+        h->cl8_cs = 0;
         h->cl8_packed = false;
         p.cl8_img = reinterpret_cast<const unsigned char*>(h->scratch + h->lay.cl8_img);
+    }
+    h->generic_ok = h->smem <= (size_t)smem_optin;
+    h->ll_ok = h->smem_ll <= (size_t)smem_optin && s->n_layers >= 2;
+    if (h->mode == 1 && (h->cl8_ok || h->cluster_ok)) h->mode = 0;       // many streams: only the cluster kernels fit
+    if (!h->generic_ok && !h->cl8_ok && !h->cluster_ok) {
+        const size_t need = h->smem > h->smem_ll ? h->smem : h->smem_ll;
+        delete h;
+        return set_err(WN_E_UNSUPP, "wn_gen_create: %zu bytes of shared memory needed for %d streams, %d available", need,
+                       s->n_streams, smem_optin);
     }
     h->tables_uploaded = false;
     h->cur_t = 0;
@@ -3048,26 +3110,45 @@ static int launch_gen_cluster(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
     return 0;
 }
 
-static int launch_gen_cl8(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
-    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cl8));
-    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+template <int CS>
+static int launch_gen_cl8_cs(wn_gen_handle* h, GenParams& p, cudaStream_t st, int* max_clusters_out, bool launch) {
+    const size_t smem = (CS == 16) ? h->smem_cl8 : h->smem_cl8_8;
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WN_CUDA(cudaFuncSetAttribute(gen_kernel_cl8<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL));
-    cfg.blockDim = dim3(GEN_NT + 64);                 // 8 worker warps, the weight producer warp, the pusher warp
-    cfg.dynamicSmemBytes = h->smem_cl8;
+    cfg.gridDim = dim3((unsigned)((h->shape.n_streams + CL8_SB - 1) / CL8_SB * CS));
+    cfg.blockDim = dim3(GEN_NT + 64 + (CS == 8 ? 32 : 0));    // 8 worker warps, the weight producer warp(s), the pusher warp
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_cl8, &cfg));
-    WN_REQUIRE(max_clusters >= 1, WN_E_UNSUPP, "wn_gen_run: a %d-CTA cluster cannot be scheduled on this device", CL);
-    WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_cl8, p));      // clusters are independent: more than fit run in waves
+    WN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gen_kernel_cl8<CS>, &cfg));
+    if (max_clusters_out) *max_clusters_out = max_clusters;
+    if (!launch) return 0;
+    WN_REQUIRE(max_clusters >= 1, WN_E_UNSUPP, "wn_gen_run: a %d-CTA cluster cannot be scheduled on this device", CS);
+    WN_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_cl8<CS>, p));   // clusters are independent: more than fit run in waves
     return 0;
+}
+// Cluster size: 16 CTAs (least work per CTA) while all clusters are co-resident, else 8 (15 clusters fit instead of 7).
+static int launch_gen_cl8(wn_gen_handle* h, GenParams& p, cudaStream_t st) {
+    if (h->cl8_cs == 0) {
+        int fit16 = 0;
+        const int rc = launch_gen_cl8_cs<16>(h, p, st, &fit16, false);
+        if (rc) return rc;
+        const int need = (h->shape.n_streams + CL8_SB - 1) / CL8_SB;
+        h->cl8_cs = (need <= fit16 || !h->cl8_8_ok) ? 16 : 8;
+        if (const char* e = getenv("WN_GEN_CL8_CS")) {
+            const int v = atoi(e);
+            if (v == 16 || (v == 8 && h->cl8_8_ok)) h->cl8_cs = v;
+        }
+    }
+    return h->cl8_cs == 16 ? launch_gen_cl8_cs<16>(h, p, st, nullptr, true) : launch_gen_cl8_cs<8>(h, p, st, nullptr, true);
 }
 
 // 64 CTAs as 4 clusters of 16, all co-resident (the clusters exchange through the L2 while they run): launched with the
@@ -3130,6 +3211,12 @@ extern "C" int wn_gen_set_mode(wn_gen_handle* h, int mode) {
     return 0;
 }
 
+extern "C" int wn_gen_weights_changed(wn_gen_handle* h) {
+    WN_REQUIRE(h, WN_E_STATE, "wn_gen_weights_changed: null handle");
+    h->cl8_packed = false;          // the next wn_gen_reset splits the weights again
+    return 0;
+}
+
 extern "C" int wn_gen_check(wn_gen_handle* h, void* stream) {
     WN_REQUIRE(h, WN_E_STATE, "wn_gen_check: null handle");
     int flag = 0;
@@ -3167,7 +3254,6 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
         int rc;
         const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
         if ((h->mode == 0 || h->mode == 6) && h->cl8_ok) {       // several streams of a 256-wide net: 8 streams per cluster
-            p.n_wslots = 4;
             rc = launch_gen_cl8(h, p, st);
         } else if ((auto_cluster || h->mode == 4) && h->cluster_ok) {
             p.n_wslots = h->n_wslots_cluster;
@@ -3180,7 +3266,10 @@ extern "C" int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stre
             p.n_wslots = h->n_wslots_fast;
             p.regA = h->xn_fast;                    // the fast kernel reads its input-vector pitch from regA
             rc = p.n_wslots ? launch_gen_fast<true>(h, p, st) : launch_gen_fast<false>(h, p, st);
-        } else if (h->mode == 0 || h->mode == 2) {
+        } else if (!(((h->mode == 0 || h->mode == 2) && h->ll_ok) || h->generic_ok)) {
+            return set_err(WN_E_UNSUPP, "wn_gen_run: %d streams need a cluster kernel (modes 4, 6) for this net; mode %d does not fit in "
+                           "shared memory", h->shape.n_streams, h->mode);
+        } else if ((h->mode == 0 || h->mode == 2) && h->ll_ok) {
             if (h->shape.n_streams == 1)
                 rc = p.n_wslots ? launch_gen_ll<1, true>(h, p, st) : launch_gen_ll<1, false>(h, p, st);
             else
@@ -3215,8 +3304,8 @@ extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block,
     const bool cl8 = (h->mode == 0 || h->mode == 6) && h->cl8_ok;
     const bool cluster = !cl8 && (auto_cluster || h->mode == 4) && h->cluster_ok;
     const bool fast = !cluster && ((h->mode == 5 && h->x2_ok) || ((h->mode == 0 || h->mode == 3) && h->fast_ok));
-    if (grid) *grid = cl8 ? (h->shape.n_streams + CL8_SB - 1) / CL8_SB * CL : cluster ? h->shape.n_streams * CL : h->grid;
-    if (block) *block = cl8 ? GEN_NT + 64 : (cluster || fast) ? GEN_NT + 32 : GEN_NT;        // + the producer (and pusher) warp
+    if (grid) *grid = cl8 ? (h->shape.n_streams + CL8_SB - 1) / CL8_SB * (h->cl8_cs ? h->cl8_cs : CL) : cluster ? h->shape.n_streams * CL : h->grid;
+    if (block) *block = cl8 ? GEN_NT + 64 + (h->cl8_cs == 8 ? 32 : 0) : (cluster || fast) ? GEN_NT + 32 : GEN_NT;   // + helper warps
     if (barriers_per_eval) *barriers_per_eval = 2 * h->shape.n_layers + 2;      // exchange stages per evaluation
     return 0;
 }

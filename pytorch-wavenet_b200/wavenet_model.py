@@ -210,6 +210,7 @@ class _Runtime:
         self.packed = None
         self.ws = {}
         self.samplers = {}
+        self.weights_epoch = 0                # bumped by invalidate(): parameters were written behind the version counters
         self.block_mode = "auto"     # "auto": tensor-core blocks when the shape allows, "ffma": exact-fp32 SIMT, "tc"
         self.fast_tf32 = False       # opt-in single-pass TF32 blocks (~1e-3 on the logits: outside the parity bar)
         self.tc_precision = "bf16x2"  # tensor-core operand split: "tf32x3" (3xTF32) or "bf16x2" (bf16 pairs, 2x the MMA rate)
@@ -240,6 +241,7 @@ class _Runtime:
         make_data_parallel call this, and code that edits ``p.data`` by hand between no-grad forwards must too
         (``model.invalidate_packed_weights()``)."""
         self.pack_key = None
+        self.weights_epoch += 1
 
     def device(self):
         dev = self.model.start_conv.weight.device
@@ -816,8 +818,12 @@ class _Runtime:
         dev = self.device()
         P = self._params()
         key = (n_streams, tuple(p.data_ptr() for p in m.parameters()))
+        wkey = (tuple(p._version for p in m.parameters()), self.weights_epoch)
         s = self.samplers.get(n_streams)
         if s is not None and s["key"] == key:
+            if s["wkey"] != wkey:                 # same tensors, new values: the batched kernel re-splits its weight images
+                native.check(lib.wn_gen_weights_changed(s["handle"]), "gen weights changed")
+                s["wkey"] = wkey
             return s
         if s is not None:
             lib.wn_gen_destroy(s["handle"])
@@ -844,7 +850,7 @@ class _Runtime:
         handle = ctypes.c_void_p()
         native.check(lib.wn_gen_create(ctypes.byref(shape), ctypes.byref(wts), rings.data_ptr(), scratch.data_ptr(),
                                        ctypes.byref(handle)), "gen create")
-        s = dict(key=key, handle=handle, rings=rings, scratch=scratch, n_streams=n_streams)
+        s = dict(key=key, wkey=wkey, handle=handle, rings=rings, scratch=scratch, n_streams=n_streams)
         self.samplers[n_streams] = s
         return s
 

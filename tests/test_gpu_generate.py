@@ -294,6 +294,23 @@ def test_batched_cluster_kernel_cfg2(golden):
     # the default for several streams of this net is this kernel
     d, ld = m.generate_fast_batch(60, first, temperature=1.0, uniforms=uni, return_logits=True)
     assert np.array_equal(d, idx6) and np.array_equal(ld, lg6)
+    # 64 streams (8 clusters: more than the 7 sixteen-CTA clusters a B200 holds, so the 8-CTA-cluster variant runs) equal
+    # the same streams run 11 at a time
+    first64 = np.concatenate([first] * 6)[:64]
+    uni64 = np.concatenate([uni] * 6)[:64]
+    i64, l64 = m.generate_fast_batch(60, first64, temperature=1.0, uniforms=uni64, return_logits=True)
+    for s in range(64):
+        assert np.array_equal(i64[s], idx6[s % 11]) and np.array_equal(l64[s], lg6[s % 11])
+    # in-place weight updates reach the pre-split weight images (wn_gen_weights_changed)
+    with torch.no_grad():
+        m.end_conv_2.weight.mul_(0.5)
+        m.filter_convs[3].weight.add_(0.01)
+        m.skip_convs[7].weight.mul_(1.5)
+    _, la = m.generate_fast_batch(60, first[:3], temperature=1.0, uniforms=uni[:3], forced=idx6[:3], return_logits=True)
+    rt.gen_mode = 2
+    _, lb = m.generate_fast_batch(60, first[:3], temperature=1.0, uniforms=uni[:3], forced=idx6[:3], return_logits=True)
+    rt.gen_mode = None
+    assert rel_err(la, lb) < 2e-5 and rel_err(la, lg6f) > 1e-2
 
 
 def test_cfg4_64_streams_vs_oracle(golden):

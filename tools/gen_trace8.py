@@ -27,8 +27,3 @@ print("layers 0-2:", d[:3].tolist())
 w = np.array(buf[2040:2044], dtype=np.int64)
 print(f"whole evaluation (T={temp}): prologue {t[0] - w[0]} cycles, layers {w[1] - t[0]}, head {w[2] - w[1]}, sampling {w[3] - w[2]}, "
       f"total {w[3] - w[0]} = {(w[3] - w[0]) / 1.9e3:.1f} us at 1.9 GHz")
-iss = np.array(buf[1000:1150], dtype=np.int64).reshape(50, 3)[:, [0, 2]]
-tt = t[1:].reshape(50, 11)
-print("weight images: cycles from the producer's issue to 'landed' as seen by thread 0 (upper bound where it did not wait):")
-print(f"  stage 1 (64 KB): mean {(tt[:, 0] - iss[:, 0]).mean():.0f}   stage 2 (32 KB): mean {(tt[:, 6] - iss[:, 1]).mean():.0f}")
-print(f"  issue relative to the previous stage's MMA end: stage-1 image {(iss[1:, 0] - tt[:-1, 2]).mean():.0f}, stage-2 image {(iss[1:, 1] - tt[:-1, 8]).mean():.0f}")
