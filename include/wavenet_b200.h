@@ -371,9 +371,10 @@ typedef struct wn_gen_run_args {
 int wn_gen_run(wn_gen_handle* h, const wn_gen_run_args* a, void* stream);
 int wn_gen_destroy(wn_gen_handle* h);
 /* Which sampler kernel runs (all implement the same schedule; call right after wn_gen_reset):
- *   0  auto: one stream -> the single-stream L2 kernel 3 (lowest latency: the whole GPU works on one sample);
- *            several streams -> the batched cluster kernel 6 where it applies, else one cluster per stream (kernel 4);
- *            otherwise the generic kernel
+ *   0  auto: 256-wide k = 2 nets -> the tensor-core cluster kernel 6, for any number of streams (measured: one stream
+ *            107.7 us/sample against 150.7 for kernel 3; 64 streams 382 k samples/s against 23 k for kernel 4);
+ *            other nets: one stream -> the single-stream L2 kernel 3, several streams -> one cluster per stream
+ *            (kernel 4) where it applies, otherwise the generic kernel
  *   1  atomic grid barrier between stages (the simple reference kernel)
  *   2  generic flag-in-data exchange through L2 (any shape, any number of streams)
  *   3  single-stream L2 kernel with register-free cooperative polling (k = 2, power-of-two row split)
@@ -382,10 +383,13 @@ int wn_gen_destroy(wn_gen_handle* h);
  *      of the producer's cluster through distributed shared memory and reach the other clusters through ONE L2 poller per
  *      (cluster, producer) that forwards them by DSMEM (256-wide nets: R = D = S = E = classes = 256).  Measured 2x slower
  *      than kernel 3 (a 16-CTA DSMEM all-to-all costs as much as the L2 one it replaces): selectable, never the default
- *   6  batched tensor-core cluster kernel: 8 streams per 16-CTA cluster (256-wide nets, >= 2 streams).  The weights of a
- *      stage enter shared memory once per 8 streams, as bf16 hi/lo pairs pre-split into MMA fragment order at
- *      wn_gen_reset (wn_gen_workspace_bytes includes the images); dot products are mma.sync m16n8k16 with three MMAs per
- *      product (fp32-class: ~1e-6 on the logits); the exchange is one 512-byte cp.async.bulk per destination CTA
+ *   6  tensor-core cluster kernel: up to 8 streams per thread-block cluster (256-wide nets: R = D = S = E = classes = 256,
+ *      k = 2).  The weights of a stage enter shared memory once per 8 streams, as bf16 hi/lo pairs pre-split into MMA
+ *      fragment order at wn_gen_reset (wn_gen_workspace_bytes includes the images; wn_gen_weights_changed after in-place
+ *      weight updates); dot products are mma.sync m16n8k16 with three MMAs per product (fp32-class: ~1e-6 on the
+ *      logits); the exchange is one 512-byte st.async.v4 block per destination CTA, credited to an mbarrier there.
+ *      Clusters of 16 CTAs while all of them are co-resident (<= 7 clusters = 56 streams on a B200), else clusters of 8
+ *      CTAs that own two 16-channel slices each (<= 15 clusters = 120 streams per wave)
  * Kernels 2, 3 and 5 sum in the same order (bit-identical results); kernel 4 splits rows differently (rounding-level
  * differences). */
 int wn_gen_set_mode(wn_gen_handle* h, int mode);
@@ -397,6 +401,8 @@ int wn_gen_check(wn_gen_handle* h, void* stream);
 /* Debug aid: with WN_GEN_TRACE=1 in the environment at wn_gen_create, CTA 0 stamps clock64() at 8 points of every layer
  * of the LAST evaluation of a launch (single-stream kernel only); this copies the first n stamps to the host. */
 int wn_gen_read_trace(wn_gen_handle* h, long long* host_out, int n, void* stream);
+/* Which kernel wn_gen_run launches in the handle's current mode: the number (1-6) documented at wn_gen_set_mode. */
+int wn_gen_kernel_id(const wn_gen_handle* h);
 /* how wn_gen_run launches: grid size, block size, dependent exchange stages per evaluation */
 int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval);
 

@@ -2290,19 +2290,20 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
     // stores from the worker warps (E), and ~1 200 more for a multicast copy from a global staging slot (the fence after the
     // global stores).  The workers only signal "staged" (bar.arrive on barrier 2) and move on to the next stage.
     const unsigned sm_base = smem_u32(smb);
+    unsigned rdelta[CS];                                 // shared::cluster address of CTA d minus the local address (pusher warp)
+#pragma unroll
+    for (int d = 0; d < CS; ++d) rdelta[d] = (warp == GEN_WARPS + 1) ? mapa_u32(sm_base, (unsigned)d) - sm_base : 0u;
     auto push = [&](int sb, unsigned char* vec, int bar_i) {
 #pragma unroll
         for (int vr = 0; vr < VR; ++vr) {
             const uint4 v = *reinterpret_cast<const uint4*>(stg + (sb * VR + vr) * BLK + lane * 16);
             const unsigned la = smem_u32(vec + (v0 + vr) * BLK + lane * 16), lb = smem_u32(xbar + bar_i);
 #pragma unroll
-            for (int d = 0; d < CS; ++d) {
-                const unsigned delta = mapa_u32(sm_base, (unsigned)d) - sm_base;
+            for (int d = 0; d < CS; ++d)
                 asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                                 la + delta),
-                             "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(lb + delta)
+                                 la + rdelta[d]),
+                             "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(lb + rdelta[d])
                              : "memory");
-            }
         }
     };
 #define CL8_STAGED_SYNC() asm volatile("bar.sync 2, 288;" ::: "memory")
@@ -2708,9 +2709,9 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
 struct ScratchLayout {
     size_t bar, cur_idx, layers, zbuf, skipbuf, y1buf, logitbuf, err, zLL, skipLL, y1LL, logitLL, ll_end, trace, cl8_img, cl8_bytes, total;
 };
-// the batched cluster kernel's shape: several streams of a k = 2 net whose five widths are all 256
+// the batched cluster kernel's shape: a k = 2 net whose five widths are all 256 (any number of streams)
 static bool cl8_shape_ok(const wn_gen_shape& s) {
-    return s.n_streams >= 2 && s.k == 2 && s.n_layers >= 2 && s.R == CL8_W && s.D == CL8_W && s.S == CL8_W && s.E == CL8_W &&
+    return s.n_streams >= 1 && s.k == 2 && s.n_layers >= 2 && s.R == CL8_W && s.D == CL8_W && s.S == CL8_W && s.E == CL8_W &&
            s.classes == CL8_W;
 }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -3295,6 +3296,18 @@ extern "C" int wn_gen_read_trace(wn_gen_handle* h, long long* host_out, int n, v
 extern "C" int wn_gen_destroy(wn_gen_handle* h) {
     delete h;
     return 0;
+}
+
+/* the kernel wn_gen_run picks in the handle's current mode: the mode number (1-6) of wn_gen_set_mode */
+extern "C" int wn_gen_kernel_id(const wn_gen_handle* h) {
+    if (!h) return 0;
+    const bool auto_cluster = h->mode == 0 && h->cluster_ok && (h->shape.n_streams > 1 || !h->fast_ok);
+    if ((h->mode == 0 || h->mode == 6) && h->cl8_ok) return 6;
+    if ((auto_cluster || h->mode == 4) && h->cluster_ok) return 4;
+    if (h->mode == 5 && h->x2_ok) return 5;
+    if ((h->mode == 0 || h->mode == 3) && h->fast_ok) return 3;
+    if ((h->mode == 0 || h->mode == 2) && h->ll_ok) return 2;
+    return 1;
 }
 
 extern "C" int wn_gen_launch_info(const wn_gen_handle* h, int* grid, int* block, int* barriers_per_eval) {

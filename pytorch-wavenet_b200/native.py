@@ -184,6 +184,7 @@ SIGNATURES = {
     "wn_gen_destroy": (C.c_int, [C.c_void_p]),
     "wn_gen_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "wn_gen_weights_changed": (C.c_int, [C.c_void_p]),
+    "wn_gen_kernel_id": (C.c_int, [C.c_void_p]),
     "wn_gen_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wn_gen_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_void_p]),
     "wn_gen_launch_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),

@@ -38,7 +38,7 @@ if what == "step":
         if i == 2:
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()              # set_to_none: what WavenetTrainer.train does
         loss = wt.fused_cross_entropy(model.forward_indices(idx), tgt)      # the loss the bench and WavenetTrainer use
         loss.backward()
         opt.step()
