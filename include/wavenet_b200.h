@@ -318,6 +318,9 @@ int    wn_scatter_rows(const void* d_idx, int idx_is_u8, const float* d_dh, floa
 size_t wn_colsum_workspace_bytes(long long rows, int C);
 int    wn_colsum(const float* d_x, float* d_out, float* d_work, long long rows, int C, int ld, void* stream);
 int    wn_relu_copy(const float* d_x, float* d_y, long long n, void* stream);
+/* x *= *d_scale in place (d_scale: one float on the device -- the gradient autograd passes into the loss node,
+ * wavenet_training.py:71 `loss.backward()`); no pass over x when the scalar is 1.  n % 4 == 0. */
+int    wn_scale_by(float* d_x, long long n, const float* d_scale, void* stream);
 
 /* ---------------------------------------------------------------- (G) Fast-WaveNet sampler
  * replaces WaveNetModel.generate_fast's warm-up and sampling loops (wavenet_model.py:250-302) together with

@@ -157,6 +157,17 @@ __global__ void relu_copy_kernel(const float4* __restrict__ x, float4* __restric
     }
 }
 
+// x *= *scale (a device scalar: the gradient autograd hands to the loss node), skipped entirely when the scalar is 1
+__global__ void scale_by_kernel(float4* __restrict__ x, long long n4, const float* __restrict__ scale) {
+    const float s = *scale;
+    if (s == 1.f) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        x[i] = v;
+    }
+}
+
 }  // namespace misc
 }  // namespace wn
 
@@ -221,6 +232,14 @@ extern "C" int wn_relu_copy(const float* d_x, float* d_y, long long n, void* str
     WN_REQUIRE(d_x && d_y && n >= 0 && n % 4 == 0, WN_E_BADARG, "wn_relu_copy: bad arguments (n must be a multiple of 4)");
     if (n == 0) return 0;
     misc::relu_copy_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((const float4*)d_x, (float4*)d_y, n / 4);
+    WN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wn_scale_by(float* d_x, long long n, const float* d_scale, void* stream) {
+    WN_REQUIRE(d_x && d_scale && n >= 0 && n % 4 == 0, WN_E_BADARG, "wn_scale_by: bad arguments (n must be a multiple of 4)");
+    if (n == 0) return 0;
+    misc::scale_by_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((float4*)d_x, n / 4, d_scale);
     WN_CUDA(cudaGetLastError());
     return 0;
 }

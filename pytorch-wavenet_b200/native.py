@@ -176,6 +176,7 @@ SIGNATURES = {
     "wn_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
     "wn_colsum": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "wn_relu_copy": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p]),
+    "wn_scale_by": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "wn_gen_workspace_bytes": (C.c_int, [C.POINTER(GenShape), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "wn_gen_create": (C.c_int, [C.POINTER(GenShape), C.POINTER(GenWeights), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),

@@ -1169,8 +1169,9 @@ class WaveNetModel(nn.Module):
         """``n_streams`` independent generate_fast runs batched in one kernel (the reference has a single stream,
         wavenet_model.py:179).  first_samples: (n_streams, n_given) ints.  Returns int64 indices
         (n_streams, num_samples) [and the per-step logits].  Run through the same sampler kernel, stream s equals a
-        single-stream run bit for bit (the default picks a latency kernel for one stream and one thread-block cluster per
-        stream otherwise; those differ at rounding level)."""
+        single-stream run bit for bit (256-wide nets run the tensor-core cluster kernel for any number of streams; other
+        nets a latency kernel for one stream and one thread-block cluster per stream otherwise, which differ at rounding
+        level)."""
         self.eval()
         first = np.asarray(first_samples.detach().cpu().numpy() if torch.is_tensor(first_samples) else first_samples)
         first = first.astype(np.int64).reshape(first.shape[0], -1) if first.ndim > 1 else first.astype(np.int64)[None, :]
@@ -1184,11 +1185,14 @@ class WaveNetModel(nn.Module):
 
     def _export_queues(self):
         """Point ``dilated_queues[i].data`` at stream 0 of the sampler's device rings (a (C, max_length) view).
-        Ring elements are 8-byte {value, tag} pairs (see csrc/gen.cu); the view picks the values."""
+        Ring elements are 8-byte {value, tag} pairs (see csrc/gen.cu; plain floats under the grid-barrier kernel); the view
+        picks the values."""
         rt = self._runtime()
         s, evals = rt.last_run["sampler"], rt.last_run["evals"]
         R, NS, off = self.residual_channels, s["n_streams"], 0
-        pairs = s["rings"].view(-1, 2)
+        # the grid-barrier kernel (1) keeps plain floats in the ring memory, every other kernel {value, tag} pairs
+        plain = native.lib().wn_gen_kernel_id(s["handle"]) == 1
+        pairs = s["rings"].view(-1, 1) if plain else s["rings"].view(-1, 2)
         for q in self.dilated_queues:
             n = q.max_length * NS * R
             q.data = pairs[off:off + n, 0].view(q.max_length, NS, R)[:, 0, :].t()

@@ -45,6 +45,16 @@ class _FusedCrossEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (dlogits,) = ctx.saved_tensors
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("fused_cross_entropy: backward called twice (the stored gradient is scaled in place; the "
+                               "network's own autograd node does not support a second backward either)")
+        ctx.consumed = True
+        if ctx.needs_input_grad[0] and grad_out.numel() == 1 and grad_out.dtype == torch.float32 and dlogits.numel() % 4 == 0:
+            # scale in place by the (device) scalar: no pass at all when it is 1, which is what loss.backward() passes
+            with torch.cuda.device(dlogits.device):
+                native.check(native.lib().wn_scale_by(dlogits.data_ptr(), dlogits.numel(), grad_out.contiguous().data_ptr(),
+                                                      torch.cuda.current_stream(dlogits.device).cuda_stream), "scale dlogits")
+            return dlogits, None
         return dlogits * grad_out, None
 
 
