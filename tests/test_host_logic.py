@@ -146,6 +146,32 @@ def test_shape_predicates_and_workspace_sizes_are_host_side():
     assert lib.wn_tc_convert_weights_bf16(None, None, 0, None) < 0
 
 
+def test_sampler_workspace_and_argument_errors_are_host_side():
+    """wn_gen_workspace_bytes needs no device: a 256-wide k = 2 net reserves room for the tensor-core sampler's pre-split
+    weight images (16 blocks x (3 x 32 KB per layer + 2 x 16 KB for the head)), other shapes do not; null handles and
+    pointers are argument errors."""
+    import ctypes
+    import native
+    lib = native.lib()
+
+    def scratch_bytes(width, n_layers, n_streams):
+        dil = (ctypes.c_int * n_layers)(*[2 ** (i % 10) for i in range(n_layers)])
+        shape = native.GenShape(n_layers, 2, width, width, width, width, 256, n_streams, dil)
+        rb, sb = ctypes.c_size_t(), ctypes.c_size_t()
+        assert lib.wn_gen_workspace_bytes(ctypes.byref(shape), ctypes.byref(rb), ctypes.byref(sb)) == 0
+        assert rb.value == 8 * sum(d + 1 for d in dil) * n_streams * width        # {value, tag} pairs, ring_len = d + 1
+        return sb.value
+
+    images = 16 * (50 * 3 * 32768 + 2 * 16384)
+    wide, narrow = scratch_bytes(256, 50, 1), scratch_bytes(128, 50, 1)
+    assert wide - images >= 0 and wide - images < 4 * narrow and narrow < images
+    assert scratch_bytes(256, 50, 64) > wide
+    assert lib.wn_gen_kernel_id(None) == 0
+    assert lib.wn_gen_weights_changed(None) < 0 and b"null handle" in lib.wn_last_error_string()
+    assert lib.wn_gen_set_mode(None, 6) < 0
+    assert lib.wn_scale_by(None, 4, None, None) < 0 and b"bad arguments" in lib.wn_last_error_string()
+
+
 def test_dataset_matches_reference_items(golden):
     """WavenetDataset (reference audio_data.py:12-131): same lengths, same item -> sample-window map (incl. windows that
     cross array boundaries and the train / test split), and the index mode (one_hot=False)
