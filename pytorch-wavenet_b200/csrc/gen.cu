@@ -2443,11 +2443,15 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
         mma_bf16_16816(d.hl, ah, b.y, b.w);
         mma_bf16_16816(d.hh, ah, b.x, b.z);
     };
-    // this warp's four k-steps (4*kq .. 4*kq+3) of its m-tile of a 32 KB layer image against blocks 4*kq.. of vector x
-    auto mma_quarter = [&](const unsigned char* wimg, const unsigned char* x, Acc3& d) {
+    // this warp's four k-steps (4*kq .. 4*kq+3) of its m-tile of the 32 KB layer image of every virtual rank (images VR apart
+    // by CL8_IMG2) against blocks 4*kq.. of vector x.  The virtual ranks' chains are interleaved k-step by k-step: they are
+    // independent, share the B fragments, and hide each other's MMA latency (nothing is stored until all are issued).
+    auto mma_quarter = [&](const unsigned char* wimg, const unsigned char* x, Acc3 (&d)[VR]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            mma_step(wimg + ((size_t)(mt * 16 + 4 * kq + i) * 2) * 512 + lane * 16, x + (4 * kq + i) * BLK, d);
+#pragma unroll
+            for (int vr = 0; vr < VR; ++vr)
+                mma_step(wimg + vr * CL8_IMG2 + ((size_t)(mt * 16 + 4 * kq + i) * 2) * 512 + lane * 16, x + (4 * kq + i) * BLK, d[vr]);
     };
     // sum over the 4 K quarters of output (m-tile m, row r of the tile, stream s): fragment element (lane', j) of each partial
     auto part_sum = [&](const float* pb, int m, int r, int s) {
@@ -2560,20 +2564,16 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
                 const unsigned char* wimg = stage_weights();
                 TR8();         // 1: stage-1 weights (old tap) landed
 #pragma unroll
-                for (int vr = 0; vr < VR; ++vr) {
-                    acc_zero(d[vr]);
-                    mma_quarter(wimg + vr * CL8_IMG2, Xold, d[vr]);
-                }
+                for (int vr = 0; vr < VR; ++vr) acc_zero(d[vr]);
+                mma_quarter(wimg, Xold, d);
                 release_slot();
                 wimg = stage_weights();
                 if (l > 0) xwait(l & 1);
                 TR8();         // 2: old-tap MMAs done, h arrived
-#pragma unroll
-                for (int vr = 0; vr < VR; ++vr) {
-                    mma_quarter(wimg + vr * CL8_IMG2, xc, d[vr]);
-                    acc_store(d[vr], part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
-                }
+                mma_quarter(wimg, xc, d);
                 release_slot();
+#pragma unroll
+                for (int vr = 0; vr < VR; ++vr) acc_store(d[vr], part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
                 TR8();         // 3: MMAs done, partials stored
                 WORKER_SYNC();
                 TR8();         // 4: barrier
@@ -2598,14 +2598,13 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
                 TR8();         // 7: stage-2 weights landed
                 xwait(2 + (l & 1));
                 TR8();         // 8: z arrived
+                Acc3 d[VR];
 #pragma unroll
-                for (int vr = 0; vr < VR; ++vr) {
-                    Acc3 d;
-                    acc_zero(d);
-                    if (active) mma_quarter(wimg + vr * CL8_IMG2, zb, d);
-                    acc_store(d, part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
-                }
+                for (int vr = 0; vr < VR; ++vr) acc_zero(d[vr]);
+                if (active) mma_quarter(wimg, zb, d);
                 release_slot();
+#pragma unroll
+                for (int vr = 0; vr < VR; ++vr) acc_store(d[vr], part_of(pb_i, vr) + ((kq * 2 + mt) * 32 + lane) * 4);
                 TR8();         // 9: MMAs done, partials stored
                 WORKER_SYNC();
                 TR8();         // 10: barrier
@@ -2640,18 +2639,19 @@ __global__ void __launch_bounds__(GEN_NT + 64 + (CS == 8 ? 32 : 0), 1) gen_kerne
         sb_i ^= 1;
         auto head_stage = [&](const unsigned char* x) {     // this warp's 2 k-steps of each virtual rank's m-tile -> part
             const unsigned char* wimg = stage_weights();
+            Acc3 d[VR];
 #pragma unroll
-            for (int vr = 0; vr < VR; ++vr) {
-                Acc3 d;
-                acc_zero(d);
+            for (int vr = 0; vr < VR; ++vr) acc_zero(d[vr]);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int vr = 0; vr < VR; ++vr) {
                     const int ks = 2 * warp + i;
-                    mma_step(wimg + vr * CL8_IMGH + ((size_t)ks * 2) * 512 + lane * 16, x + ks * BLK, d);
+                    mma_step(wimg + vr * CL8_IMGH + ((size_t)ks * 2) * 512 + lane * 16, x + ks * BLK, d[vr]);
                 }
-                acc_store(d, part_of(pb_i, vr) + (warp * 32 + lane) * 4);
-            }
             release_slot();
+#pragma unroll
+            for (int vr = 0; vr < VR; ++vr) acc_store(d[vr], part_of(pb_i, vr) + (warp * 32 + lane) * 4);
         };
         auto head_sum = [&](const float* pb, int r, int s) {  // 8 partials, one per warp
             const float* q = pb + (((r & 7) * 4 + (s >> 1)) << 2) + ((r >> 3) << 1) + (s & 1);
