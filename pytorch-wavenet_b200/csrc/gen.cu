@@ -2107,23 +2107,27 @@ __global__ void __launch_bounds__(GEN_NT + 32, 1) gen_kernel_x2(const GenParams 
 }
 
 // ================================================================================================ batched cluster kernel
-// Several streams per cluster, on tensor cores: one 16-CTA cluster advances CL8_SB = 8 independent streams together, so the
-// weights of a stage are streamed into shared memory ONCE for 8 streams (gen_kernel_cluster streams all 79 MB per stream
-// per step, and only 9 clusters fit on the device, so 64 streams ran as 8 waves).  256-wide nets (R = D = S = E = classes
-// = 256, k = 2).  Per stage, CTA `rank` owns 16 channels of the output vector (all 8 streams):
-//   * the dot products are mma.sync m16n8k16 (M = 16 rows of the stage, N = the 8 streams, K = 16 input channels = the block
-//     one source CTA contributed) with bf16 hi/lo operand pairs -- x = hi + lo exactly up to 2^-17 relative, three MMAs per
-//     product (hi.hi + lo.hi + hi.lo), fp32 accumulation -- the scheme of the training kernels (tc_block.cu).  Weights are
+// Tensor-core sampler for 256-wide nets (R = D = S = E = classes = 256, k = 2), one stream or many: a thread-block cluster
+// advances up to CL8_SB = 8 independent streams together, so the weights of a stage enter shared memory ONCE per 8 streams
+// and step (gen_kernel_cluster streams all 79 MB per stream and step; only 7 of its clusters are co-resident, so 64 streams
+// ran as waves).  Every exchanged vector is 16 blocks of 16 channels x 8 streams; a CTA owns one block (clusters of 16) or
+// two (clusters of 8) and computes those rows of every stage for all 8 streams:
+//   * the dot products are mma.sync m16n8k16 (M = 16 rows of the stage, N = the 8 streams, K = 16 input channels = one
+//     block) with bf16 hi/lo operand pairs -- x = hi + lo up to 2^-17 relative, three MMAs per product (lo.hi, hi.lo, hi.hi
+//     on independent accumulators), fp32 accumulation: the scheme of the training kernels (tc_block.cu).  Weights are
 //     pre-split ONCE per session into fragment-ordered images (cl8_pack_kernel): a warp's A fragments are two conflict-free
-//     LDS.128, and the whole stage image is ONE bulk copy per CTA.  Activations are exchanged already split, in B-fragment
-//     order, so a k-step's B operands are one LDS.128;
-//   * exchange: the 16 x 8 outputs of a CTA are a 512-byte block staged in shared memory and pushed to every CTA of the
-//     cluster with one cp.async.bulk (shared::cta -> shared::cluster) each, completing bytes on an mbarrier of the
-//     destination; consumers sleep on their own mbarrier.  Measured 1 125-1 254 cycles per round, against 2 600-4 100 for
-//     the same payload as per-lane remote stores (tools/dsmem_probe.cu, variants F and E);
+//     LDS.128, a stage's image is one bulk copy.  Activations are exchanged already split, in B-fragment order: a k-step's
+//     B operands are one LDS.128.  8 warps = 2 m-tiles x 4 K quarters; the partials meet in shared memory and 128-256
+//     finishing threads apply bias / tanh.sigmoid / the residual add and stage the CTA's block(s);
+//   * exchange: a pusher warp reads a staged 512-byte block back and issues ONE st.async.v4 per destination CTA, crediting
+//     the bytes to an mbarrier there; consumers sleep on their own mbarrier.  893-1 017 cycles per all-to-all round against
+//     1 125-1 254 with a bulk copy per destination and 2 624-4 144 with per-lane stores (tools/dsmem_probe.cu: H, F, E);
+//   * weights: producer warp(s) keep a 128 KB ring of images full (bulk copies; cp.async for the second block of an 8-CTA
+//     cluster's CTA);
 //   * history: the {value, tag} fp32 ring of the other kernels (same layout: sessions, queue export and kernel switches keep
 //     working), written by the owning CTA, fetched one stage ahead into registers, validated by tag, split on arrival.
-// Streams never mix (N is the stream index of the MMA): a multi-stream run equals the single-stream runs bit for bit.
+// Streams never mix (N is the stream index of the MMA) and both cluster sizes add in the same order: a stream's indices and
+// logits do not depend on how many streams run beside it, bit for bit.
 constexpr int CL8_SB = 8;               // streams per cluster
 constexpr int CL8_W = 256;              // the width this kernel is specialised for
 constexpr int CL8_BLK = 512;            // bytes of one (source CTA) block of an exchanged vector: 8 streams x 16 channels x (hi, lo)
