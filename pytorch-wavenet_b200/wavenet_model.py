@@ -861,7 +861,7 @@ class _Runtime:
         stream = torch.cuda.current_stream(self.device()).cuda_stream
         if reset:
             native.check(lib.wn_gen_reset(s["handle"], stream), "gen reset")
-            mode = getattr(self, "gen_mode", None)            # None: library default (flag-in-data exchange)
+            mode = getattr(self, "gen_mode", None)            # None: library default (wn_gen_set_mode 0: the tensor-core cluster kernel for 256-wide nets)
             if mode is not None:
                 native.check(lib.wn_gen_set_mode(s["handle"], int(mode)), "gen mode")
         args = native.GenRunArgs()
